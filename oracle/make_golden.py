@@ -1,0 +1,240 @@
+"""ORACLE - TEST INFRASTRUCTURE ONLY.  Generates ``tests/golden/*.npz``.
+
+Runs the UNMODIFIED reference (``/root/reference/src``) in this container behind the import
+shims in ``oracle/shims`` and stores its outputs as fixtures.  ``/root/reference`` does not
+exist on the GPU box, so tests read only the committed ``.npz`` files.
+
+    python oracle/make_golden.py            # rewrites tests/golden/
+
+Fixtures (all produced by the reference's own classes through ``GraphCreator`` /
+``directional_edge_features`` / ``haversine_distance`` - nothing from this repository's
+product code is on that path, only ``anemoi_graphs_b200.grids`` for the synthetic inputs):
+
+* ``toy.npz``        2 000 random data points -> TriNodes(2): CutOff 0.6, MultiScale x_hops 1 and 2,
+                     KNN k=3, masked KNN / CutOff, every attribute x norm; full arrays.
+* ``o96_res5.npz``   config 1 (O96 -> TriNodes 5): full edge_index of the three edge sets
+                     (canonical (dst, src) order), hidden nodes, cut-off radius, strided attribute
+                     samples + float64 sums.
+* ``tri_nodes.npz``  TriNodes coordinates + node ordering for resolutions 0-4, multi-scale edges
+                     for resolution 3 with x_hops 1, 2, 3.
+* ``attr_vectors.npz`` SURVEY appendix-B style edge cases for EdgeLength / EdgeDirection.
+"""
+
+from __future__ import annotations
+
+import hashlib
+import pathlib
+import sys
+import warnings
+
+REPO = pathlib.Path(__file__).resolve().parents[1]
+sys.path[:0] = [str(REPO / "oracle" / "shims"), "/root/reference/src", str(REPO)]
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+from anemoi.graphs.create import GraphCreator  # noqa: E402
+from anemoi.graphs.edges.directional import directional_edge_features  # noqa: E402
+from anemoi.graphs.utils import haversine_distance  # noqa: E402
+from anemoi.utils.config import DotDict  # noqa: E402
+
+from anemoi_graphs_b200 import grids  # noqa: E402
+
+OUT = REPO / "tests" / "golden"
+NORMS = [None, "l1", "l2", "unit-max", "unit-range", "unit-std"]
+T = "anemoi.graphs."
+
+
+def canon(ei: np.ndarray) -> np.ndarray:
+    order = np.lexsort((ei[0], ei[1]))
+    return np.ascontiguousarray(ei[:, order])
+
+
+def sha(a: np.ndarray) -> str:
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def attr_cfg(norm="unit-std", rotated=True, invert=False):
+    return {
+        "edge_length": {"_target_": T + "edges.attributes.EdgeLength", "norm": norm, "invert": invert},
+        "edge_dirs": {"_target_": T + "edges.attributes.EdgeDirection", "norm": norm, "luse_rotated_features": rotated},
+    }
+
+
+def build(nodes: dict, edges: list) -> object:
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return GraphCreator(DotDict({"nodes": nodes, "edges": edges})).update_graph(
+            __import__("torch_geometric.data", fromlist=["HeteroData"]).HeteroData()
+        )
+
+
+def latlon_nodes(lat, lon, attributes=None):
+    return {
+        "node_builder": {"_target_": T + "nodes.LatLonNodes", "latitudes": lat, "longitudes": lon},
+        "attributes": attributes or {},
+    }
+
+
+def tri_nodes(res):
+    return {"node_builder": {"_target_": T + "nodes.TriNodes", "resolution": res}, "attributes": {}}
+
+
+def edges(src, dst, builders, attributes=None):
+    return {"source_name": src, "target_name": dst, "edge_builders": builders, "attributes": attributes or {}}
+
+
+def make_toy() -> None:
+    lat, lon = grids.uniform_sphere(2000, seed=7)
+    out: dict[str, np.ndarray] = {"data_lat_deg": lat, "data_lon_deg": lon}
+    nodes = {"data": latlon_nodes(lat, lon), "hidden": tri_nodes(2)}
+    g = build(
+        nodes,
+        [
+            edges("data", "hidden", [{"_target_": T + "edges.CutOffEdges", "cutoff_factor": 0.6}]),
+            edges("hidden", "hidden", [{"_target_": T + "edges.MultiScaleEdges", "x_hops": 1}]),
+            edges("hidden", "data", [{"_target_": T + "edges.KNNEdges", "num_nearest_neighbours": 3}]),
+        ],
+    )
+    out["data_x"] = g["data"].x.numpy()
+    out["hidden_x"] = g["hidden"].x.numpy()
+    out["hidden_node_ordering"] = np.asarray(g["hidden"]["_node_ordering"], dtype=np.int64)
+    out["cutoff_edge_index"] = g[("data", "to", "hidden")].edge_index.numpy()
+    out["multiscale1_edge_index"] = g[("hidden", "to", "hidden")].edge_index.numpy()
+    out["knn3_edge_index"] = g[("hidden", "to", "data")].edge_index.numpy()
+
+    g2 = build(nodes, [edges("hidden", "hidden", [{"_target_": T + "edges.MultiScaleEdges", "x_hops": 2}])])
+    out["multiscale2_edge_index"] = g2[("hidden", "to", "hidden")].edge_index.numpy()
+
+    # several builders on one node pair (concat_edges: sorted unique columns) + self KNN on hidden
+    g3 = build(
+        nodes,
+        [
+            edges(
+                "data",
+                "hidden",
+                [
+                    {"_target_": T + "edges.CutOffEdges", "cutoff_factor": 0.6},
+                    {"_target_": T + "edges.KNNEdges", "num_nearest_neighbours": 5},
+                ],
+            ),
+            edges("hidden", "hidden", [{"_target_": T + "edges.KNNEdges", "num_nearest_neighbours": 4}]),
+        ],
+    )
+    out["cutoff_plus_knn5_edge_index"] = g3[("data", "to", "hidden")].edge_index.numpy()
+    out["cutoff_plus_knn5_edge_type"] = np.array(g3[("data", "to", "hidden")].edge_type)
+    out["hidden_self_knn4_edge_index"] = g3[("hidden", "to", "hidden")].edge_index.numpy()
+
+    # masks: boolean node attributes registered by hand, then masked builders
+    from torch_geometric.data import HeteroData  # shim
+
+    from anemoi.graphs.edges import CutOffEdges, KNNEdges
+
+    g4 = HeteroData()
+    g4["data"].x = g["data"].x
+    g4["hidden"].x = g["hidden"].x
+    rng = np.random.default_rng(11)
+    dmask = torch.from_numpy(rng.random(2000) < 0.5)[:, None]
+    hmask = torch.from_numpy(rng.random(out["hidden_x"].shape[0]) < 0.7)[:, None]
+    g4["data"]["m"] = dmask
+    g4["hidden"]["m"] = hmask
+    out["data_mask"] = dmask.numpy()
+    out["hidden_mask"] = hmask.numpy()
+    KNNEdges("hidden", "data", 3, source_mask_attr_name="m", target_mask_attr_name="m").update_graph(g4)
+    CutOffEdges("data", "hidden", 0.6, source_mask_attr_name="m", target_mask_attr_name="m").update_graph(g4)
+    out["masked_knn3_edge_index"] = g4[("hidden", "to", "data")].edge_index.numpy()
+    out["masked_cutoff_edge_index"] = g4[("data", "to", "hidden")].edge_index.numpy()
+
+    # attributes on the three base edge sets for every norm / mode
+    from anemoi.graphs.edges.attributes import EdgeDirection, EdgeLength
+
+    for tag, key in (("cutoff", ("data", "to", "hidden")), ("ms1", ("hidden", "to", "hidden")), ("knn3", ("hidden", "to", "data"))):
+        for norm in NORMS:
+            n = "none" if norm is None else norm.replace("-", "_")
+            out[f"{tag}_len_{n}"] = EdgeLength(norm=norm).compute(g, key).numpy()
+            out[f"{tag}_dir_rot_{n}"] = EdgeDirection(norm=norm).compute(g, key).numpy()
+        out[f"{tag}_len_inv_unit_max"] = EdgeLength(norm="unit-max", invert=True).compute(g, key).numpy()
+        out[f"{tag}_dir_norot_unit_std"] = EdgeDirection(norm="unit-std", luse_rotated_features=False).compute(g, key).numpy()
+        out[f"{tag}_dir_norot_none"] = EdgeDirection(norm=None, luse_rotated_features=False).compute(g, key).numpy()
+    np.savez_compressed(OUT / "toy.npz", **out)
+    print("toy.npz", {k: v.shape for k, v in out.items() if "edge_index" in k})
+
+
+def make_o96() -> None:
+    lat, lon = grids.octahedral_grid(96)
+    nodes = {"data": latlon_nodes(lat, lon), "hidden": tri_nodes(5)}
+    g = build(
+        nodes,
+        [
+            edges("data", "hidden", [{"_target_": T + "edges.CutOffEdges", "cutoff_factor": 0.6}], attr_cfg()),
+            edges("hidden", "hidden", [{"_target_": T + "edges.MultiScaleEdges", "x_hops": 1}], attr_cfg()),
+            edges("hidden", "data", [{"_target_": T + "edges.KNNEdges", "num_nearest_neighbours": 3}], attr_cfg()),
+        ],
+    )
+    from anemoi.graphs.utils import get_grid_reference_distance
+
+    out: dict[str, np.ndarray] = {}
+    out["data_x_sha256"] = np.array(sha(g["data"].x.numpy()))
+    out["hidden_x"] = g["hidden"].x.numpy()
+    out["hidden_node_ordering"] = np.asarray(g["hidden"]["_node_ordering"], dtype=np.int32)
+    out["reference_distance"] = np.array(get_grid_reference_distance(g["hidden"].x), dtype=np.float64)
+    stride = 37
+    for tag, key in (("cutoff", ("data", "to", "hidden")), ("multiscale", ("hidden", "to", "hidden")), ("knn3", ("hidden", "to", "data"))):
+        ei = g[key].edge_index.numpy()
+        order = np.lexsort((ei[0], ei[1]))
+        out[f"{tag}_edge_index"] = np.ascontiguousarray(ei[:, order])
+        for a in ("edge_length", "edge_dirs"):
+            v = g[key][a].numpy()[order]
+            out[f"{tag}_{a}_sample"] = v[::stride]
+            out[f"{tag}_{a}_sum64"] = np.array(v.astype(np.float64).sum())
+            out[f"{tag}_{a}_abs_sum64"] = np.array(np.abs(v.astype(np.float64)).sum())
+    out["attr_sample_stride"] = np.array(stride)
+    np.savez_compressed(OUT / "o96_res5.npz", **out)
+    print("o96_res5.npz", {k: v.shape for k, v in out.items() if k.endswith("edge_index")})
+
+
+def make_tri() -> None:
+    out: dict[str, np.ndarray] = {}
+    for res in range(5):
+        g = build({"hidden": tri_nodes(res)}, [])
+        out[f"res{res}_x"] = g["hidden"].x.numpy()
+        out[f"res{res}_node_ordering"] = np.asarray(g["hidden"]["_node_ordering"], dtype=np.int32)
+    for hops in (1, 2, 3):
+        g = build({"hidden": tri_nodes(3)}, [edges("hidden", "hidden", [{"_target_": T + "edges.MultiScaleEdges", "x_hops": hops}])])
+        out[f"res3_hops{hops}_edge_index"] = canon(g[("hidden", "to", "hidden")].edge_index.numpy())
+    # a resolution LIST (only levels 1 and 3)
+    g = build(
+        {"hidden": {"node_builder": {"_target_": T + "nodes.TriNodes", "resolution": [1, 3]}, "attributes": {}}},
+        [edges("hidden", "hidden", [{"_target_": T + "edges.MultiScaleEdges", "x_hops": 1}])],
+    )
+    out["res_1_3_hops1_edge_index"] = canon(g[("hidden", "to", "hidden")].edge_index.numpy())
+    np.savez_compressed(OUT / "tri_nodes.npz", **out)
+    print("tri_nodes.npz", {k: v.shape for k, v in out.items()})
+
+
+def make_attr_vectors() -> None:
+    h = np.float32(np.pi / 2)
+    src = np.array(
+        [(0.10, 0.20), (0.5, 6.28), (1.5, 1.0), (-1.5, 2.0), (h, 0.0), (0.1, 1.0), (0.0, 1.0), (0.3, 0.4), (h, 0.0),
+         (0.3, 0.4), (-0.7, 3.0), (1.2, 5.9), (0.0, 0.0), (-h, 1.0)],
+        dtype=np.float32,
+    )  # fmt: skip
+    dst = np.array(
+        [(0.12, 0.25), (0.5, 0.01), (h, 0.0), (-h, 0.0), (1.5, 1.0), (0.2, 1.0), (0.0, 1.1), (0.3, 0.4), (h, 0.0),
+         (-0.3, 0.4 + np.pi), (-0.7001, 3.0001), (1.2001, 0.1), (1e-4, 1e-4), (-1.5, 1.0)],
+        dtype=np.float32,
+    )  # fmt: skip
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        rot = directional_edge_features(src.T.copy(), dst.T.copy(), True).T
+        norot = directional_edge_features(src.T.copy(), dst.T.copy(), False).T
+        length = haversine_distance(src, dst)
+    np.savez_compressed(OUT / "attr_vectors.npz", src=src, dst=dst, dir_rotated=rot, dir_nonrotated=norot, length=length)
+    print("attr_vectors.npz", rot.dtype, length.dtype)
+
+
+if __name__ == "__main__":
+    OUT.mkdir(parents=True, exist_ok=True)
+    make_attr_vectors()
+    make_tri()
+    make_toy()
+    make_o96()

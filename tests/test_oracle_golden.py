@@ -1,0 +1,150 @@
+"""Pins ``oracle/ref_path.py`` (the CPU restatement) to outputs of the UNMODIFIED reference
+(``tests/golden/*.npz``, produced by ``oracle/make_golden.py``) and to the reference's published
+counts.  CPU only."""
+
+import numpy as np
+import pytest
+
+from anemoi_graphs_b200 import grids
+from oracle import ref_path as R
+
+NORMS = [None, "l1", "l2", "unit-max", "unit-range", "unit-std"]
+
+
+def _n(norm):
+    return "none" if norm is None else norm.replace("-", "_")
+
+
+def test_tri_nodes_match_reference(golden):
+    g = golden("tri_nodes")
+    for res in range(5):
+        x, order = R.tri_nodes(res)
+        assert x.dtype == np.float32
+        np.testing.assert_array_equal(order, g[f"res{res}_node_ordering"])
+        np.testing.assert_array_equal(x.view(np.int32), g[f"res{res}_x"].view(np.int32))
+    # reference's own pin: tests/nodes/test_tri_nodes.py:32
+    assert R.tri_nodes(2)[0].shape == (162, 2)
+
+
+@pytest.mark.parametrize("hops", [1, 2, 3])
+def test_multiscale_matches_reference(golden, hops):
+    g = golden("tri_nodes")
+    ei = R.multiscale_edges_tri(range(4), hops, g["res3_node_ordering"])
+    np.testing.assert_array_equal(ei, g[f"res3_hops{hops}_edge_index"])
+
+
+def test_multiscale_resolution_list_and_networkx_variant(golden):
+    g = golden("tri_nodes")
+    ei = R.multiscale_edges_tri([1, 3], 1, g["res3_node_ordering"])
+    np.testing.assert_array_equal(ei, g["res_1_3_hops1_edge_index"])
+    slow = R.multiscale_edges_tri_networkx(range(3), 2, g["res2_node_ordering"], g["res2_x"])
+    fast = R.multiscale_edges_tri(range(3), 2, g["res2_node_ordering"])
+    np.testing.assert_array_equal(R.canonical_sort(slow), fast)
+
+
+def test_multiscale_published_counts():
+    # docs/graphs/edges/tri_refined_edges.csv: multilevel edge counts for levels 0..4
+    expect = [60, 300, 1260, 5100, 20460]
+    for res, e in enumerate(expect):
+        _, order = R.tri_nodes(res)
+        assert R.multiscale_edges_tri(range(res + 1), 1, order).shape[1] == e
+
+
+def test_toy_edges_match_reference(golden):
+    g = golden("toy")
+    dx, hx = g["data_x"], g["hidden_x"]
+    np.testing.assert_array_equal(
+        grids.latlon_deg_to_x(g["data_lat_deg"], g["data_lon_deg"]).numpy().view(np.int32), dx.view(np.int32)
+    )
+    np.testing.assert_array_equal(R.cutoff_edges(dx, hx, 0.6), g["cutoff_edge_index"])
+    np.testing.assert_array_equal(R.knn_edges(hx, dx, 3), g["knn3_edge_index"])
+    np.testing.assert_array_equal(R.knn_edges(hx, hx, 4), g["hidden_self_knn4_edge_index"])
+    ms1 = R.multiscale_edges_tri(range(3), 1, g["hidden_node_ordering"])
+    np.testing.assert_array_equal(ms1, R.canonical_sort(g["multiscale1_edge_index"]))
+    ms2 = R.multiscale_edges_tri(range(3), 2, g["hidden_node_ordering"])
+    np.testing.assert_array_equal(ms2, R.canonical_sort(g["multiscale2_edge_index"]))
+    both = R.concat_edges(R.cutoff_edges(dx, hx, 0.6), R.knn_edges(dx, hx, 5))
+    np.testing.assert_array_equal(both, g["cutoff_plus_knn5_edge_index"])
+    np.testing.assert_array_equal(
+        R.masked_edges("knn", hx, dx, g["hidden_mask"], g["data_mask"], 3), g["masked_knn3_edge_index"]
+    )
+    np.testing.assert_array_equal(
+        R.masked_edges("cutoff", dx, hx, g["data_mask"], g["hidden_mask"], 0.6), g["masked_cutoff_edge_index"]
+    )
+
+
+def test_toy_canonical_knn_has_no_untied_mismatch(golden):
+    g = golden("toy")
+    ei, info = R.knn_edges_canonical(g["hidden_x"], g["data_x"], 3)
+    assert info["untied_mismatch"].size == 0
+    assert info["tied_queries"].size == 0  # random points: no exact ties
+    np.testing.assert_array_equal(ei, R.canonical_sort(g["knn3_edge_index"]))
+
+
+def test_toy_attributes_match_reference(golden):
+    g = golden("toy")
+    dx, hx = g["data_x"], g["hidden_x"]
+    cases = (
+        ("cutoff", dx, hx, g["cutoff_edge_index"]),
+        ("ms1", hx, hx, g["multiscale1_edge_index"]),
+        ("knn3", hx, dx, g["knn3_edge_index"]),
+    )
+    for tag, sx, tx, ei in cases:
+        for norm in NORMS:
+            np.testing.assert_array_equal(R.edge_length(sx, tx, ei, norm), g[f"{tag}_len_{_n(norm)}"])
+            np.testing.assert_array_equal(R.edge_direction(sx, tx, ei, norm), g[f"{tag}_dir_rot_{_n(norm)}"])
+        np.testing.assert_array_equal(R.edge_length(sx, tx, ei, "unit-max", invert=True), g[f"{tag}_len_inv_unit_max"])
+        np.testing.assert_array_equal(
+            R.edge_direction(sx, tx, ei, "unit-std", rotated=False), g[f"{tag}_dir_norot_unit_std"]
+        )
+
+
+def test_attr_vectors(golden):
+    g = golden("attr_vectors")
+    src, dst = g["src"], g["dst"]
+    with np.errstate(all="ignore"):
+        rot = R.edge_directions_raw(src.T.copy(), dst.T.copy(), True).T
+        length = R.haversine_distance(src, dst)
+    np.testing.assert_array_equal(rot, g["dir_rotated"])
+    np.testing.assert_array_equal(length, g["length"])
+    np.testing.assert_array_equal(R.edge_directions_raw(src.T.copy(), dst.T.copy(), False).T, g["dir_nonrotated"])
+    # SURVEY appendix B known answers
+    np.testing.assert_allclose(rot[0], (-0.808158205, -0.588965463), rtol=0, atol=1e-9)
+    np.testing.assert_allclose(length[0], 0.053570323, rtol=1e-7)
+
+
+def test_o96_res5_matches_reference_and_published_counts(golden):
+    g = golden("o96_res5")
+    lat, lon = grids.octahedral_grid(96)
+    dx = grids.latlon_deg_to_x(lat, lon).numpy()
+    assert dx.shape == (40320, 2)
+    hx, order = R.tri_nodes(5)
+    np.testing.assert_array_equal(hx.view(np.int32), g["hidden_x"].view(np.int32))
+    np.testing.assert_array_equal(order, g["hidden_node_ordering"])
+    assert R.grid_reference_distance(hx) == float(g["reference_distance"])
+    cut = R.canonical_sort(R.cutoff_edges(dx, hx, 0.6))
+    knn = R.canonical_sort(R.knn_edges(hx, dx, 3))
+    ms = R.multiscale_edges_tri(range(6), 1, order)
+    # docs/_static/hetero_data_graph.txt:13,19,25
+    assert (cut.shape[1], ms.shape[1], knn.shape[1]) == (62980, 81900, 120960)
+    np.testing.assert_array_equal(cut, g["cutoff_edge_index"])
+    np.testing.assert_array_equal(ms, g["multiscale_edge_index"])
+    np.testing.assert_array_equal(knn, g["knn3_edge_index"])
+    stride = int(g["attr_sample_stride"])
+    for tag, sx, tx, ei in (("cutoff", dx, hx, cut), ("multiscale", hx, hx, ms), ("knn3", hx, dx, knn)):
+        np.testing.assert_array_equal(R.edge_length(sx, tx, ei, "unit-std")[::stride], g[f"{tag}_edge_length_sample"])
+        np.testing.assert_array_equal(R.edge_direction(sx, tx, ei, "unit-std")[::stride], g[f"{tag}_edge_dirs_sample"])
+
+
+def test_o96_res5_tie_enumeration(golden):
+    """88 queries have an exact k/k+1 tie, 46 of them resolved differently by sklearn."""
+    g = golden("o96_res5")
+    lat, lon = grids.octahedral_grid(96)
+    dx = grids.latlon_deg_to_x(lat, lon).numpy()
+    ei, info = R.knn_edges_canonical(g["hidden_x"], dx, 3)
+    assert info["untied_mismatch"].size == 0
+    assert info["tied_queries"].size == 88
+    assert info["differs_from_reference"].size == 46
+    ref = g["knn3_edge_index"]
+    untied = ~np.isin(ref[1], info["tied_queries"])
+    np.testing.assert_array_equal(ei[:, ~np.isin(ei[1], info["tied_queries"])], ref[:, untied])
