@@ -1,0 +1,321 @@
+// K6/K7: icosphere subdivision and multi-scale (x_hops) edges for global TriNodes.
+//
+// K6 replaces trimesh.creation.icosphere as used by the reference
+// (/root/reference/src/anemoi/graphs/generate/tri_icosahedron.py:121,173) - trimesh is a third-party
+// dependency; its published algorithm (icosahedron table, Trimesh.subdivide with midpoints numbered
+// by np.unique over (min | max << 32), refine_spherical after every level) is restated in
+// oracle/trimesh_icosphere.py and re-designed here without any sort: a midpoint's number is
+//     V + (number of edges whose larger endpoint is < u) + (rank of v among u's smaller neighbours)
+// for the edge (v < u), i.e. a per-vertex count, one exclusive scan and a <= 6-entry local sort.
+// All vertex arithmetic uses explicit round-to-nearest float64 intrinsics in numpy's operation order,
+// so vertices are bit-identical to the CPU restatement.
+//
+// K7 replaces tri_icosahedron.add_edges_to_nx_graph + nx.to_scipy_sparse_array
+// (generate/tri_icosahedron.py:138-224, edges/builder.py:412-455): per level a fixed-width adjacency
+// table (degree <= 6), then one thread per graph node runs the <= x_hops frontier expansion on every
+// requested level the vertex exists in, unions the results, relabels through rank_of_vertex and
+// sorts - the output is already in canonical (dst, src) order.  count -> scan -> fill.
+#include <math.h>
+
+#include "agx_common.cuh"
+
+static inline int64_t ico_nv(int level) { return 10 * ((int64_t)1 << (2 * level)) + 2; }
+static inline int64_t ico_nf(int level) { return 20 * ((int64_t)1 << (2 * level)); }
+static inline int64_t ico_face_offset(int level) { return 20 * ((((int64_t)1 << (2 * level)) - 1) / 3); }
+
+// ---------------------------------------------------------------------------------------------
+// subdivision
+// ---------------------------------------------------------------------------------------------
+__global__ void k_ico_lower_neighbours(const int32_t* __restrict__ faces, int64_t nf, int* __restrict__ cnt,
+                                       int32_t* __restrict__ lower) {
+    for (int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; f < nf; f += (int64_t)gridDim.x * blockDim.x) {
+        int v[3] = {faces[3 * f], faces[3 * f + 1], faces[3 * f + 2]};
+#pragma unroll
+        for (int e = 0; e < 3; ++e) {
+            int a = v[e], b = v[(e + 1) % 3];
+            if (a > b) {  // each undirected edge has exactly one half-edge with a > b
+                int slot = atomicAdd(&cnt[a], 1);
+                lower[6 * (int64_t)a + slot] = b;
+            }
+        }
+    }
+}
+
+__global__ void k_ico_sort_lower(const int* __restrict__ cnt, int32_t* __restrict__ lower, int64_t nv) {
+    for (int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; u < nv; u += (int64_t)gridDim.x * blockDim.x) {
+        int m = cnt[u];
+        int32_t* l = lower + 6 * u;
+        for (int i = 1; i < m; ++i) {
+            int x = l[i], j = i - 1;
+            while (j >= 0 && l[j] > x) {
+                l[j + 1] = l[j];
+                --j;
+            }
+            l[j + 1] = x;
+        }
+    }
+}
+
+__global__ void k_ico_midpoints(const int* __restrict__ cnt, const int32_t* __restrict__ lower,
+                                const int64_t* __restrict__ base, int64_t nv, double* __restrict__ vert) {
+    for (int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; u < nv; u += (int64_t)gridDim.x * blockDim.x) {
+        int m = cnt[u];
+        for (int s = 0; s < m; ++s) {
+            int64_t v = lower[6 * u + s];
+            int64_t id = nv + base[u] + s;
+#pragma unroll
+            for (int c = 0; c < 3; ++c)  // vertices[edges[unique]].mean(axis=1): (p_min + p_max) / 2
+                vert[3 * id + c] = __ddiv_rn(__dadd_rn(vert[3 * v + c], vert[3 * u + c]), 2.0);
+        }
+    }
+}
+
+__device__ __forceinline__ int ico_mid(int a, int b, const int* cnt, const int32_t* lower, const int64_t* base, int64_t nv) {
+    int u = max(a, b), v = min(a, b);
+    int m = cnt[u];
+    int pos = 0;
+    for (int s = 0; s < m; ++s)
+        if (lower[6 * (int64_t)u + s] == v) pos = s;
+    return (int)(nv + base[u] + pos);
+}
+
+__global__ void k_ico_faces(const int32_t* __restrict__ faces, int64_t nf, const int* __restrict__ cnt,
+                            const int32_t* __restrict__ lower, const int64_t* __restrict__ base, int64_t nv,
+                            int32_t* __restrict__ out) {
+    for (int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; f < nf; f += (int64_t)gridDim.x * blockDim.x) {
+        int a = faces[3 * f], b = faces[3 * f + 1], c = faces[3 * f + 2];
+        int m0 = ico_mid(a, b, cnt, lower, base, nv), m1 = ico_mid(b, c, cnt, lower, base, nv),
+            m2 = ico_mid(c, a, cnt, lower, base, nv);
+        int32_t* o = out + 12 * f;
+        o[0] = a;  o[1] = m0; o[2] = m2;
+        o[3] = m0; o[4] = b;  o[5] = m1;
+        o[6] = m2; o[7] = m1; o[8] = c;
+        o[9] = m0; o[10] = m1; o[11] = m2;
+    }
+}
+
+// icosphere's refine_spherical: scalar = sqrt(dot(v**2, [1,1,1])); v += (v / scalar) * (radius - scalar)
+__global__ void k_ico_refine(double* __restrict__ vert, int64_t nv) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (int64_t)gridDim.x * blockDim.x) {
+        double x = vert[3 * i], y = vert[3 * i + 1], z = vert[3 * i + 2];
+        double scalar = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z)));
+        double off = __dsub_rn(1.0, scalar);
+        vert[3 * i] = __dadd_rn(x, __dmul_rn(__ddiv_rn(x, scalar), off));
+        vert[3 * i + 1] = __dadd_rn(y, __dmul_rn(__ddiv_rn(y, scalar), off));
+        vert[3 * i + 2] = __dadd_rn(z, __dmul_rn(__ddiv_rn(z, scalar), off));
+    }
+}
+
+// cartesian_to_latlon_rad (generate/transforms.py:50-52): lat = arcsin(z / sum(xyz^2)), lon = arctan2(y, x)
+__global__ void k_ico_latlon(const double* __restrict__ vert, int64_t nv, float2* __restrict__ latlon) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (int64_t)gridDim.x * blockDim.x) {
+        double x = vert[3 * i], y = vert[3 * i + 1], z = vert[3 * i + 2];
+        double n2 = __dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z));
+        latlon[i] = make_float2((float)asin(__ddiv_rn(z, n2)), (float)atan2(y, x));
+    }
+}
+
+extern "C" int agx_icosphere(int max_level, double* vertices, int32_t* faces_all, float* latlon, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    AGX_REQUIRE(max_level >= 0 && max_level <= 12, AGX_ERR_ARG, "agx_icosphere: level %d out of [0, 12]", max_level);
+    AGX_REQUIRE(vertices && faces_all, AGX_ERR_ARG, "agx_icosphere: NULL buffer");
+    // trimesh.creation.icosahedron
+    const double t = (1.0 + sqrt(5.0)) / 2.0;
+    const double s = sqrt(2.0 + t);
+    const double raw[36] = {-1, t, 0, 1, t, 0, -1, -t, 0, 1, -t, 0, 0, -1, t, 0, 1, t,
+                            0, -1, -t, 0, 1, -t, t, 0, -1, t, 0, 1, -t, 0, -1, -t, 0, 1};
+    static const int32_t f0[60] = {0, 11, 5, 0, 5, 1, 0, 1, 7, 0, 7, 10, 0, 10, 11, 1, 5, 9, 5, 11, 4, 11, 10, 2, 10, 7, 6, 7, 1, 8,
+                                   3, 9, 4, 3, 4, 2, 3, 2, 6, 3, 6, 8, 3, 8, 9, 4, 9, 5, 2, 4, 11, 6, 2, 10, 8, 6, 7, 9, 8, 1};
+    double v0[36];
+    for (int i = 0; i < 36; ++i) v0[i] = raw[i] / s;
+    AGX_CUDA_OK(cudaMemcpyAsync(vertices, v0, sizeof(v0), cudaMemcpyHostToDevice, stream));
+    AGX_CUDA_OK(cudaMemcpyAsync(faces_all, f0, sizeof(f0), cudaMemcpyHostToDevice, stream));
+    AGX_CUDA_OK(cudaStreamSynchronize(stream));  // v0 lives on this stack frame
+
+    int64_t nv_max = ico_nv(max_level);
+    int* cnt = nullptr;
+    int32_t* lower = nullptr;
+    int64_t* base = nullptr;
+    if (max_level > 0) {
+        int64_t nv_prev = ico_nv(max_level - 1);
+        AGX_CUDA_OK(cudaMallocAsync(&cnt, nv_prev * sizeof(int), stream));
+        AGX_CUDA_OK(cudaMallocAsync(&lower, 6 * nv_prev * sizeof(int32_t), stream));
+        AGX_CUDA_OK(cudaMallocAsync(&base, (nv_prev + 1) * sizeof(int64_t), stream));
+    }
+    for (int level = 0; level < max_level; ++level) {
+        int64_t nv = ico_nv(level), nf = ico_nf(level);
+        const int32_t* faces = faces_all + 3 * ico_face_offset(level);
+        int32_t* faces_next = faces_all + 3 * ico_face_offset(level + 1);
+        AGX_CUDA_OK(cudaMemsetAsync(cnt, 0, nv * sizeof(int), stream));
+        int gf = agx_grid(nf, 256, 8), gv = agx_grid(nv, 256, 8);
+        k_ico_lower_neighbours<<<gf, 256, 0, stream>>>(faces, nf, cnt, lower);
+        k_ico_sort_lower<<<gv, 256, 0, stream>>>(cnt, lower, nv);
+        int rc = agx_exclusive_scan(cnt, nv, base, nullptr, stream);
+        if (rc) return rc;
+        k_ico_midpoints<<<gv, 256, 0, stream>>>(cnt, lower, base, nv, vertices);
+        k_ico_faces<<<gf, 256, 0, stream>>>(faces, nf, cnt, lower, base, nv, faces_next);
+        k_ico_refine<<<agx_grid(ico_nv(level + 1), 256, 8), 256, 0, stream>>>(vertices, ico_nv(level + 1));
+        agx_note_launch(5);
+    }
+    if (latlon) {
+        k_ico_latlon<<<agx_grid(nv_max, 256, 8), 256, 0, stream>>>(vertices, nv_max, (float2*)latlon);
+        agx_note_launch(1);
+    }
+    AGX_LAUNCH_OK();
+    if (max_level > 0) {
+        AGX_CUDA_OK(cudaFreeAsync(cnt, stream));
+        AGX_CUDA_OK(cudaFreeAsync(lower, stream));
+        AGX_CUDA_OK(cudaFreeAsync(base, stream));
+    }
+    return AGX_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// multi-scale edges
+// ---------------------------------------------------------------------------------------------
+#define MS_MAX_LEVELS 16
+
+struct MsLevels {
+    const int32_t* nb[MS_MAX_LEVELS];   // adjacency table of each requested level: nb[6*v + s]
+    const int* deg[MS_MAX_LEVELS];
+    int64_t nv[MS_MAX_LEVELS];
+    int n;
+};
+
+__global__ void k_ms_adjacency(const int32_t* __restrict__ faces, int64_t nf, int* __restrict__ deg,
+                               int32_t* __restrict__ nb) {
+    for (int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; f < nf; f += (int64_t)gridDim.x * blockDim.x) {
+        int v[3] = {faces[3 * f], faces[3 * f + 1], faces[3 * f + 2]};
+#pragma unroll
+        for (int e = 0; e < 3; ++e) {  // the half-edges of all faces are every directed edge exactly once
+            int a = v[e], b = v[(e + 1) % 3];
+            int slot = atomicAdd(&deg[a], 1);
+            nb[6 * (int64_t)a + slot] = b;
+        }
+    }
+}
+
+// scratch element i of node t lives at scratch[i * n_nodes + t] (coalesced across threads)
+__global__ void __launch_bounds__(128) k_ms_expand(MsLevels lv, int x_hops, int64_t n_nodes, int hop_cap,
+                                                    const int32_t* __restrict__ node_ordering,
+                                                    const int32_t* __restrict__ rank_of_vertex,
+                                                    int32_t* __restrict__ counts, int32_t* __restrict__ scratch) {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_nodes; t += (int64_t)gridDim.x * blockDim.x) {
+        const int u = node_ordering[t];
+        int32_t* uni = scratch + t;                                      // union list (ranks), stride n_nodes
+        int32_t* que = scratch + (int64_t)lv.n * hop_cap * n_nodes + t;  // BFS queue (vertex ids), stride n_nodes
+        int n_uni = 0;
+        for (int l = 0; l < lv.n; ++l) {
+            if (u >= lv.nv[l]) continue;  // vertex does not exist at this level
+            const int32_t* nb = lv.nb[l];
+            const int* deg = lv.deg[l];
+            int n_que = 1, frontier_begin = 0;
+            que[0] = u;
+            for (int hop = 0; hop < x_hops; ++hop) {
+                int frontier_end = n_que;
+                for (int i = frontier_begin; i < frontier_end; ++i) {
+                    int w = que[(int64_t)i * n_nodes];
+                    int d = deg[w];
+                    for (int s = 0; s < d; ++s) {
+                        int x = nb[6 * (int64_t)w + s];
+                        bool seen = false;
+                        for (int j = 0; j < n_que; ++j) seen |= (que[(int64_t)j * n_nodes] == x);
+                        if (!seen) que[(int64_t)(n_que++) * n_nodes] = x;
+                    }
+                }
+                frontier_begin = frontier_end;
+            }
+            for (int i = 1; i < n_que; ++i) {  // i = 0 is the centre (center=False)
+                int r = rank_of_vertex[que[(int64_t)i * n_nodes]];
+                bool seen = false;
+                for (int j = 0; j < n_uni; ++j) seen |= (uni[(int64_t)j * n_nodes] == r);
+                if (!seen) uni[(int64_t)(n_uni++) * n_nodes] = r;
+            }
+        }
+        for (int i = 1; i < n_uni; ++i) {  // ascending source rank
+            int x = uni[(int64_t)i * n_nodes], j = i - 1;
+            while (j >= 0 && uni[(int64_t)j * n_nodes] > x) {
+                uni[(int64_t)(j + 1) * n_nodes] = uni[(int64_t)j * n_nodes];
+                --j;
+            }
+            uni[(int64_t)(j + 1) * n_nodes] = x;
+        }
+        counts[t] = n_uni;
+    }
+}
+
+__global__ void k_ms_fill(int64_t n_nodes, const int32_t* __restrict__ counts, const int64_t* __restrict__ offsets,
+                          const int32_t* __restrict__ scratch, int32_t* __restrict__ out_src,
+                          int32_t* __restrict__ out_dst) {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_nodes; t += (int64_t)gridDim.x * blockDim.x) {
+        int m = counts[t];
+        int64_t o = offsets[t];
+        for (int i = 0; i < m; ++i) {
+            out_src[o + i] = scratch[(int64_t)i * n_nodes + t];
+            out_dst[o + i] = (int32_t)t;
+        }
+    }
+}
+
+static inline int ms_hop_cap(int x_hops) { return 3 * x_hops * (x_hops + 1) + 1; }
+
+extern "C" int64_t agx_multiscale_scratch_per_node(int n_levels, int x_hops) {
+    return (int64_t)(n_levels + 1) * ms_hop_cap(x_hops);
+}
+
+extern "C" int agx_multiscale_tri_count(int max_level, const int32_t* faces_all, const int32_t* levels, int n_levels,
+                                        int x_hops, const int32_t* node_ordering, const int32_t* rank_of_vertex,
+                                        int32_t* counts, int32_t* scratch, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    AGX_REQUIRE(max_level >= 0 && max_level <= 12, AGX_ERR_ARG, "agx_multiscale_tri_count: bad max_level %d", max_level);
+    AGX_REQUIRE(n_levels > 0 && n_levels <= MS_MAX_LEVELS, AGX_ERR_ARG, "agx_multiscale_tri_count: 1..%d levels supported", MS_MAX_LEVELS);
+    AGX_REQUIRE(x_hops > 0, AGX_ERR_ARG, "x_hops == 0, graph would have no edges ...");
+    AGX_REQUIRE(x_hops <= 8, AGX_ERR_UNSUPPORTED, "agx_multiscale_tri_count: x_hops = %d > 8 is not built yet", x_hops);
+    AGX_REQUIRE(faces_all && levels && node_ordering && rank_of_vertex && counts && scratch, AGX_ERR_ARG,
+                "agx_multiscale_tri_count: NULL buffer");
+    int64_t n_nodes = ico_nv(max_level);
+    MsLevels lv;
+    lv.n = n_levels;
+    int* deg_all = nullptr;
+    int32_t* nb_all = nullptr;
+    int64_t tot_v = 0;
+    for (int l = 0; l < n_levels; ++l) {
+        AGX_REQUIRE(levels[l] >= 0 && levels[l] <= max_level, AGX_ERR_ARG, "agx_multiscale_tri_count: level %d out of [0, %d]",
+                    levels[l], max_level);
+        tot_v += ico_nv(levels[l]);
+    }
+    AGX_CUDA_OK(cudaMallocAsync(&deg_all, tot_v * sizeof(int), stream));
+    AGX_CUDA_OK(cudaMallocAsync(&nb_all, 6 * tot_v * sizeof(int32_t), stream));
+    AGX_CUDA_OK(cudaMemsetAsync(deg_all, 0, tot_v * sizeof(int), stream));
+    int64_t off = 0;
+    for (int l = 0; l < n_levels; ++l) {
+        int64_t nv = ico_nv(levels[l]), nf = ico_nf(levels[l]);
+        lv.nb[l] = nb_all + 6 * off;
+        lv.deg[l] = deg_all + off;
+        lv.nv[l] = nv;
+        k_ms_adjacency<<<agx_grid(nf, 256, 8), 256, 0, stream>>>(faces_all + 3 * ico_face_offset(levels[l]), nf,
+                                                                 deg_all + off, nb_all + 6 * off);
+        off += nv;
+    }
+    k_ms_expand<<<agx_grid(n_nodes, 128, 16), 128, 0, stream>>>(lv, x_hops, n_nodes, ms_hop_cap(x_hops), node_ordering,
+                                                                rank_of_vertex, counts, scratch);
+    AGX_LAUNCH_OK();
+    agx_note_launch(n_levels + 1);
+    AGX_CUDA_OK(cudaFreeAsync(deg_all, stream));
+    AGX_CUDA_OK(cudaFreeAsync(nb_all, stream));
+    return AGX_OK;
+}
+
+extern "C" int agx_multiscale_tri_fill(int64_t n_nodes, const int32_t* counts, const int64_t* offsets,
+                                       const int32_t* scratch, int64_t scratch_per_node, int32_t* out_src,
+                                       int32_t* out_dst, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    (void)scratch_per_node;
+    AGX_REQUIRE(n_nodes >= 0, AGX_ERR_ARG, "agx_multiscale_tri_fill: n_nodes < 0");
+    if (n_nodes == 0) return AGX_OK;
+    AGX_REQUIRE(counts && offsets && scratch && out_src && out_dst, AGX_ERR_ARG, "agx_multiscale_tri_fill: NULL buffer");
+    k_ms_fill<<<agx_grid(n_nodes, 256, 8), 256, 0, stream>>>(n_nodes, counts, offsets, scratch, out_src, out_dst);
+    AGX_LAUNCH_OK();
+    agx_note_launch(1);
+    return AGX_OK;
+}

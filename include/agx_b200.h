@@ -1,0 +1,138 @@
+/* agx_b200 - C ABI of the B200-native edge-construction path of anemoi-graphs.
+ *
+ * One shared library (libagx_b200.so, CUDA sm_100a) exports exactly these symbols; the Python
+ * host layer (anemoi_graphs_b200/_cabi.py) binds them with ctypes.  Each entry point names the
+ * reference interface it replaces (paths relative to /root/reference/src/anemoi/graphs/).
+ *
+ * Conventions
+ *  - every pointer marked DEV is a CUDA device pointer owned by the caller; HOST pointers are
+ *    plain host memory.  No torch / C++ types cross the boundary.
+ *  - node coordinates are float32 (lat, lon) pairs in RADIANS, interleaved (n x 2), exactly the
+ *    layout of `graph[name].x` (nodes/builders/base.py:54,84-101).
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  All work is
+ *    enqueued on it; functions that return a value through a HOST pointer synchronise the stream.
+ *  - return value: 0 on success, a negative AGX_ERR_* code otherwise; agx_last_error() gives a
+ *    thread-local message.  Nothing throws; there is no global state besides opaque handles.
+ *  - variable-size outputs use count -> (caller allocates) -> fill.
+ *  - there is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *    AGX_ERR_CUDA.
+ */
+#ifndef AGX_B200_H
+#define AGX_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AGX_ABI_VERSION 1
+
+#define AGX_OK 0
+#define AGX_ERR_CUDA -1      /* CUDA runtime / launch failure (includes "no device") */
+#define AGX_ERR_ARG -2       /* invalid argument */
+#define AGX_ERR_UNSUPPORTED -3 /* valid in the reference, not built yet (message says what) */
+#define AGX_ERR_OVERFLOW -4  /* an internal fixed-capacity buffer was too small */
+
+/* normalisation codes: normalise.py:20-55 */
+#define AGX_NORM_NONE 0
+#define AGX_NORM_L1 1
+#define AGX_NORM_L2 2
+#define AGX_NORM_UNIT_MAX 3
+#define AGX_NORM_UNIT_RANGE 4
+#define AGX_NORM_UNIT_STD 5
+
+typedef struct agx_index agx_index_t;
+
+const char* agx_last_error(void);
+int agx_abi_version(void);
+/* number of kernels this library has launched in the calling process (bench.py "gpu_launches") */
+int64_t agx_launch_count(void);
+
+/* ---- neighbour index -------------------------------------------------------------------------
+ * Replaces `NearestNeighbors(metric="haversine").fit(coords)` (edges/builder.py:259-260,364-365;
+ * utils.py:37-39; generate/masks.py:74): bins the reference points into 6*C*C equi-angular
+ * cube-sphere cells (C = cells_per_face, 0 = choose from n and `hint_k` / `hint_radius`).
+ * `latlon` must stay valid until agx_index_free.                                               */
+int agx_index_build(const float* latlon /*DEV n*2*/, int64_t n, int cells_per_face, int hint_k,
+                    double hint_radius, void* stream, agx_index_t** out);
+int agx_index_free(agx_index_t* index, void* stream);
+int agx_index_info(const agx_index_t* index, int64_t* n, int* cells_per_face);
+
+/* ---- KNN --------------------------------------------------------------------------------------
+ * Replaces `kneighbors_graph(target, n_neighbors=k)` / `kneighbors(...)` (edges/builder.py:261-265,
+ * utils.py:62, generate/masks.py:97).  For query q (0 <= q < nq) writes its k nearest reference
+ * points, ascending (distance, index), to out_src[q*k .. q*k+k); if out_dst != NULL also
+ * out_dst[q*k+j] = dst_base + q (so (out_src, out_dst) are the two rows of edge_index,
+ * edges/builder.py:86-87).  Decisions are float64 haversine `rdist` on the float32 inputs
+ * (sklearn _dist_metrics.pyx.tp:2639-2648); ties within 2^-40 relative go to the lower index.
+ * out_rdist (optional, nq*k) receives the float64 rdist of every neighbour.
+ * stats (optional, DEV int64[4]) += {queries refined in float64, queries with a tie at the k-th
+ * boundary, queries needing a wider search, 0}.                                                 */
+int agx_knn(const agx_index_t* index, const float* q_latlon /*DEV nq*2*/, int64_t nq, int k,
+            int32_t* out_src /*DEV*/, int32_t* out_dst /*DEV or NULL*/, int64_t dst_base,
+            double* out_rdist /*DEV or NULL*/, int64_t* stats /*DEV or NULL*/, void* stream);
+
+/* ---- cut-off (radius) search -------------------------------------------------------------------
+ * Replaces `radius_neighbors_graph(target, radius)` (edges/builder.py:366): every reference point
+ * with rdist <= sin^2(radius/2) (inclusive).  count -> scan -> fill; output grouped by query, in
+ * cell-scan order (deterministic).  `offsets` has nq+1 entries; total = offsets[nq].
+ * stats (optional, DEV int64[4]) += {pairs decided in float64, pairs within 2^-40 relative of the
+ * threshold, 0, 0}.                                                                             */
+int agx_radius_count(const agx_index_t* index, const float* q_latlon /*DEV*/, int64_t nq, double radius,
+                     int32_t* counts /*DEV nq*/, void* stream);
+int agx_exclusive_scan(const int32_t* counts /*DEV n*/, int64_t n, int64_t* offsets /*DEV n+1*/,
+                       int64_t* total /*HOST or NULL; sync if given*/, void* stream);
+int agx_radius_fill(const agx_index_t* index, const float* q_latlon /*DEV*/, int64_t nq, double radius,
+                    const int64_t* offsets /*DEV nq+1*/, int32_t* out_src /*DEV*/, int32_t* out_dst /*DEV*/,
+                    int64_t dst_base, int64_t* stats /*DEV or NULL*/, void* stream);
+
+/* ---- grid reference distance --------------------------------------------------------------------
+ * Replaces `dists[dists > 0].max()` (utils.py:62-63) on the float64 rdist of a k=2 self query
+ * (agx_knn with out_rdist): largest strictly positive value and its flat position.            */
+int agx_max_positive(const double* values /*DEV n*/, int64_t n, double* out_value /*HOST*/,
+                     int64_t* out_index /*HOST*/, void* stream);
+
+/* ---- edge attributes ------------------------------------------------------------------------------
+ * agx_node_tables: per node float32 (x, y, z, cos lat) with numpy's float32 sin/cos bits
+ * (generate/transforms.py:106-110) and, if quat != NULL, the float64 quaternion (x, y, w, pad; z = 0) of
+ * the rotation taking the node to the north pole (edges/directional.py:19-37, ε-nudge of
+ * generate/transforms.py:133-140 included).
+ * agx_edge_attrs: replaces EdgeLength.compute / EdgeDirection.compute (edges/attributes.py:42-157):
+ * raw values -> global normalisation -> float32.  want_len/want_dir select outputs;
+ * dir_rotated = luse_rotated_features.  Two passes when a norm needs global statistics.        */
+int agx_node_tables(const float* latlon /*DEV n*2*/, int64_t n, float* xyzc /*DEV n*4*/,
+                    double* quat /*DEV n*4 or NULL*/, void* stream);
+int agx_edge_attrs(const int32_t* edge_src /*DEV E*/, const int32_t* edge_dst /*DEV E*/, int64_t n_edges,
+                   const float* src_latlon, const float* src_xyzc, const float* dst_latlon,
+                   const float* dst_xyzc, const double* dst_quat /*needed for rotated dirs*/,
+                   int len_norm /*AGX_NORM_* or -1 = skip*/, int len_invert, float* out_len /*DEV E*/,
+                   int dir_norm /*AGX_NORM_* or -1 = skip*/, int dir_rotated, float* out_dir /*DEV E*2*/,
+                   double* workspace /*DEV, >= agx_edge_attrs_workspace() doubles*/, void* stream);
+int64_t agx_edge_attrs_workspace(void);
+
+/* ---- icosphere + multi-scale edges -------------------------------------------------------------------
+ * agx_icosphere: replaces trimesh.creation.icosphere (generate/tri_icosahedron.py:121,173):
+ * float64 vertices (10*4^r+2, 3) and int32 faces (20*4^r, 3) of every level 0..max_level, in
+ * trimesh's numbering (level-r vertices are a prefix of level-(r+1)); also float32 (lat, lon) of
+ * the finest level per generate/transforms.py:34-52.  Buffers sized for the finest level;
+ * `faces_all` holds the levels back to back (level r at offset 20*(4^r-1)/3 faces).
+ * agx_multiscale_tri: replaces tri_icosahedron.add_edges_to_nx_graph + nx.to_scipy_sparse_array
+ * (generate/tri_icosahedron.py:138-224, edges/builder.py:412-455) for global TriNodes: union over the
+ * requested levels of vertex pairs within x_hops mesh hops, relabelled by `rank_of_vertex`
+ * (position in node_ordering), emitted sorted by (dst, src).  count -> fill via `offsets`.      */
+int agx_icosphere(int max_level, double* vertices /*DEV nv*3*/, int32_t* faces_all /*DEV*/,
+                  float* latlon /*DEV nv*2 or NULL*/, void* stream);
+int agx_multiscale_tri_count(int max_level, const int32_t* faces_all /*DEV*/, const int32_t* levels /*HOST*/,
+                             int n_levels, int x_hops, const int32_t* node_ordering /*DEV nv*/,
+                             const int32_t* rank_of_vertex /*DEV nv*/, int32_t* counts /*DEV nv*/,
+                             int32_t* scratch /*DEV nv*agx_multiscale_scratch_per_node()*/, void* stream);
+int64_t agx_multiscale_scratch_per_node(int n_levels, int x_hops);
+int agx_multiscale_tri_fill(int64_t n_nodes, const int32_t* counts, const int64_t* offsets /*DEV nv+1*/,
+                            const int32_t* scratch, int64_t scratch_per_node, int32_t* out_src,
+                            int32_t* out_dst, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AGX_B200_H */
