@@ -42,12 +42,26 @@ SIGNATURES = {
          c_int, c_void_p, c_void_p, c_void_p],
     ),  # fmt: skip
     "agx_edge_attrs_workspace": (c_int64, []),
+    "agx_edge_attrs_stats": (
+        c_int,
+        [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
+         c_void_p, c_void_p],
+    ),  # fmt: skip
+    "agx_edge_attrs_apply": (
+        c_int,
+        [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int,
+         c_int, c_void_p, c_void_p, c_int64, c_void_p, c_void_p],
+    ),  # fmt: skip
     "agx_icosphere": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "agx_multiscale_tri_count": (
         c_int,
         [c_int, c_void_p, POINTER(c_int32), c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     ),
     "agx_multiscale_scratch_per_node": (c_int64, [c_int, c_int]),
+    "agx_multiscale_tri_count_mapped": (
+        c_int,
+        [c_int, c_void_p, POINTER(c_int32), c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    ),
     "agx_multiscale_tri_fill": (c_int, [c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
 }
 

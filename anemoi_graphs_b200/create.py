@@ -1,0 +1,130 @@
+"""Graph creator (/root/reference/src/anemoi/graphs/create.py:26-188).
+
+Same recipe schema, same order of operations (node builders, then for every edge set its builders and ONE
+attribute registration on the merged edge set by the last builder, :83-90), same ``clean`` /
+``post_process`` / ``save`` semantics.  The whole update runs inside one deferred-copy scope: kernels and
+device->host copies are enqueued back to back and awaited once.
+"""
+
+from __future__ import annotations
+
+import logging
+from itertools import chain
+from pathlib import Path
+from warnings import warn
+
+import torch
+
+from . import device as _device
+from .config import DotDict
+from .config import instantiate
+from .graph import HeteroData
+
+LOGGER = logging.getLogger(__name__)
+
+
+class GraphCreator:
+    """Graph creator."""
+
+    config: DotDict
+
+    def __init__(self, config: str | Path | DotDict | dict):
+        if isinstance(config, Path) or isinstance(config, str):
+            self.config = DotDict.from_file(config)
+        elif isinstance(config, DotDict):
+            self.config = config
+        else:  # omegaconf DictConfig / plain mapping
+            self.config = DotDict(_to_container(config))
+
+        # Support previous version. This will be deprecated in a future release
+        edges = []
+        for edges_cfg in self.config.get("edges", []):
+            if "edge_builder" in edges_cfg:
+                warn(
+                    "This format will be deprecated. The key 'edge_builder' is renamed to 'edge_builders' and takes a list of edge builders. In addition, the source_mask_attr_name & target_mask_attr_name fields are moved under the each edge builder.",
+                    DeprecationWarning,
+                    stacklevel=2,
+                )
+
+                edge_builder_cfg = edges_cfg.get("edge_builder")
+                if edge_builder_cfg is not None:
+                    edge_builder_cfg = DotDict(edge_builder_cfg)
+                    edge_builder_cfg.source_mask_attr_name = edges_cfg.get("source_mask_attr_name", None)
+                    edge_builder_cfg.target_mask_attr_name = edges_cfg.get("target_mask_attr_name", None)
+                    edges_cfg["edge_builders"] = [edge_builder_cfg]
+
+            edges.append(edges_cfg)
+        self.config.edges = edges
+
+    def update_graph(self, graph):
+        """Instantiate the node and edge builders of the recipe and apply them to the graph (create.py:62-92)."""
+        with _device.deferred():
+            for nodes_name, nodes_cfg in self.config.get("nodes", {}).items():
+                graph = instantiate(nodes_cfg.node_builder, name=nodes_name).update_graph(
+                    graph, attrs_config=nodes_cfg.get("attributes", {})
+                )
+
+            for edges_cfg in self.config.get("edges", {}):
+                for edge_builder_cfg in edges_cfg.edge_builders:
+                    edge_builder = instantiate(
+                        edge_builder_cfg, source_name=edges_cfg.source_name, target_name=edges_cfg.target_name
+                    )
+                    graph = edge_builder.update_graph(graph, attrs_config=None)
+
+                graph = edge_builder.register_attributes(graph, edges_cfg.get("attributes", {}))
+
+        return graph
+
+    def clean(self, graph):
+        """Remove private attributes used during creation from the graph (create.py:94-114)."""
+        LOGGER.info("Cleaning graph.")
+        for type_name in chain(graph.node_types, graph.edge_types):
+            attr_names_to_remove = [attr_name for attr_name in graph[type_name] if attr_name.startswith("_")]
+            for attr_name in attr_names_to_remove:
+                del graph[type_name][attr_name]
+                LOGGER.info(f"{attr_name} deleted from graph.")
+
+        return graph
+
+    def post_process(self, graph):
+        """Apply the configured post-processors, in order (create.py:116-140)."""
+        for processor in self.config.get("post_processors", []):
+            graph = instantiate(processor).update_graph(graph)
+
+        return graph
+
+    def save(self, graph, save_path: Path, overwrite: bool = False) -> None:
+        """Save the generated graph to the output path (create.py:142-161)."""
+        save_path = Path(save_path)
+
+        if not save_path.exists() or overwrite:
+            save_path.parent.mkdir(parents=True, exist_ok=True)
+            torch.save(graph, save_path)
+            LOGGER.info(f"Graph saved at {save_path}.")
+        else:
+            LOGGER.info("Graph already exists. Use overwrite=True to overwrite.")
+
+    def create(self, save_path: Path | None = None, overwrite: bool = False):
+        """Create the graph and save it to the output path (create.py:163-188)."""
+        graph = HeteroData()
+        graph = self.update_graph(graph)
+        graph = self.clean(graph)
+        graph = self.post_process(graph)
+
+        if save_path is None:
+            LOGGER.warning("No output path specified. The graph will not be saved.")
+        else:
+            self.save(graph, save_path, overwrite)
+
+        return graph
+
+
+def _to_container(config):
+    try:  # pragma: no cover - omegaconf is not in this image
+        from omegaconf import DictConfig, OmegaConf
+
+        if isinstance(config, DictConfig):
+            return OmegaConf.to_container(config, resolve=True)
+    except ImportError:
+        pass
+    return dict(config)

@@ -238,9 +238,9 @@ __global__ void __launch_bounds__(ATTR_THREADS) k_edge_attrs(
     }
 }
 
-// Fold the per-block partials in block order (deterministic) and turn them into normalisation
-// parameters (normalise.py:33-52).  ws[0..1] = length (shift, div); ws[2..5] = direction.
-__global__ void k_attr_finalize(double* __restrict__ ws, int n_blocks, int64_t n_edges, int len_norm, int dir_norm) {
+// Fold the per-block partials in block order (deterministic) into stats[8] =
+// {len sum, sumsq, min, max, dir sum, sumsq, min, max}.
+__global__ void k_attr_fold(const double* __restrict__ ws, int n_blocks, double* __restrict__ stats) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     Stat4 L, D;
     L.init();
@@ -251,20 +251,31 @@ __global__ void k_attr_finalize(double* __restrict__ ws, int n_blocks, int64_t n
         L.merge(l);
         D.merge(d);
     }
+    stats[0] = L.sum; stats[1] = L.sumsq; stats[2] = L.mn; stats[3] = L.mx;
+    stats[4] = D.sum; stats[5] = D.sumsq; stats[6] = D.mn; stats[7] = D.mx;
+}
+
+// Global statistics -> normalisation parameters (normalise.py:33-52).
+// ws[0..1] = length (shift, div); ws[2..5] = direction (shift, 1/div, shift, div).
+__global__ void k_attr_params(double* __restrict__ ws, const double* __restrict__ stats, int64_t n_edges, int len_norm,
+                              int dir_norm) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
     for (int which = 0; which < 2; ++which) {
-        const Stat4& S = which ? D : L;
         int norm = which ? dir_norm : len_norm;
-        double count = (double)n_edges * (which ? 2.0 : 1.0);
         double shift = 0.0, div = 1.0;
-        if (norm == AGX_NORM_L1) div = S.sum;
-        else if (norm == AGX_NORM_L2) div = sqrt(S.sumsq);
-        else if (norm == AGX_NORM_UNIT_MAX) div = S.mx;
-        else if (norm == AGX_NORM_UNIT_RANGE) { shift = S.mn; div = S.mx - S.mn; }
-        else if (norm == AGX_NORM_UNIT_STD) {
-            double mean = S.sum / count;
-            double var = S.sumsq / count - mean * mean;
-            double sd = var > 0.0 ? sqrt(var) : 0.0;
-            div = sd == 0.0 ? 1.0 : sd;  // normalise.py:46-50: skipped when std == 0
+        if (norm > 0) {
+            const double* S = stats + 4 * which;  // sum, sumsq, min, max
+            double count = (double)n_edges * (which ? 2.0 : 1.0);
+            if (norm == AGX_NORM_L1) div = S[0];
+            else if (norm == AGX_NORM_L2) div = sqrt(S[1]);
+            else if (norm == AGX_NORM_UNIT_MAX) div = S[3];
+            else if (norm == AGX_NORM_UNIT_RANGE) { shift = S[2]; div = S[3] - S[2]; }
+            else if (norm == AGX_NORM_UNIT_STD) {
+                double mean = S[0] / count;
+                double var = S[1] / count - mean * mean;
+                double sd = var > 0.0 ? sqrt(var) : 0.0;
+                div = sd == 0.0 ? 1.0 : sd;  // normalise.py:46-50: skipped when std == 0
+            }
         }
         if (which == 0) {
             ws[0] = shift;
@@ -278,38 +289,88 @@ __global__ void k_attr_finalize(double* __restrict__ ws, int n_blocks, int64_t n
     }
 }
 
-extern "C" int agx_edge_attrs(const int32_t* edge_src, const int32_t* edge_dst, int64_t n_edges,
-                              const float* src_latlon, const float* src_xyzc, const float* dst_latlon,
-                              const float* dst_xyzc, const double* dst_quat, int len_norm, int len_invert,
-                              float* out_len, int dir_norm, int dir_rotated, float* out_dir, double* workspace,
-                              void* stream_) {
-    cudaStream_t stream = (cudaStream_t)stream_;
+static int attrs_check(const int32_t* edge_src, const int32_t* edge_dst, int64_t n_edges, const float* src_latlon,
+                       const float* src_xyzc, const float* dst_latlon, const float* dst_xyzc, const double* dst_quat,
+                       int want_dir, int dir_rotated, const double* workspace) {
     AGX_REQUIRE(n_edges >= 0, AGX_ERR_ARG, "agx_edge_attrs: n_edges < 0");
-    int want_len = len_norm >= 0, want_dir = dir_norm >= 0;
-    AGX_REQUIRE(len_norm <= AGX_NORM_UNIT_STD && dir_norm <= AGX_NORM_UNIT_STD, AGX_ERR_ARG, "agx_edge_attrs: unknown norm code");
-    if (n_edges == 0 || (!want_len && !want_dir)) return AGX_OK;
+    if (n_edges == 0) return AGX_OK;
     AGX_REQUIRE(edge_src && edge_dst && src_latlon && src_xyzc && dst_latlon && dst_xyzc && workspace, AGX_ERR_ARG,
                 "agx_edge_attrs: NULL buffer");
-    AGX_REQUIRE(!want_len || out_len, AGX_ERR_ARG, "agx_edge_attrs: out_len is NULL");
-    AGX_REQUIRE(!want_dir || out_dir, AGX_ERR_ARG, "agx_edge_attrs: out_dir is NULL");
     AGX_REQUIRE(!(want_dir && dir_rotated) || dst_quat, AGX_ERR_ARG, "agx_edge_attrs: rotated directions need dst_quat");
+    return AGX_OK;
+}
+
+static inline int attrs_grid(int64_t n_edges) {
     int grid = agx_grid(n_edges, ATTR_THREADS, 8);
-    if (grid > ATTR_MAX_BLOCKS) grid = ATTR_MAX_BLOCKS;
-    bool need_stats = (want_len && len_norm > 0) || (want_dir && dir_norm > 0);
-    if (need_stats) {
+    return grid > ATTR_MAX_BLOCKS ? ATTR_MAX_BLOCKS : grid;
+}
+
+extern "C" int agx_edge_attrs_stats(const int32_t* edge_src, const int32_t* edge_dst, int64_t n_edges,
+                                    const float* src_latlon, const float* src_xyzc, const float* dst_latlon,
+                                    const float* dst_xyzc, const double* dst_quat, int want_len, int want_dir,
+                                    int dir_rotated, double* stats, double* workspace, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    AGX_REQUIRE(stats != nullptr, AGX_ERR_ARG, "agx_edge_attrs_stats: stats is NULL");
+    int rc = attrs_check(edge_src, edge_dst, n_edges, src_latlon, src_xyzc, dst_latlon, dst_xyzc, dst_quat, want_dir,
+                         dir_rotated, workspace);
+    if (rc) return rc;
+    int grid = 0;
+    if (n_edges > 0 && (want_len || want_dir)) {
+        grid = attrs_grid(n_edges);
         k_edge_attrs<true><<<grid, ATTR_THREADS, 0, stream>>>(
             edge_src, edge_dst, n_edges, (const float2*)src_latlon, (const float4*)src_xyzc, (const float2*)dst_latlon,
-            (const float4*)dst_xyzc, (const double2*)dst_quat, want_len && len_norm > 0, len_invert, out_len,
-            want_dir && dir_norm > 0, dir_rotated, out_dir, workspace);
+            (const float4*)dst_xyzc, (const double2*)dst_quat, want_len, 0, nullptr, want_dir, dir_rotated, nullptr,
+            workspace);
         agx_note_launch(1);
     }
-    k_attr_finalize<<<1, 32, 0, stream>>>(workspace, need_stats ? grid : 0, n_edges, want_len ? len_norm : 0,
-                                         want_dir ? dir_norm : 0);
-    k_edge_attrs<false><<<grid, ATTR_THREADS, 0, stream>>>(
+    k_attr_fold<<<1, 32, 0, stream>>>(workspace, grid, stats);  // grid == 0: the empty statistics (a rank with no edges)
+    AGX_LAUNCH_OK();
+    agx_note_launch(1);
+    return AGX_OK;
+}
+
+extern "C" int agx_edge_attrs_apply(const int32_t* edge_src, const int32_t* edge_dst, int64_t n_edges,
+                                    const float* src_latlon, const float* src_xyzc, const float* dst_latlon,
+                                    const float* dst_xyzc, const double* dst_quat, int len_norm, int len_invert,
+                                    float* out_len, int dir_norm, int dir_rotated, float* out_dir, const double* stats,
+                                    int64_t n_edges_global, double* workspace, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int want_len = len_norm >= 0, want_dir = dir_norm >= 0;
+    AGX_REQUIRE(len_norm <= AGX_NORM_UNIT_STD && dir_norm <= AGX_NORM_UNIT_STD, AGX_ERR_ARG, "agx_edge_attrs: unknown norm code");
+    int rc = attrs_check(edge_src, edge_dst, n_edges, src_latlon, src_xyzc, dst_latlon, dst_xyzc, dst_quat, want_dir,
+                         dir_rotated, workspace);
+    if (rc) return rc;
+    if (n_edges == 0 || (!want_len && !want_dir)) return AGX_OK;
+    AGX_REQUIRE(!want_len || out_len, AGX_ERR_ARG, "agx_edge_attrs: out_len is NULL");
+    AGX_REQUIRE(!want_dir || out_dir, AGX_ERR_ARG, "agx_edge_attrs: out_dir is NULL");
+    bool need_stats = (want_len && len_norm > 0) || (want_dir && dir_norm > 0);
+    AGX_REQUIRE(!need_stats || stats, AGX_ERR_ARG, "agx_edge_attrs_apply: this normalisation needs the global statistics");
+    AGX_REQUIRE(n_edges_global >= n_edges, AGX_ERR_ARG, "agx_edge_attrs_apply: n_edges_global < n_edges");
+    k_attr_params<<<1, 32, 0, stream>>>(workspace, stats, n_edges_global, want_len ? len_norm : 0, want_dir ? dir_norm : 0);
+    k_edge_attrs<false><<<attrs_grid(n_edges), ATTR_THREADS, 0, stream>>>(
         edge_src, edge_dst, n_edges, (const float2*)src_latlon, (const float4*)src_xyzc, (const float2*)dst_latlon,
         (const float4*)dst_xyzc, (const double2*)dst_quat, want_len, len_invert, out_len, want_dir, dir_rotated, out_dir,
         workspace);
     AGX_LAUNCH_OK();
     agx_note_launch(2);
     return AGX_OK;
+}
+
+extern "C" int agx_edge_attrs(const int32_t* edge_src, const int32_t* edge_dst, int64_t n_edges,
+                              const float* src_latlon, const float* src_xyzc, const float* dst_latlon,
+                              const float* dst_xyzc, const double* dst_quat, int len_norm, int len_invert,
+                              float* out_len, int dir_norm, int dir_rotated, float* out_dir, double* workspace,
+                              void* stream_) {
+    int want_len = len_norm >= 0, want_dir = dir_norm >= 0;
+    bool need_stats = (want_len && len_norm > 0) || (want_dir && dir_norm > 0);
+    double* stats = workspace ? workspace + 6 : nullptr;  // ws[6..13]: between the parameters and the block partials
+    if (need_stats && n_edges > 0) {
+        int rc = agx_edge_attrs_stats(edge_src, edge_dst, n_edges, src_latlon, src_xyzc, dst_latlon, dst_xyzc, dst_quat,
+                                      want_len && len_norm > 0, want_dir && dir_norm > 0, dir_rotated, stats, workspace,
+                                      stream_);
+        if (rc) return rc;
+    }
+    return agx_edge_attrs_apply(edge_src, edge_dst, n_edges, src_latlon, src_xyzc, dst_latlon, dst_xyzc, dst_quat,
+                                len_norm, len_invert, out_len, dir_norm, dir_rotated, out_dir, stats, n_edges, workspace,
+                                stream_);
 }

@@ -176,9 +176,10 @@ extern "C" int agx_icosphere(int max_level, double* vertices, int32_t* faces_all
 #define MS_MAX_LEVELS 16
 
 struct MsLevels {
-    const int32_t* nb[MS_MAX_LEVELS];   // adjacency table of each requested level: nb[6*v + s]
+    const int32_t* nb[MS_MAX_LEVELS];    // adjacency table of each requested level: nb[6*v + s]
     const int* deg[MS_MAX_LEVELS];
-    int64_t nv[MS_MAX_LEVELS];
+    const int32_t* vmap[MS_MAX_LEVELS];  // level vertex -> graph node position, or -1 (vertex not valid)
+    const int32_t* inv[MS_MAX_LEVELS];   // graph node position -> level vertex, or -1
     int n;
 };
 
@@ -197,18 +198,17 @@ __global__ void k_ms_adjacency(const int32_t* __restrict__ faces, int64_t nf, in
 
 // scratch element i of node t lives at scratch[i * n_nodes + t] (coalesced across threads)
 __global__ void __launch_bounds__(128) k_ms_expand(MsLevels lv, int x_hops, int64_t n_nodes, int hop_cap,
-                                                    const int32_t* __restrict__ node_ordering,
-                                                    const int32_t* __restrict__ rank_of_vertex,
                                                     int32_t* __restrict__ counts, int32_t* __restrict__ scratch) {
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_nodes; t += (int64_t)gridDim.x * blockDim.x) {
-        const int u = node_ordering[t];
-        int32_t* uni = scratch + t;                                      // union list (ranks), stride n_nodes
+        int32_t* uni = scratch + t;                                      // union list (graph positions), stride n_nodes
         int32_t* que = scratch + (int64_t)lv.n * hop_cap * n_nodes + t;  // BFS queue (vertex ids), stride n_nodes
         int n_uni = 0;
         for (int l = 0; l < lv.n; ++l) {
-            if (u >= lv.nv[l]) continue;  // vertex does not exist at this level
+            const int u = lv.inv[l][t];
+            if (u < 0) continue;  // this graph node is not a (valid) vertex of the level
             const int32_t* nb = lv.nb[l];
             const int* deg = lv.deg[l];
+            const int32_t* vmap = lv.vmap[l];
             int n_que = 1, frontier_begin = 0;
             que[0] = u;
             for (int hop = 0; hop < x_hops; ++hop) {
@@ -218,6 +218,7 @@ __global__ void __launch_bounds__(128) k_ms_expand(MsLevels lv, int x_hops, int6
                     int d = deg[w];
                     for (int s = 0; s < d; ++s) {
                         int x = nb[6 * (int64_t)w + s];
+                        if (vmap[x] < 0) continue;  // mesh edges need both endpoints valid (tri_icosahedron.py:214-215)
                         bool seen = false;
                         for (int j = 0; j < n_que; ++j) seen |= (que[(int64_t)j * n_nodes] == x);
                         if (!seen) que[(int64_t)(n_que++) * n_nodes] = x;
@@ -226,13 +227,13 @@ __global__ void __launch_bounds__(128) k_ms_expand(MsLevels lv, int x_hops, int6
                 frontier_begin = frontier_end;
             }
             for (int i = 1; i < n_que; ++i) {  // i = 0 is the centre (center=False)
-                int r = rank_of_vertex[que[(int64_t)i * n_nodes]];
-                bool seen = false;
+                int r = vmap[que[(int64_t)i * n_nodes]];
+                bool seen = (r == (int)t);  // two vertices of one level never share a node; guard self loops anyway
                 for (int j = 0; j < n_uni; ++j) seen |= (uni[(int64_t)j * n_nodes] == r);
                 if (!seen) uni[(int64_t)(n_uni++) * n_nodes] = r;
             }
         }
-        for (int i = 1; i < n_uni; ++i) {  // ascending source rank
+        for (int i = 1; i < n_uni; ++i) {  // ascending source position
             int x = uni[(int64_t)i * n_nodes], j = i - 1;
             while (j >= 0 && uni[(int64_t)j * n_nodes] > x) {
                 uni[(int64_t)(j + 1) * n_nodes] = uni[(int64_t)j * n_nodes];
@@ -257,33 +258,31 @@ __global__ void k_ms_fill(int64_t n_nodes, const int32_t* __restrict__ counts, c
     }
 }
 
+// vmap / inv of one level for GLOBAL TriNodes: vmap[v] = rank_of_vertex[v], inv[t] = node_ordering[t] if it is a
+// vertex of the level (lower levels are prefixes of the finest one).
+__global__ void k_ms_global_maps(const int32_t* __restrict__ node_ordering, int64_t n_nodes, int64_t nv_level,
+                                 int32_t* __restrict__ inv) {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_nodes; t += (int64_t)gridDim.x * blockDim.x) {
+        int u = node_ordering[t];
+        inv[t] = u < nv_level ? u : -1;
+    }
+}
+
 static inline int ms_hop_cap(int x_hops) { return 3 * x_hops * (x_hops + 1) + 1; }
 
 extern "C" int64_t agx_multiscale_scratch_per_node(int n_levels, int x_hops) {
     return (int64_t)(n_levels + 1) * ms_hop_cap(x_hops);
 }
 
-extern "C" int agx_multiscale_tri_count(int max_level, const int32_t* faces_all, const int32_t* levels, int n_levels,
-                                        int x_hops, const int32_t* node_ordering, const int32_t* rank_of_vertex,
-                                        int32_t* counts, int32_t* scratch, void* stream_) {
-    cudaStream_t stream = (cudaStream_t)stream_;
-    AGX_REQUIRE(max_level >= 0 && max_level <= 12, AGX_ERR_ARG, "agx_multiscale_tri_count: bad max_level %d", max_level);
-    AGX_REQUIRE(n_levels > 0 && n_levels <= MS_MAX_LEVELS, AGX_ERR_ARG, "agx_multiscale_tri_count: 1..%d levels supported", MS_MAX_LEVELS);
-    AGX_REQUIRE(x_hops > 0, AGX_ERR_ARG, "x_hops == 0, graph would have no edges ...");
-    AGX_REQUIRE(x_hops <= 8, AGX_ERR_UNSUPPORTED, "agx_multiscale_tri_count: x_hops = %d > 8 is not built yet", x_hops);
-    AGX_REQUIRE(faces_all && levels && node_ordering && rank_of_vertex && counts && scratch, AGX_ERR_ARG,
-                "agx_multiscale_tri_count: NULL buffer");
-    int64_t n_nodes = ico_nv(max_level);
+static int ms_run(int max_level, const int32_t* faces_all, const int32_t* levels, int n_levels, int x_hops,
+                  int64_t n_nodes, const int32_t* const* vmap, const int32_t* const* inv, int32_t* counts,
+                  int32_t* scratch, cudaStream_t stream) {
     MsLevels lv;
     lv.n = n_levels;
     int* deg_all = nullptr;
     int32_t* nb_all = nullptr;
     int64_t tot_v = 0;
-    for (int l = 0; l < n_levels; ++l) {
-        AGX_REQUIRE(levels[l] >= 0 && levels[l] <= max_level, AGX_ERR_ARG, "agx_multiscale_tri_count: level %d out of [0, %d]",
-                    levels[l], max_level);
-        tot_v += ico_nv(levels[l]);
-    }
+    for (int l = 0; l < n_levels; ++l) tot_v += ico_nv(levels[l]);
     AGX_CUDA_OK(cudaMallocAsync(&deg_all, tot_v * sizeof(int), stream));
     AGX_CUDA_OK(cudaMallocAsync(&nb_all, 6 * tot_v * sizeof(int32_t), stream));
     AGX_CUDA_OK(cudaMemsetAsync(deg_all, 0, tot_v * sizeof(int), stream));
@@ -292,18 +291,73 @@ extern "C" int agx_multiscale_tri_count(int max_level, const int32_t* faces_all,
         int64_t nv = ico_nv(levels[l]), nf = ico_nf(levels[l]);
         lv.nb[l] = nb_all + 6 * off;
         lv.deg[l] = deg_all + off;
-        lv.nv[l] = nv;
+        lv.vmap[l] = vmap[l];
+        lv.inv[l] = inv[l];
         k_ms_adjacency<<<agx_grid(nf, 256, 8), 256, 0, stream>>>(faces_all + 3 * ico_face_offset(levels[l]), nf,
                                                                  deg_all + off, nb_all + 6 * off);
         off += nv;
     }
-    k_ms_expand<<<agx_grid(n_nodes, 128, 16), 128, 0, stream>>>(lv, x_hops, n_nodes, ms_hop_cap(x_hops), node_ordering,
-                                                                rank_of_vertex, counts, scratch);
+    (void)max_level;
+    k_ms_expand<<<agx_grid(n_nodes, 128, 16), 128, 0, stream>>>(lv, x_hops, n_nodes, ms_hop_cap(x_hops), counts, scratch);
     AGX_LAUNCH_OK();
     agx_note_launch(n_levels + 1);
     AGX_CUDA_OK(cudaFreeAsync(deg_all, stream));
     AGX_CUDA_OK(cudaFreeAsync(nb_all, stream));
     return AGX_OK;
+}
+
+static int ms_check(const char* who, int max_level, const int32_t* levels, int n_levels, int x_hops) {
+    AGX_REQUIRE(max_level >= 0 && max_level <= 12, AGX_ERR_ARG, "%s: bad max_level %d", who, max_level);
+    AGX_REQUIRE(n_levels > 0 && n_levels <= MS_MAX_LEVELS, AGX_ERR_ARG, "%s: 1..%d levels supported", who, MS_MAX_LEVELS);
+    AGX_REQUIRE(x_hops > 0, AGX_ERR_ARG, "x_hops == 0, graph would have no edges ...");
+    AGX_REQUIRE(x_hops <= 8, AGX_ERR_UNSUPPORTED, "%s: x_hops = %d > 8 is not built yet", who, x_hops);
+    AGX_REQUIRE(levels != nullptr, AGX_ERR_ARG, "%s: levels is NULL", who);
+    for (int l = 0; l < n_levels; ++l)
+        AGX_REQUIRE(levels[l] >= 0 && levels[l] <= max_level, AGX_ERR_ARG, "%s: level %d out of [0, %d]", who, levels[l], max_level);
+    return AGX_OK;
+}
+
+extern "C" int agx_multiscale_tri_count(int max_level, const int32_t* faces_all, const int32_t* levels, int n_levels,
+                                        int x_hops, const int32_t* node_ordering, const int32_t* rank_of_vertex,
+                                        int32_t* counts, int32_t* scratch, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int rc = ms_check("agx_multiscale_tri_count", max_level, levels, n_levels, x_hops);
+    if (rc) return rc;
+    AGX_REQUIRE(faces_all && node_ordering && rank_of_vertex && counts && scratch, AGX_ERR_ARG,
+                "agx_multiscale_tri_count: NULL buffer");
+    int64_t n_nodes = ico_nv(max_level);
+    int32_t* inv_all = nullptr;
+    AGX_CUDA_OK(cudaMallocAsync(&inv_all, (int64_t)n_levels * n_nodes * sizeof(int32_t), stream));
+    const int32_t *vmap[MS_MAX_LEVELS], *inv[MS_MAX_LEVELS];
+    for (int l = 0; l < n_levels; ++l) {
+        vmap[l] = rank_of_vertex;  // every vertex of a global mesh is a graph node
+        inv[l] = inv_all + (int64_t)l * n_nodes;
+        k_ms_global_maps<<<agx_grid(n_nodes, 256, 8), 256, 0, stream>>>(node_ordering, n_nodes, ico_nv(levels[l]),
+                                                                        inv_all + (int64_t)l * n_nodes);
+    }
+    agx_note_launch(n_levels);
+    rc = ms_run(max_level, faces_all, levels, n_levels, x_hops, n_nodes, vmap, inv, counts, scratch, stream);
+    cudaFreeAsync(inv_all, stream);
+    return rc;
+}
+
+extern "C" int agx_multiscale_tri_count_mapped(int max_level, const int32_t* faces_all, const int32_t* levels,
+                                               int n_levels, int x_hops, int64_t n_nodes, const int32_t* vertex_map,
+                                               const int32_t* node_vertex, int32_t* counts, int32_t* scratch,
+                                               void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int rc = ms_check("agx_multiscale_tri_count_mapped", max_level, levels, n_levels, x_hops);
+    if (rc) return rc;
+    AGX_REQUIRE(n_nodes >= 0, AGX_ERR_ARG, "agx_multiscale_tri_count_mapped: n_nodes < 0");
+    if (n_nodes == 0) return AGX_OK;
+    AGX_REQUIRE(faces_all && vertex_map && node_vertex && counts && scratch, AGX_ERR_ARG,
+                "agx_multiscale_tri_count_mapped: NULL buffer");
+    const int32_t *vmap[MS_MAX_LEVELS], *inv[MS_MAX_LEVELS];
+    for (int l = 0; l < n_levels; ++l) {
+        vmap[l] = vertex_map;  // lower levels are prefixes of the finest one: one map serves every level
+        inv[l] = node_vertex + (int64_t)l * n_nodes;
+    }
+    return ms_run(max_level, faces_all, levels, n_levels, x_hops, n_nodes, vmap, inv, counts, scratch, stream);
 }
 
 extern "C" int agx_multiscale_tri_fill(int64_t n_nodes, const int32_t* counts, const int64_t* offsets,

@@ -1,0 +1,244 @@
+"""Device residency, deferred device->host copies and the multi-GPU shard context.
+
+The reference keeps every tensor on the CPU (``graph[name].x``, ``edge_index``, attributes) and the
+builders hand numpy arrays to sklearn.  Here the arithmetic runs on the GPU, so the builders need
+
+* a device copy of the node coordinates and of what is derived from ONE node set (the float32 xyz
+  table, the rotation quaternions) that survives from one builder to the next - kept on the node
+  storage under ``_agx_state`` (private, removed by ``GraphCreator.clean`` like every ``_`` attribute,
+  /root/reference/src/anemoi/graphs/create.py:108-112);
+* the device copy of an ``edge_index`` the builder has just produced, so the attribute kernel does not
+  re-upload it - kept on the edge storage under ``_agx_edge_index``;
+* device->host copies that do not stall the stream: outputs go to pinned host tensors with
+  ``non_blocking=True`` and are awaited once, at the end of the outermost ``deferred()`` scope
+  (``GraphCreator.update_graph`` opens one; a builder used on its own flushes before it returns).
+
+Residency rule: tensors come back where the coordinates live.  A graph whose ``x`` tensors are CUDA
+tensors gets CUDA ``edge_index`` / attributes and nothing crosses PCIe.
+
+Multi-GPU: when ``torch.distributed`` is initialised with more than one rank every rank runs the same
+recipe; query nodes (and, for attributes, edges) are split into contiguous per-rank ranges and the
+per-rank blocks are concatenated in rank order with an all-gather (``all_gather_v``), so every rank
+ends with the complete graph, in the same order as a single-GPU build.
+"""
+
+from __future__ import annotations
+
+import contextlib
+from dataclasses import dataclass, field
+
+import torch
+
+from . import _cabi
+
+_defer_depth = 0
+_pending: list[torch.cuda.Event] = []
+_resident = False
+
+
+def set_resident(flag: bool) -> bool:
+    """Device-resident graphs: node builders place ``x`` on the GPU, so every edge tensor stays there too
+    (nothing crosses PCIe until the caller asks).  Returns the previous setting."""
+    global _resident
+    prev, _resident = _resident, bool(flag)
+    return prev
+
+
+def is_resident() -> bool:
+    return _resident
+
+
+def compute_device(like: torch.Tensor | None = None) -> torch.device:
+    """The CUDA device this process computes on (raises without one: there is no CPU fallback)."""
+    _cabi.require_cuda()
+    if like is not None and like.is_cuda:
+        return like.device
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def to_device(t: torch.Tensor, dtype: torch.dtype | None = None) -> torch.Tensor:
+    dev = compute_device(t)
+    if not t.is_cuda:
+        t = t.to(dev, non_blocking=True)
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    return t.contiguous()
+
+
+@contextlib.contextmanager
+def deferred():
+    """Scope inside which device->host copies are only awaited at exit."""
+    global _defer_depth
+    _defer_depth += 1
+    try:
+        yield
+    finally:
+        _defer_depth -= 1
+        if _defer_depth == 0:
+            flush()
+
+
+def flush() -> None:
+    """Wait for every outstanding device->host copy issued by ``to_host``."""
+    while _pending:
+        _pending.pop().synchronize()
+
+
+def maybe_flush() -> None:
+    if _defer_depth == 0:
+        flush()
+
+
+def to_host(t: torch.Tensor) -> torch.Tensor:
+    """Asynchronous copy of a CUDA tensor into a pinned host tensor (awaited by ``flush``)."""
+    if not t.is_cuda:
+        return t
+    out = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    out.copy_(t, non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record()
+    _pending.append(ev)
+    return out
+
+
+def like_input(result: torch.Tensor, reference_input: torch.Tensor) -> torch.Tensor:
+    """Return ``result`` (CUDA) on the device the caller's input lives on."""
+    return result if reference_input.is_cuda else to_host(result)
+
+
+# --------------------------------------------------------------------------------------------------
+# per-node-set device state
+# --------------------------------------------------------------------------------------------------
+def _key(t: torch.Tensor) -> tuple:
+    return (t.data_ptr(), t._version, tuple(t.shape), str(t.device))
+
+
+@dataclass
+class NodeState:
+    key: tuple
+    x: torch.Tensor  # CUDA float32 (n, 2)
+    tables: object | None = None  # ops.NodeTables
+    extras: dict = field(default_factory=dict)
+
+
+STATE_ATTR = "_agx_state"
+EDGE_ATTR = "_agx_edge_index"
+
+
+def node_state(nodes) -> NodeState:
+    """Device copy of ``nodes.x`` (uploaded once per node set; re-uploaded if ``x`` was replaced or modified)."""
+    flush()  # x may be a pinned tensor one of our own copies is still filling
+    x = nodes["x"]
+    st = nodes.get(STATE_ATTR, None) if hasattr(nodes, "get") else None
+    if isinstance(st, NodeState) and st.key == _key(x):
+        return st
+    st = NodeState(key=_key(x), x=to_device(x, torch.float32))
+    nodes[STATE_ATTR] = st
+    return st
+
+
+def node_tables(nodes, with_rotation: bool):
+    from . import ops
+
+    st = node_state(nodes)
+    if st.tables is None or (with_rotation and st.tables.quat is None):
+        st.tables = ops.NodeTables(st.x, with_rotation=with_rotation)
+    return st.tables
+
+
+def remember_edge_index(store, host_or_dev: torch.Tensor, dev: torch.Tensor) -> None:
+    store[EDGE_ATTR] = (_key(host_or_dev), dev)
+
+
+def device_edge_index(store) -> torch.Tensor:
+    """CUDA int32 (2, E) copy of ``store.edge_index``."""
+    ei = store["edge_index"]
+    if ei.is_cuda:
+        return ei if ei.dtype == torch.int32 and ei.is_contiguous() else ei.to(torch.int32).contiguous()
+    cached = store.get(EDGE_ATTR, None) if hasattr(store, "get") else None
+    if cached is not None and cached[0] == _key(ei):
+        return cached[1]
+    flush()
+    dev = to_device(ei, torch.int32)
+    remember_edge_index(store, ei, dev)
+    return dev
+
+
+# --------------------------------------------------------------------------------------------------
+# multi-GPU shard context
+# --------------------------------------------------------------------------------------------------
+def world() -> tuple[int, int]:
+    """(rank, world_size) of the sharded build; (0, 1) when torch.distributed is not initialised."""
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard_range(n: int, rank: int | None = None, world_size: int | None = None) -> tuple[int, int]:
+    """Contiguous range of ``n`` units owned by ``rank``: ``[rank*n//W, (rank+1)*n//W)``."""
+    if rank is None or world_size is None:
+        rank, world_size = world()
+    return (rank * n) // world_size, ((rank + 1) * n) // world_size
+
+
+def all_gather_counts(count: int, device: torch.device) -> list[int]:
+    import torch.distributed as dist
+
+    _, w = world()
+    mine = torch.tensor([count], dtype=torch.int64, device=device)
+    out = torch.empty(w, dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(out, mine)
+    return [int(v) for v in out.tolist()]
+
+
+def all_gather_v(full: torch.Tensor, counts: list[int], dim: int) -> torch.Tensor:
+    """In-place variable-length all-gather along ``dim``.
+
+    ``full`` is the complete output buffer; this rank has already written its own block (the slice at
+    offset ``sum(counts[:rank])`` of length ``counts[rank]``) - the kernels write straight into it, so
+    there is no staging copy.  NCCL moves every rank's block into every other rank's buffer.
+    """
+    import torch.distributed as dist
+
+    rank, w = world()
+    if w == 1:
+        return full
+    offs = [0]
+    for c in counts:
+        offs.append(offs[-1] + c)
+    if dim == 0 or full.shape[0] == 1:
+        rows = [full]
+    else:  # (R, E) row-major: each row is its own contiguous gather
+        rows = [full[r] for r in range(full.shape[0])]
+        dim = 0
+    backend = dist.get_backend()
+    for row in rows:
+        views = [row.narrow(dim, offs[r], counts[r]) for r in range(w)]
+        if backend == "nccl":
+            # unequal sizes: ProcessGroupNCCL falls back to one grouped ncclBroadcast per rank, still in place
+            dist.all_gather(views, views[rank])
+        else:  # gloo (CPU tests): broadcasts
+            for r in range(w):
+                if counts[r]:
+                    dist.broadcast(views[r], src=r)
+    return full
+
+
+def all_gather_stats(stats: torch.Tensor) -> torch.Tensor:
+    """Combine per-rank attribute statistics {sum, sumsq, min, max} x {len, dir} in rank order."""
+    import torch.distributed as dist
+
+    _, w = world()
+    if w == 1:
+        return stats
+    allst = torch.empty((w, 8), dtype=stats.dtype, device=stats.device)
+    dist.all_gather_into_tensor(allst, stats.reshape(1, 8))
+    out = torch.empty_like(stats)
+    for base in (0, 4):
+        out[base] = allst[:, base].sum()
+        out[base + 1] = allst[:, base + 1].sum()
+        out[base + 2] = allst[:, base + 2].min()
+        out[base + 3] = allst[:, base + 3].max()
+    return out

@@ -1,0 +1,144 @@
+"""Edge attributes (/root/reference/src/anemoi/graphs/edges/attributes.py:24-157).
+
+``EdgeLength`` and ``EdgeDirection`` keep the reference's constructor arguments and ``compute(graph,
+edges_name)`` contract (float32 ``(E, 1)`` / ``(E, 2)`` tensors, normalised over the whole edge set).
+Raw values, the global reduction for the normalisation and the final float32 cast are one fused CUDA
+kernel pair (``ops.edge_attributes``); when both attributes are requested for an edge set
+(``compute_attributes``) they share a single pass over ``edge_index``.
+"""
+
+from __future__ import annotations
+
+from abc import ABC
+
+import torch
+
+from .. import device as _device
+from .. import ops
+from .._cabi import NORM_CODES
+
+
+def _check_norm(norm) -> None:
+    if norm not in NORM_CODES:
+        # normalise.py:53-55
+        raise ValueError(
+            f"Attribute normalisation \"{norm}\" is not valid. Options are: 'l1', 'l2', 'unit-max' or 'unit-std'."
+        )
+
+
+class BaseEdgeAttribute(ABC):
+    """Base class for edge attributes."""
+
+    def __init__(self, norm: str | None = None) -> None:
+        self.norm = norm
+
+    def _kernel_args(self) -> dict:
+        raise NotImplementedError
+
+    def _pick(self, length, direction) -> torch.Tensor:
+        raise NotImplementedError
+
+    def compute(self, graph, edges_name: tuple[str, str, str], *args, **kwargs) -> torch.Tensor:
+        """Compute the edge attributes."""
+        out = compute_attributes(graph, edges_name, {"value": self})["value"]
+        _device.maybe_flush()
+        return out
+
+
+class EdgeDirection(BaseEdgeAttribute):
+    """Edge direction feature (edges/attributes.py:56-104).
+
+    1. Rotated features: the target nodes are rotated to the north pole to compute the edge direction.
+    2. Non-rotated features: difference in latitude and longitude between the source and target nodes.
+
+    Attributes
+    ----------
+    norm : Optional[str]
+        Normalisation method. Options: None, "l1", "l2", "unit-max", "unit-range", "unit-std".
+    luse_rotated_features : bool
+        Whether to use rotated features.
+    """
+
+    def __init__(self, norm: str | None = None, luse_rotated_features: bool = True) -> None:
+        super().__init__(norm)
+        self.luse_rotated_features = luse_rotated_features
+
+    def _kernel_args(self) -> dict:
+        return dict(direction=True, direction_norm=self.norm, direction_rotated=bool(self.luse_rotated_features))
+
+    def _pick(self, length, direction):
+        return direction
+
+
+class EdgeLength(BaseEdgeAttribute):
+    """Edge length feature: haversine distance on the unit sphere (edges/attributes.py:107-157).
+
+    Attributes
+    ----------
+    norm : Optional[str]
+        Normalisation method. Options: None, "l1", "l2", "unit-max", "unit-range", "unit-std".
+    invert : bool
+        Whether to invert the edge lengths, i.e. 1 - edge_length. Defaults to False.
+    """
+
+    def __init__(self, norm: str | None = None, invert: bool = False) -> None:
+        super().__init__(norm)
+        self.invert = invert
+
+    def _kernel_args(self) -> dict:
+        return dict(length=True, length_norm=self.norm, length_invert=bool(self.invert))
+
+    def _pick(self, length, direction):
+        return length
+
+
+def _check_nodes(graph, edges_name) -> tuple[str, str]:
+    source_name, _, target_name = edges_name
+    assert (
+        source_name in graph.node_types
+    ), f"Node \"{source_name}\" not found in graph. Optional nodes are {', '.join(graph.node_types)}."
+    assert (
+        target_name in graph.node_types
+    ), f"Node \"{target_name}\" not found in graph. Optional nodes are {', '.join(graph.node_types)}."
+    return source_name, target_name
+
+
+def compute_attributes(graph, edges_name: tuple[str, str, str], attrs: dict) -> dict:
+    """Evaluate a set of attribute objects on one edge set.
+
+    Pairs one ``EdgeLength`` with one ``EdgeDirection`` per kernel pass; foreign attribute objects (anything
+    with a ``compute(graph, edges_name)`` method) are called as the reference would call them
+    (edges/builder.py:133)."""
+    ours = {k: a for k, a in attrs.items() if isinstance(a, (EdgeLength, EdgeDirection))}
+    out: dict = {}
+    for k, a in attrs.items():
+        if k not in ours:
+            out[k] = a.compute(graph, edges_name)
+    if not ours:
+        return out
+    source_name, target_name = _check_nodes(graph, edges_name)
+    for a in ours.values():
+        _check_norm(a.norm)
+    store = graph[tuple(edges_name)]
+    edge_index = _device.device_edge_index(store)
+    host_side = not store["edge_index"].is_cuda
+    want_rot = any(isinstance(a, EdgeDirection) and a.luse_rotated_features for a in ours.values())
+    src = _device.node_tables(graph[source_name], with_rotation=False)
+    dst = _device.node_tables(graph[target_name], with_rotation=want_rot)
+    lengths = [(k, a) for k, a in ours.items() if isinstance(a, EdgeLength)]
+    dirs = [(k, a) for k, a in ours.items() if isinstance(a, EdgeDirection)]
+    _, w = _device.world()
+    while lengths or dirs:
+        kl = lengths.pop(0) if lengths else None
+        kd = dirs.pop(0) if dirs else None
+        args = dict(length=False, direction=False, sharded=w > 1)
+        if kl:
+            args.update(kl[1]._kernel_args())
+        if kd:
+            args.update(kd[1]._kernel_args())
+        ln, dr = ops.edge_attributes(edge_index, src, dst, **args)
+        if kl:
+            out[kl[0]] = _device.to_host(ln) if host_side else ln
+        if kd:
+            out[kd[0]] = _device.to_host(dr) if host_side else dr
+    return {k: out[k] for k in attrs}  # the recipe's order

@@ -1,0 +1,113 @@
+"""Triangular refined-icosahedron nodes and multi-scale edges
+(/root/reference/src/anemoi/graphs/generate/tri_icosahedron.py).
+
+Vertices and faces of every refinement level come from the device subdivision kernels
+(``ops.Icosphere``, which restates ``trimesh.creation.icosphere``); the multi-scale edges from the CSR
+frontier-expansion kernels.  No networkx graph is built: where the reference threads an ``nx.DiGraph``
+through the hidden node attribute ``_nx_graph``, this package keeps the device mesh there.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .. import device as _device
+from .. import ops
+from .utils import get_coordinates_ordering
+
+
+class DeviceMesh:
+    """What the hidden ``_nx_graph`` attribute holds here: the icosphere of a node set on the device."""
+
+    def __init__(self, icosphere: ops.Icosphere, node_ordering: np.ndarray) -> None:
+        self.icosphere = icosphere
+        self.node_ordering = node_ordering
+
+    def number_of_nodes(self) -> int:
+        return int(len(self.node_ordering))
+
+    def __getstate__(self):  # never pickled with device memory (``clean`` removes it anyway)
+        return {"icosphere": None, "node_ordering": self.node_ordering}
+
+
+_ICO_CACHE: dict = {}
+
+
+def get_icosphere(resolution: int) -> ops.Icosphere:
+    """Device icosphere of ``resolution`` (all levels 0..resolution)."""
+    return ops.Icosphere(int(resolution))
+
+
+def get_latlon_coords_icosphere(resolution: int) -> np.ndarray:
+    """float32 (lat, lon) radians of the icosphere vertices (tri_icosahedron.py:108-123)."""
+    return get_icosphere(resolution).latlon.cpu().numpy()
+
+
+def create_tri_nodes(resolution: int, area_mask_builder=None):
+    """Global (or area-limited) mesh nodes from a refined icosahedron (tri_icosahedron.py:24-58).
+
+    Returns ``(mesh, coords_rad, node_ordering)``: the device mesh, the float32 vertex coordinates (not
+    ordered) and the order that sorts them by latitude and longitude."""
+    ico = get_icosphere(resolution)
+    coords_rad = ico.latlon.cpu().numpy()
+    node_ordering = get_coordinates_ordering(coords_rad)
+
+    if area_mask_builder is not None:
+        area_mask = area_mask_builder.get_mask_device(ico.latlon).cpu().numpy()
+        node_ordering = node_ordering[area_mask[node_ordering]]
+
+    return DeviceMesh(ico, node_ordering), coords_rad, node_ordering
+
+
+def create_stretched_tri_nodes(base_resolution: int, lam_resolution: int, area_mask_builder=None):
+    """Global mesh with two resolution levels (tri_icosahedron.py:61-105): ``base_resolution`` outside the
+    area of interest, ``lam_resolution`` inside."""
+    assert area_mask_builder is not None, "AOI mask builder must be provided to build refined grid."
+    ico = get_icosphere(max(base_resolution, lam_resolution))
+    lam = ico if lam_resolution == ico.max_level else get_icosphere(lam_resolution)
+    n_base = ops.ico_num_vertices(base_resolution)
+    # lower levels are prefixes of the finest one; if base > lam (unusual) generate it separately
+    base_latlon = ico.latlon[:n_base] if base_resolution <= ico.max_level else get_icosphere(base_resolution).latlon
+    base_area_mask = ~area_mask_builder.get_mask_device(base_latlon)
+    lam_latlon = lam.latlon[: ops.ico_num_vertices(lam_resolution)]
+    lam_area_mask = area_mask_builder.get_mask_device(lam_latlon)
+
+    coords_rad = torch.cat([base_latlon[base_area_mask], lam_latlon[lam_area_mask]]).cpu().numpy()
+    node_ordering = get_coordinates_ordering(coords_rad)
+    return DeviceMesh(lam, node_ordering), coords_rad, node_ordering
+
+
+def multiscale_edges(nodes, resolutions, x_hops: int = 1, area_mask_builder=None) -> torch.Tensor:
+    """Multi-scale connections of a tri-node set: CUDA int32 (2, E) sorted by (target, source).
+
+    Replaces ``add_edges_to_nx_graph`` + ``nx.to_scipy_sparse_array`` (tri_icosahedron.py:138-224,
+    edges/builder.py:412-455): for every level ``r`` in ``resolutions`` the directed pairs (u -> v), u != v,
+    within ``x_hops`` hops on the level-r mesh restricted to valid vertices; level vertices are identified with
+    graph nodes by nearest neighbour (tri_icosahedron.py:185)."""
+    assert x_hops > 0, "x_hops == 0, graph would have no edges ..."
+    resolutions = [int(r) for r in resolutions]
+    mesh = nodes.get("_nx_graph", None)
+    ico = mesh.icosphere if isinstance(mesh, DeviceMesh) and mesh.icosphere is not None else None
+    if ico is None or ico.max_level < max(resolutions):
+        ico = get_icosphere(max(resolutions))
+    st = _device.node_state(nodes)
+    n_nodes = int(st.x.shape[0])
+    node_type = nodes["node_type"]
+    if node_type == "TriNodes" and area_mask_builder is None and n_nodes == ops.ico_num_vertices(ico.max_level):
+        order = torch.as_tensor(np.asarray(nodes["_node_ordering"]), dtype=torch.int32)
+        return ops.multiscale_tri_edges(ico, resolutions, x_hops, order)
+    # limited-area / stretched: valid vertices by the area mask, vertex -> node by 1-NN
+    nv = ops.ico_num_vertices(max(resolutions))
+    coords = ico.latlon[:nv]
+    with ops.NeighbourIndex(st.x, hint_k=1) as index:
+        nearest = index.knn(coords, 1)[0]
+    if area_mask_builder is not None:
+        valid = area_mask_builder.get_mask_device(coords)
+        vertex_map = torch.where(valid, nearest, torch.full_like(nearest, -1))
+    else:
+        vertex_map = nearest
+    if ico.max_level > max(resolutions):
+        pad = torch.full((ops.ico_num_vertices(ico.max_level) - nv,), -1, dtype=torch.int32, device=vertex_map.device)
+        vertex_map = torch.cat([vertex_map, pad])
+    return ops.multiscale_tri_edges_mapped(ico, resolutions, x_hops, n_nodes, vertex_map)

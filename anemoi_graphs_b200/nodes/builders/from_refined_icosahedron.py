@@ -1,0 +1,142 @@
+"""Nodes from iterative refinements of an icosahedron
+(/root/reference/src/anemoi/graphs/nodes/builders/from_refined_icosahedron.py:30-191).
+
+Same class names, constructor arguments and hidden attributes (``_resolutions``, ``_nx_graph``,
+``_node_ordering``, ``_area_mask_builder``) as the reference; ``_nx_graph`` holds the device mesh
+(``generate.tri_icosahedron.DeviceMesh``) instead of a networkx graph.
+"""
+
+from __future__ import annotations
+
+import logging
+from abc import ABC
+from abc import abstractmethod
+
+import numpy as np
+import torch
+
+from ...generate.masks import KNNAreaMaskBuilder
+from ...generate.tri_icosahedron import create_stretched_tri_nodes
+from ...generate.tri_icosahedron import create_tri_nodes
+from .base import BaseNodeBuilder
+
+LOGGER = logging.getLogger(__name__)
+
+_H3_MESSAGE = (
+    "hexagonal (H3) nodes are not built: the reference takes cell ids, centres and neighbourhoods from the h3 C "
+    "library (generate/hex_icosahedron.py:47,79,99,147), which is neither under /root/reference nor installed "
+    "here, so a restatement could not be checked against anything (DESIGN.md, out of scope)."
+)
+
+
+class IcosahedralNodes(BaseNodeBuilder, ABC):
+    """Nodes based on iterative refinements of an icosahedron.
+
+    Attributes
+    ----------
+    resolution : list[int] | int
+        Refinement level of the mesh.
+    """
+
+    def __init__(self, resolution: int | list[int], name: str) -> None:
+        if isinstance(resolution, int):
+            self.resolutions = list(range(resolution + 1))
+        else:
+            self.resolutions = resolution
+
+        super().__init__(name)
+        self.hidden_attributes = BaseNodeBuilder.hidden_attributes | {
+            "resolutions",
+            "nx_graph",
+            "node_ordering",
+            "area_mask_builder",
+        }
+
+    def get_coordinates(self) -> torch.Tensor:
+        """float32 (num_nodes, 2) coordinates in radians, in graph order."""
+        self.nx_graph, coords_rad, self.node_ordering = self.create_nodes()
+        return torch.tensor(coords_rad[self.node_ordering], dtype=torch.float32)
+
+    @abstractmethod
+    def create_nodes(self) -> tuple[object, np.ndarray, np.ndarray]: ...
+
+
+class LimitedAreaIcosahedralNodes(IcosahedralNodes):
+    """Icosahedral nodes restricted to an area of interest."""
+
+    def __init__(
+        self,
+        resolution: int | list[int],
+        reference_node_name: str,
+        name: str,
+        mask_attr_name: str | None = None,
+        margin_radius_km: float = 100.0,
+    ) -> None:
+        super().__init__(resolution, name)
+
+        self.area_mask_builder = KNNAreaMaskBuilder(reference_node_name, margin_radius_km, mask_attr_name)
+
+    def register_nodes(self, graph):
+        self.area_mask_builder.fit(graph)
+        return super().register_nodes(graph)
+
+
+class TriNodes(IcosahedralNodes):
+    """Nodes based on iterative refinements of an icosahedron (triangular mesh)."""
+
+    def create_nodes(self):
+        return create_tri_nodes(resolution=max(self.resolutions))
+
+
+class HexNodes(IcosahedralNodes):
+    """Nodes based on H3 hexagonal refinements - not built (no h3, no oracle)."""
+
+    def create_nodes(self):
+        raise NotImplementedError(_H3_MESSAGE)
+
+
+class LimitedAreaTriNodes(LimitedAreaIcosahedralNodes):
+    """Triangular-mesh nodes within an area of interest."""
+
+    def create_nodes(self):
+        return create_tri_nodes(resolution=max(self.resolutions), area_mask_builder=self.area_mask_builder)
+
+
+class LimitedAreaHexNodes(LimitedAreaIcosahedralNodes):
+    """H3 nodes within an area of interest - not built (no h3, no oracle)."""
+
+    def create_nodes(self):
+        raise NotImplementedError(_H3_MESSAGE)
+
+
+class StretchedIcosahedronNodes(IcosahedralNodes):
+    """Icosahedral nodes with 2 different resolutions."""
+
+    def __init__(
+        self,
+        global_resolution: int,
+        lam_resolution: int,
+        name: str,
+        reference_node_name: str,
+        mask_attr_name: str,
+        margin_radius_km: float = 100.0,
+    ) -> None:
+        super().__init__(lam_resolution, name)
+        self.global_resolution = global_resolution
+
+        self.area_mask_builder = KNNAreaMaskBuilder(reference_node_name, margin_radius_km, mask_attr_name)
+
+    def register_nodes(self, graph):
+        self.area_mask_builder.fit(graph)
+        return super().register_nodes(graph)
+
+
+class StretchedTriNodes(StretchedIcosahedronNodes):
+    """Triangular-mesh nodes with 2 different resolutions."""
+
+    def create_nodes(self):
+        return create_stretched_tri_nodes(
+            base_resolution=self.global_resolution,
+            lam_resolution=max(self.resolutions),
+            area_mask_builder=self.area_mask_builder,
+        )

@@ -17,6 +17,46 @@ from . import _cabi
 from ._cabi import NORM_CODES, check, current_stream, load_library, ptr
 
 
+class Timeline:
+    """CUDA-event stopwatch around the C-ABI calls (``bench.py`` switches it on to time each kernel live,
+    on the stream the kernel is launched on).  ``spans[name]`` collects (start, end) event pairs."""
+
+    def __init__(self) -> None:
+        self.spans: dict[str, list] = {}
+        self.units: dict[str, float] = {}
+
+    def record(self, name: str, start, end, units: float = 0.0) -> None:
+        self.spans.setdefault(name, []).append((start, end))
+        self.units[name] = self.units.get(name, 0.0) + units
+
+    def totals_ms(self) -> dict[str, float]:
+        torch.cuda.synchronize()
+        return {k: sum(a.elapsed_time(b) for a, b in v) for k, v in self.spans.items()}
+
+    def counts(self) -> dict[str, int]:
+        return {k: len(v) for k, v in self.spans.items()}
+
+
+timeline: Timeline | None = None
+
+
+class _span:
+    def __init__(self, name: str, units: float = 0.0) -> None:
+        self.name, self.units = name, units
+
+    def __enter__(self):
+        if timeline is not None:
+            self.start = torch.cuda.Event(enable_timing=True)
+            self.start.record()
+        return self
+
+    def __exit__(self, *exc):
+        if timeline is not None:
+            end = torch.cuda.Event(enable_timing=True)
+            end.record()
+            timeline.record(self.name, self.start, end, self.units)
+
+
 def _dev_x(x: torch.Tensor) -> torch.Tensor:
     """float32 (n, 2) contiguous CUDA coordinates."""
     _cabi.require_cuda()
@@ -37,11 +77,13 @@ class NeighbourIndex:
         self.x = _dev_x(x)  # kept alive: the index reads it during float64 refinement
         self.n = int(self.x.shape[0])
         handle = c_void_p()
-        check(
-            self.lib.agx_index_build(
-                ptr(self.x), self.n, int(cells_per_face), int(hint_k), float(hint_radius), current_stream(), byref(handle)
-            )
-        )
+        with _span("index_build", self.n):
+            check(
+                self.lib.agx_index_build(
+                    ptr(self.x), self.n, int(cells_per_face), int(hint_k), float(hint_radius), current_stream(),
+                    byref(handle),
+                )
+            )  # fmt: skip
         self.handle = handle
 
     @property
@@ -76,42 +118,68 @@ class NeighbourIndex:
         return_rdist: bool = False,
         stats: torch.Tensor | None = None,
         out: torch.Tensor | None = None,
+        out_offset: int = 0,
     ):
         """``edge_index`` (2, nq*k) int32 - row 0 the k nearest reference points of each query, row 1
-        ``dst_base + query`` - and optionally the float64 ``rdist`` (nq, k)."""
+        ``dst_base + query`` - and optionally the float64 ``rdist`` (nq, k).  With ``out`` (a larger
+        contiguous (2, E) int32 buffer) the block is written at column ``out_offset`` instead."""
         q = _dev_x(q)
         nq = int(q.shape[0])
         if out is None:
             out = torch.empty((2, nq * k), dtype=torch.int32, device=q.device)
-        assert out.shape == (2, nq * k) and out.dtype == torch.int32 and out.is_contiguous()
+            out_offset = 0
+        assert out.dim() == 2 and out.shape[0] == 2 and out.dtype == torch.int32 and out.is_contiguous()
+        assert 0 <= out_offset and out_offset + nq * k <= out.shape[1]
         rdist = torch.empty((nq, k), dtype=torch.float64, device=q.device) if return_rdist else None
-        check(
-            self.lib.agx_knn(
-                self.handle, ptr(q), nq, int(k), out[0].data_ptr(), out[1].data_ptr(), int(dst_base), ptr(rdist),
-                ptr(stats), current_stream(),
-            )
-        )  # fmt: skip
+        row = out.shape[1] * 4
+        with _span("knn", nq * k):
+            check(
+                self.lib.agx_knn(
+                    self.handle, ptr(q), nq, int(k), out.data_ptr() + 4 * out_offset,
+                    out.data_ptr() + row + 4 * out_offset, int(dst_base), ptr(rdist), ptr(stats), current_stream(),
+                )
+            )  # fmt: skip
         return (out, rdist) if return_rdist else out
 
-    def radius(self, q: torch.Tensor, radius: float, dst_base: int = 0, stats: torch.Tensor | None = None) -> torch.Tensor:
-        """``edge_index`` (2, E) int32 of every (reference, query) pair within ``radius`` (inclusive)."""
+    def radius_count(self, q: torch.Tensor, radius: float) -> tuple[torch.Tensor, int]:
+        """Pass 1 of the cut-off search: ``(offsets (nq+1,) int64, total)``."""
         q = _dev_x(q)
         nq = int(q.shape[0])
         counts = torch.empty(nq, dtype=torch.int32, device=q.device)
         offsets = torch.empty(nq + 1, dtype=torch.int64, device=q.device)
         stream = current_stream()
-        check(self.lib.agx_radius_count(self.handle, ptr(q), nq, float(radius), ptr(counts), stream))
+        with _span("radius_count", nq):
+            check(self.lib.agx_radius_count(self.handle, ptr(q), nq, float(radius), ptr(counts), stream))
         total = c_int64()
         check(self.lib.agx_exclusive_scan(ptr(counts), nq, ptr(offsets), byref(total), stream))
-        out = torch.empty((2, total.value), dtype=torch.int32, device=q.device)
-        if total.value:
-            check(
-                self.lib.agx_radius_fill(
-                    self.handle, ptr(q), nq, float(radius), ptr(offsets), out[0].data_ptr(), out[1].data_ptr(),
-                    int(dst_base), ptr(stats), stream,
-                )
-            )  # fmt: skip
+        return offsets, int(total.value)
+
+    def radius_fill(
+        self, q: torch.Tensor, radius: float, offsets: torch.Tensor, total: int, out: torch.Tensor, out_offset: int = 0,
+        dst_base: int = 0, stats: torch.Tensor | None = None,
+    ) -> torch.Tensor:  # fmt: skip
+        """Pass 2: write the ``total`` pairs at column ``out_offset`` of the contiguous (2, E) int32 ``out``."""
+        q = _dev_x(q)
+        assert out.dim() == 2 and out.shape[0] == 2 and out.dtype == torch.int32 and out.is_contiguous()
+        assert 0 <= out_offset and out_offset + total <= out.shape[1]
+        if total:
+            row = out.shape[1] * 4
+            with _span("radius_fill", total):
+                check(
+                    self.lib.agx_radius_fill(
+                        self.handle, ptr(q), int(q.shape[0]), float(radius), ptr(offsets),
+                        out.data_ptr() + 4 * out_offset, out.data_ptr() + row + 4 * out_offset, int(dst_base), ptr(stats),
+                        current_stream(),
+                    )
+                )  # fmt: skip
         return out
+
+    def radius(self, q: torch.Tensor, radius: float, dst_base: int = 0, stats: torch.Tensor | None = None) -> torch.Tensor:
+        """``edge_index`` (2, E) int32 of every (reference, query) pair within ``radius`` (inclusive)."""
+        q = _dev_x(q)
+        offsets, total = self.radius_count(q, radius)
+        out = torch.empty((2, total), dtype=torch.int32, device=q.device)
+        return self.radius_fill(q, radius, offsets, total, out, 0, dst_base, stats)
 
 
 def new_stats(device) -> torch.Tensor:
@@ -155,7 +223,8 @@ class NodeTables:
         n = int(self.x.shape[0])
         self.xyzc = torch.empty((n, 4), dtype=torch.float32, device=self.x.device)
         self.quat = torch.empty((n, 4), dtype=torch.float64, device=self.x.device) if with_rotation else None
-        check(load_library().agx_node_tables(ptr(self.x), n, ptr(self.xyzc), ptr(self.quat), current_stream()))
+        with _span("node_tables", n):
+            check(load_library().agx_node_tables(ptr(self.x), n, ptr(self.xyzc), ptr(self.quat), current_stream()))
 
 
 _workspace: dict = {}
@@ -179,8 +248,15 @@ def edge_attributes(
     direction: bool = True,
     direction_norm: str | None = None,
     direction_rotated: bool = True,
+    sharded: bool = False,
 ):
-    """Fused EdgeLength / EdgeDirection: returns ``(len (E, 1) float32 | None, dir (E, 2) float32 | None)``."""
+    """Fused EdgeLength / EdgeDirection: returns ``(len (E, 1) float32 | None, dir (E, 2) float32 | None)``.
+
+    ``sharded=True`` (multi-GPU): this rank evaluates only its contiguous range of the edges, the
+    normalisation statistics are combined across ranks and the attribute blocks all-gathered, so every
+    rank returns the complete arrays."""
+    from . import device as _device
+
     for norm in (length_norm, direction_norm):
         if norm not in NORM_CODES:
             raise ValueError(
@@ -194,14 +270,51 @@ def edge_attributes(
     out_dir = torch.empty((n_edges, 2), dtype=torch.float32, device=dev) if direction else None
     if direction and direction_rotated and dst.quat is None:
         raise ValueError("rotated directions need target NodeTables built with with_rotation=True")
-    check(
-        load_library().agx_edge_attrs(
-            edge_index[0].data_ptr(), edge_index[1].data_ptr(), n_edges, ptr(src.x), ptr(src.xyzc), ptr(dst.x),
-            ptr(dst.xyzc), ptr(dst.quat), NORM_CODES[length_norm] if length else -1, int(bool(length_invert)),
-            ptr(out_len), NORM_CODES[direction_norm] if direction else -1, int(bool(direction_rotated)), ptr(out_dir),
-            ptr(_attr_workspace(dev)), current_stream(),
+    lib = load_library()
+    len_code = NORM_CODES[length_norm] if length else -1
+    dir_code = NORM_CODES[direction_norm] if direction else -1
+    rank, w = _device.world() if sharded else (0, 1)
+    ws = _attr_workspace(dev)
+    stream = current_stream()
+    if w == 1:
+        with _span("edge_attrs", n_edges):
+            check(
+                lib.agx_edge_attrs(
+                    edge_index[0].data_ptr(), edge_index[1].data_ptr(), n_edges, ptr(src.x), ptr(src.xyzc), ptr(dst.x),
+                    ptr(dst.xyzc), ptr(dst.quat), len_code, int(bool(length_invert)), ptr(out_len), dir_code,
+                    int(bool(direction_rotated)), ptr(out_dir), ptr(ws), stream,
+                )
+            )  # fmt: skip
+        return out_len, out_dir
+    lo, hi = _device.shard_range(n_edges, rank, w)
+    m = hi - lo
+    e_src, e_dst = edge_index[0].data_ptr() + 4 * lo, edge_index[1].data_ptr() + 4 * lo
+    stats = None
+    if len_code > 0 or dir_code > 0:
+        stats = torch.empty(8, dtype=torch.float64, device=dev)
+        with _span("edge_attrs_stats", m):
+          check(
+            lib.agx_edge_attrs_stats(
+                e_src, e_dst, m, ptr(src.x), ptr(src.xyzc), ptr(dst.x), ptr(dst.xyzc), ptr(dst.quat), int(len_code > 0),
+                int(dir_code > 0), int(bool(direction_rotated)), ptr(stats), ptr(ws), stream,
+            )
+        )  # fmt: skip
+        stats = _device.all_gather_stats(stats)
+    with _span("edge_attrs_apply", m):
+      check(
+        lib.agx_edge_attrs_apply(
+            e_src, e_dst, m, ptr(src.x), ptr(src.xyzc), ptr(dst.x), ptr(dst.xyzc), ptr(dst.quat), len_code,
+            int(bool(length_invert)), out_len.data_ptr() + 4 * lo if length else None, dir_code,
+            int(bool(direction_rotated)), out_dir.data_ptr() + 8 * lo if direction else None, ptr(stats), n_edges, ptr(ws),
+            stream,
         )
     )  # fmt: skip
+    counts = [_device.shard_range(n_edges, r, w) for r in range(w)]
+    counts = [b - a for a, b in counts]
+    if length:
+        _device.all_gather_v(out_len, counts, 0)
+    if direction:
+        _device.all_gather_v(out_dir, counts, 0)
     return out_len, out_dir
 
 
@@ -231,11 +344,12 @@ class Icosphere:
         self.vertices = torch.empty((nv, 3), dtype=torch.float64, device=device)
         self.faces_all = torch.empty((ico_face_offset(self.max_level + 1), 3), dtype=torch.int32, device=device)
         self.latlon = torch.empty((nv, 2), dtype=torch.float32, device=device)
-        check(
-            load_library().agx_icosphere(
-                self.max_level, ptr(self.vertices), ptr(self.faces_all), ptr(self.latlon), current_stream()
+        with _span("icosphere", nv):
+            check(
+                load_library().agx_icosphere(
+                    self.max_level, ptr(self.vertices), ptr(self.faces_all), ptr(self.latlon), current_stream()
+                )
             )
-        )
 
     def faces(self, level: int) -> torch.Tensor:
         o = ico_face_offset(level)
@@ -261,12 +375,13 @@ def multiscale_tri_edges(ico: Icosphere, levels: list[int], x_hops: int, node_or
     counts = torch.empty(nv, dtype=torch.int32, device=dev)
     offsets = torch.empty(nv + 1, dtype=torch.int64, device=dev)
     stream = current_stream()
-    check(
-        lib.agx_multiscale_tri_count(
-            ico.max_level, ptr(ico.faces_all), lv, len(levels), int(x_hops), ptr(order), ptr(rank), ptr(counts),
-            ptr(scratch), stream,
-        )
-    )  # fmt: skip
+    with _span("multiscale_count", nv):
+        check(
+            lib.agx_multiscale_tri_count(
+                ico.max_level, ptr(ico.faces_all), lv, len(levels), int(x_hops), ptr(order), ptr(rank), ptr(counts),
+                ptr(scratch), stream,
+            )
+        )  # fmt: skip
     total = c_int64()
     check(lib.agx_exclusive_scan(ptr(counts), nv, ptr(offsets), byref(total), stream))
     out = torch.empty((2, total.value), dtype=torch.int32, device=dev)
@@ -279,7 +394,50 @@ def multiscale_tri_edges(ico: Icosphere, levels: list[int], x_hops: int, node_or
     return out
 
 
+def multiscale_tri_edges_mapped(
+    ico: Icosphere, levels: list[int], x_hops: int, n_nodes: int, vertex_map: torch.Tensor
+) -> torch.Tensor:
+    """MultiScaleEdges for limited-area / stretched TriNodes: (2, E) int32 sorted by (dst, src).
+
+    ``vertex_map[v]`` is the graph position of icosphere vertex ``v`` of the finest level, or -1 if the
+    vertex is masked out (lower levels are prefixes, so the same map serves every level)."""
+    lib = load_library()
+    dev = ico.vertices.device
+    if x_hops > 8:
+        raise NotImplementedError(f"x_hops = {x_hops} > 8 is not built yet")
+    vmap = vertex_map.to(device=dev, dtype=torch.int32).contiguous()
+    assert vmap.shape == (ico_num_vertices(ico.max_level),)
+    node_vertex = torch.full((len(levels), n_nodes), -1, dtype=torch.int32, device=dev)
+    for i, level in enumerate(levels):
+        nv = ico_num_vertices(int(level))
+        v = torch.nonzero(vmap[:nv] >= 0, as_tuple=False).squeeze(1)
+        node_vertex[i, vmap[v].long()] = v.to(torch.int32)
+    lv = (c_int32 * len(levels))(*[int(v) for v in levels])
+    per_node = int(lib.agx_multiscale_scratch_per_node(len(levels), int(x_hops)))
+    scratch = torch.empty(per_node * max(n_nodes, 1), dtype=torch.int32, device=dev)
+    counts = torch.zeros(n_nodes, dtype=torch.int32, device=dev)
+    offsets = torch.empty(n_nodes + 1, dtype=torch.int64, device=dev)
+    stream = current_stream()
+    check(
+        lib.agx_multiscale_tri_count_mapped(
+            ico.max_level, ptr(ico.faces_all), lv, len(levels), int(x_hops), n_nodes, ptr(vmap), ptr(node_vertex),
+            ptr(counts), ptr(scratch), stream,
+        )
+    )  # fmt: skip
+    total = c_int64()
+    check(lib.agx_exclusive_scan(ptr(counts), n_nodes, ptr(offsets), byref(total), stream))
+    out = torch.empty((2, total.value), dtype=torch.int32, device=dev)
+    if total.value:
+        check(
+            lib.agx_multiscale_tri_fill(
+                n_nodes, ptr(counts), ptr(offsets), ptr(scratch), per_node, out[0].data_ptr(), out[1].data_ptr(), stream
+            )
+        )
+    return out
+
+
 __all__ = [
+    "multiscale_tri_edges_mapped",
     "NeighbourIndex",
     "NodeTables",
     "Icosphere",

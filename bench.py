@@ -1,0 +1,469 @@
+#!/usr/bin/env python
+"""Headline benchmark: O1280 -> TriNodes(7) encoder / processor / decoder graph, edges per second.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload NAME]
+
+One STEP = one complete pass of the edge-construction path over the workload: hidden TriNodes generation
+(icosphere subdivision kernels + the host node ordering the reference defines), CutOffEdges 0.6 encoder
+(data -> hidden), MultiScaleEdges x_hops=1 processor, KNNEdges k=3 decoder (hidden -> data), EdgeLength +
+EdgeDirection (unit-std) on all three edge sets - through the reference-facing builder API
+(``GraphCreator.update_graph``), i.e. the recipe ``anemoi-graphs create`` would run.  Data-node coordinates are
+synthetic (octahedral reduced Gaussian grid, ``anemoi_graphs_b200.grids``) and are an INPUT of the step.
+
+* ``value``: edges/s with the data coordinates already resident in HBM and every output left in HBM
+  (CUDA events around exactly K steps; max over ranks).
+* ``e2e``: the same step with HOST buffers - coordinates in pinned host memory are uploaded and all
+  ``edge_index`` / attribute tensors are copied back to pinned host memory inside the timed region.
+* ``roofline``: the dominant kernel, timed live with CUDA events on its launch stream during the timed steps.
+* ``cpu_baseline`` / ``--impl reference``: the oracle (the reference's own sklearn / scipy / networkx calls,
+  ``oracle/ref_path.py``) timed on this host's cores on a bounded sample of the same workload.
+
+Multi-GPU (torchrun, one rank per GPU): query nodes are sharded by rank, per-rank edge blocks are all-gathered
+over NCCL, every rank ends with the complete graph; total work is fixed => "scaling": "strong".
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import pathlib
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+REPO = pathlib.Path(__file__).resolve().parent
+if str(REPO) not in sys.path:
+    sys.path.insert(0, str(REPO))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+T = "anemoi.graphs."
+WORKLOADS = {
+    # name: (data grid, hidden TriNodes resolution)
+    "o1280_res7": ("o1280", 7),
+    "n320_res6": ("n320", 6),
+    "o96_res5": ("o96", 5),
+}
+CUTOFF_FACTOR = 0.6
+KNN_K = 3
+X_HOPS = 1
+NORM = "unit-std"
+# algorithmic HBM bytes per output unit, SURVEY.md section 8(d) / DESIGN.md
+ALGO_BYTES = {
+    "knn": lambda nq, nr, e: 8.0 * nq + 8.0 * nr + 8.0 * e,
+    "radius_fill": lambda nq, nr, e: 8.0 * nq + 8.0 * nr + 8.0 * e,
+    "edge_attrs": lambda nq, nr, e: 20.0 * e,
+}
+
+
+def attrs_cfg():
+    return {
+        "edge_length": {"_target_": T + "edges.attributes.EdgeLength", "norm": NORM},
+        "edge_dirs": {"_target_": T + "edges.attributes.EdgeDirection", "norm": NORM},
+    }
+
+
+def recipe(resolution: int) -> dict:
+    return {
+        "nodes": {"hidden": {"node_builder": {"_target_": T + "nodes.TriNodes", "resolution": resolution}}},
+        "edges": [
+            {"source_name": "data", "target_name": "hidden", "attributes": attrs_cfg(),
+             "edge_builders": [{"_target_": T + "edges.CutOffEdges", "cutoff_factor": CUTOFF_FACTOR}]},
+            {"source_name": "hidden", "target_name": "hidden", "attributes": attrs_cfg(),
+             "edge_builders": [{"_target_": T + "edges.MultiScaleEdges", "x_hops": X_HOPS}]},
+            {"source_name": "hidden", "target_name": "data", "attributes": attrs_cfg(),
+             "edge_builders": [{"_target_": T + "edges.KNNEdges", "num_nearest_neighbours": KNN_K}]},
+        ],
+    }  # fmt: skip
+
+
+EDGE_KEYS = [("data", "to", "hidden"), ("hidden", "to", "hidden"), ("hidden", "to", "data")]
+
+
+def data_coordinates(grid: str) -> torch.Tensor:
+    from anemoi_graphs_b200 import grids
+
+    lat, lon = grids.named_grid(grid)
+    return grids.latlon_deg_to_x(lat, lon)
+
+
+# ----------------------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = (
+        "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+        "clocks_event_reasons.sw_power_cap"
+    )
+
+    def __init__(self, gpu_index: int) -> None:
+        self.gpu_index = gpu_index
+        self.lines: list[str] = []
+        self.proc = None
+
+    def start(self) -> None:
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu_index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
+            )  # fmt: skip
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self) -> None:
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            f = [c.strip() for c in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {
+            "sm_mhz": statistics.median(sm) if sm else None,
+            "sm_max_mhz": max(smax) if smax else None,
+            "samples": len(sm),
+            "reasons": sorted(reasons),
+        }
+
+
+# ----------------------------------------------------------------------------------------------------
+# the GPU arm
+# ----------------------------------------------------------------------------------------------------
+def run_step(creator, data_x: torch.Tensor):
+    from anemoi_graphs_b200.graph import HeteroData
+
+    graph = HeteroData()
+    graph["data"].x = data_x
+    graph["data"].node_type = "LatLonNodes"
+    return creator.update_graph(graph)
+
+
+def graph_edges(graph) -> int:
+    return sum(int(graph[k].edge_index.shape[1]) for k in EDGE_KEYS)
+
+
+def output_bytes(graph) -> int:
+    n = 0
+    for k in EDGE_KEYS:
+        for name in ("edge_index", "edge_length", "edge_dirs"):
+            t = graph[k][name]
+            n += t.numel() * t.element_size()
+    return n
+
+
+def bench_b200(args) -> dict:
+    import torch.distributed as dist
+
+    from anemoi_graphs_b200 import _cabi, ops
+    from anemoi_graphs_b200 import device as agx_device
+    from anemoi_graphs_b200.create import GraphCreator
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if world != args.gpus and rank == 0:
+        print(f"note: --gpus {args.gpus} but WORLD_SIZE={world}; using {world}", file=sys.stderr)
+
+    grid, res = WORKLOADS[args.workload]
+    x_host = data_coordinates(grid).pin_memory()
+    x_dev = x_host.cuda()
+    creator = GraphCreator(recipe(res))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        """CUDA-event time of `steps` calls, max over ranks (ms)."""
+        barrier()
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record()
+        out = None
+        for _ in range(steps):
+            out = fn()
+        end.record()
+        torch.cuda.synchronize()
+        ms = start.elapsed_time(end)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        barrier()
+        return ms, out
+
+    # ---- device-resident: `value` -------------------------------------------------------------------
+    agx_device.set_resident(True)
+    for _ in range(args.warmup):
+        graph = run_step(creator, x_dev)
+    n_edges = graph_edges(graph)
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    ops.timeline = ops.Timeline()
+    launches0 = _cabi.launch_count()
+    ms_total, graph = timed(lambda: run_step(creator, x_dev), args.steps)
+    launches = _cabi.launch_count() - launches0
+    spans = ops.timeline.totals_ms()
+    span_counts = ops.timeline.counts()
+    ops.timeline = None
+    clock_info = clocks.stop() if rank == 0 else {}
+    ms_per_step = ms_total / args.steps
+    value = n_edges / (ms_per_step * 1e-3)
+    sizes = {k: int(graph[k].edge_index.shape[1]) for k in EDGE_KEYS}
+    n_data, n_hidden = int(x_dev.shape[0]), int(graph["hidden"].x.shape[0])
+    del graph
+
+    # ---- end to end with host buffers: `e2e` ---------------------------------------------------------
+    agx_device.set_resident(False)
+    for _ in range(max(2, args.warmup // 2)):
+        graph = run_step(creator, x_host)
+    d2h = output_bytes(graph)
+    e2e_steps = max(1, min(args.steps, 5))
+    ms_e2e, graph = timed(lambda: run_step(creator, x_host), e2e_steps)
+    e2e_value = n_edges / (ms_e2e / e2e_steps * 1e-3)
+    del graph
+
+    # ---- roofline of the dominant kernel ---------------------------------------------------------------
+    per_call = {k: spans[k] / span_counts[k] for k in spans}
+    per_step = {k: spans[k] / args.steps for k in spans}
+    kern = max((k for k in per_step if k in ALGO_BYTES), key=lambda k: per_step[k])
+    peaks = {}
+    peaks_path = REPO / "MEASURED_PEAKS.json"
+    if peaks_path.exists():
+        peaks = json.loads(peaks_path.read_text())
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    if kern == "knn":
+        nq, nr, e = n_data // world, n_hidden, sizes[EDGE_KEYS[2]] // world
+    elif kern == "radius_fill":
+        nq, nr, e = n_hidden // world, n_data, sizes[EDGE_KEYS[0]] // world
+    else:  # edge_attrs: average over the three edge sets (one launch pair per edge set)
+        nq, nr, e = 0, 0, n_edges / 3.0 / world
+    algo_bytes = ALGO_BYTES[kern](nq, nr, e)
+    achieved = algo_bytes / (per_call[kern] * 1e-3) / 1e9
+    traffic = None
+    tpath = REPO / "profiles" / "traffic.json"
+    if tpath.exists():
+        traffic = json.loads(tpath.read_text()).get(kern)
+    roofline = {
+        "kernel": kern,
+        "bound": "hbm",
+        "achieved": round(achieved, 2),
+        "peak": peak,
+        "peak_source": peak_src,
+        "unit": "GB/s",
+        "frac": round(achieved / peak, 5),
+        "traffic": traffic,
+        "algorithmic_bytes_per_launch": algo_bytes,
+        "ms_per_launch": round(per_call[kern], 4),
+        "stage_ms_per_step": {k: round(v, 4) for k, v in sorted(per_step.items(), key=lambda kv: -kv[1])},
+    }
+
+    line = {
+        "metric": "O1280->ico7 graph edges/sec (CutOff encoder + MultiScale processor + KNN-3 decoder + EdgeLength/EdgeDirection)",
+        "value": round(value, 1),
+        "unit": "edges/s",
+        "n_gpus": world,
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": round(ms_per_step, 4),
+        "higher_is_better": True,
+        "scaling": "strong",
+        "vs_baseline": None,
+        "dtype": "f32 filter + f64 decisions, int32 indices",
+        "data": "synthetic",
+        "config": {
+            "workload": args.workload,
+            "data_nodes": n_data,
+            "hidden_nodes": n_hidden,
+            "edges": {"cutoff": sizes[EDGE_KEYS[0]], "multiscale": sizes[EDGE_KEYS[1]], "knn": sizes[EDGE_KEYS[2]]},
+            "cutoff_factor": CUTOFF_FACTOR, "knn_k": KNN_K, "x_hops": X_HOPS, "attribute_norm": NORM,
+            "sharding": f"query nodes over {world} rank(s), all-gather of edge blocks" if world > 1 else "single GPU",
+            "l2": "inputs + outputs (~0.7 GB per step) exceed the 126 MB L2; no explicit flush",
+        },
+        "e2e": {
+            "value": round(e2e_value, 1),
+            "unit": "edges/s",
+            "ms_per_step": round(ms_e2e / e2e_steps, 4),
+            "steps": e2e_steps,
+            "h2d_bytes_per_step": int(x_host.numel() * 4),
+            "d2h_bytes_per_step": int(d2h),
+        },
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "clocks": clock_info,
+    }  # fmt: skip
+    if rank == 0 and not args.no_cpu_baseline and world == 1:
+        line["cpu_baseline"] = cpu_reference(args.workload, n_jobs=4, budget_s=args.cpu_budget)
+    if world > 1:
+        dist.destroy_process_group()
+    return line if rank == 0 else {}
+
+
+# ----------------------------------------------------------------------------------------------------
+# the CPU reference arm (oracle = the reference's own sklearn / scipy / networkx calls)
+# ----------------------------------------------------------------------------------------------------
+def cpu_reference(workload: str, n_jobs: int, budget_s: float = 20.0, x=None) -> dict:
+    """Time the reference path on this host on a bounded sample of the workload and extrapolate to the full
+    graph: fixed costs (ball-tree fits, reference distance) are paid in full, per-query / per-edge costs are
+    measured on a fraction f of the queries and scaled by 1/f."""
+    from oracle import ref_path as R
+
+    grid, res = WORKLOADS[workload]
+    dx = (data_coordinates(grid) if x is None else x).numpy()
+    t_all = time.perf_counter()
+    hx, order = R.tri_nodes(res)
+    t_nodes = time.perf_counter() - t_all
+    nd, nh = dx.shape[0], hx.shape[0]
+    # query fractions sized from the survey's rates (~3e4 KNN queries/s on 4 threads)
+    f = min(1.0, max(1.0 / 256, budget_s * 0.3 * 3.0e4 / nd))
+    rng = np.random.default_rng(0)
+    qd = np.sort(rng.choice(nd, size=max(1, int(nd * f)), replace=False))
+    qh = np.sort(rng.choice(nh, size=max(1, int(nh * f)), replace=False))
+
+    from sklearn.neighbors import NearestNeighbors
+
+    t = time.perf_counter()
+    radius = R.cutoff_radius(hx, CUTOFF_FACTOR, n_jobs)  # k=2 self query on the hidden nodes (fixed cost)
+    t_refdist = time.perf_counter() - t
+    t = time.perf_counter()
+    nn = NearestNeighbors(metric="haversine", n_jobs=n_jobs).fit(dx)
+    t_fit_data = time.perf_counter() - t
+    t = time.perf_counter()
+    adj = nn.radius_neighbors_graph(hx[qh], radius=radius).tocoo()
+    cut = np.stack([adj.col, qh[adj.row]]).astype(np.int32)
+    t_cut = time.perf_counter() - t
+    del nn
+    t = time.perf_counter()
+    nn = NearestNeighbors(metric="haversine", n_jobs=n_jobs).fit(hx)
+    t_fit_hidden = time.perf_counter() - t
+    t = time.perf_counter()
+    adj = nn.kneighbors_graph(dx[qd], n_neighbors=KNN_K, mode="distance").tocoo()
+    knn = np.stack([adj.col, qd[adj.row]]).astype(np.int32)
+    t_knn = time.perf_counter() - t
+    # multi-scale: the reference's networkx path on a coarser mesh (cost is linear in the vertex count)
+    ms_res = min(res, 4)
+    mx, morder = R.tri_nodes(ms_res)
+    t = time.perf_counter()
+    ms = R.multiscale_edges_tri_networkx(range(ms_res + 1), X_HOPS, morder, mx)
+    t_ms = time.perf_counter() - t
+    ms_full_edges = sum(60 * 4**r for r in range(res + 1))
+    t_ms_full = t_ms * ms_full_edges / ms.shape[1]
+    # attributes on the sampled edges
+    t = time.perf_counter()
+    with np.errstate(all="ignore"):
+        for sx, tx, ei in ((dx, hx, cut), (hx, dx, knn)):
+            R.edge_length(sx, tx, ei, NORM)
+            R.edge_direction(sx, tx, ei, NORM)
+    t_attr = time.perf_counter() - t
+    attr_rate = (cut.shape[1] + knn.shape[1]) / t_attr
+    e_cut, e_knn = cut.shape[1] / f, knn.shape[1] / f
+    e_total = e_cut + e_knn + ms_full_edges
+    t_full = t_nodes + t_refdist + t_fit_data + t_fit_hidden + t_cut / f + t_knn / f + t_ms_full + e_total / attr_rate
+    return {
+        "value": round(e_total / t_full, 1),
+        "unit": "edges/s",
+        "cores": n_jobs if n_jobs > 0 else os.cpu_count(),
+        "host_cpus": os.cpu_count(),
+        "kind": "port",
+        "sample": (
+            f"oracle/ref_path.py (the reference's sklearn BallTree / scipy / networkx calls) on {workload}: full tree "
+            f"fits + reference distance, a random {f:.4f} of the KNN and cut-off queries, MultiScale via networkx at "
+            f"res {ms_res}, attributes on the sampled edges; per-query/per-edge times scaled to the full graph "
+            f"({int(e_total)} edges, est. {t_full:.1f} s)"
+        ),
+        "measured_s": round(time.perf_counter() - t_all, 2),
+        "stage_s": {
+            "tri_nodes": round(t_nodes, 3), "ref_distance": round(t_refdist, 3), "fit_data_tree": round(t_fit_data, 3),
+            "fit_hidden_tree": round(t_fit_hidden, 3), "cutoff_query_sample": round(t_cut, 3),
+            "knn_query_sample": round(t_knn, 3), "multiscale_sample": round(t_ms, 3), "attrs_sample": round(t_attr, 3),
+        },
+        "estimated_full_graph_s": round(t_full, 2),
+    }  # fmt: skip
+
+
+def bench_reference(args) -> dict:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return {}
+    grid, res = WORKLOADS[args.workload]
+    x = data_coordinates(grid)
+    n_steps = args.steps + args.warmup
+    budget = max(4.0, min(20.0, 150.0 / max(1, n_steps)))
+    for _ in range(args.warmup):
+        cpu_reference(args.workload, n_jobs=-1, budget_s=budget, x=x)
+    vals, last = [], None
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        last = cpu_reference(args.workload, n_jobs=-1, budget_s=budget, x=x)
+        vals.append(last["value"])
+    wall = time.perf_counter() - t0
+    value = float(np.mean(vals))
+    return {
+        "impl": "reference",
+        "metric": "O1280->ico7 graph edges/sec (CutOff encoder + MultiScale processor + KNN-3 decoder + EdgeLength/EdgeDirection)",
+        "value": round(value, 1),
+        "unit": "edges/s",
+        "n_gpus": args.gpus,
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": round(wall / max(1, args.steps) * 1e3, 2),
+        "higher_is_better": True,
+        "scaling": "strong",
+        "vs_baseline": None,
+        "dtype": "f64 (sklearn BallTree haversine), f32/f64 numpy attributes",
+        "data": "synthetic",
+        "config": {"workload": args.workload, "note": "CPU only; the reference has no GPU or multi-process path"},
+        "cpu_baseline": {k: last[k] for k in ("value", "unit", "cores", "host_cpus", "kind", "sample")} | {"value": round(value, 1)},
+        "e2e": {"value": round(value, 1), "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }  # fmt: skip
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="o1280_res7", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for the cpu_baseline sample")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    line = bench_reference(args) if args.impl == "reference" else bench_b200(args)
+    if line:
+        print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

@@ -110,6 +110,21 @@ int agx_edge_attrs(const int32_t* edge_src /*DEV E*/, const int32_t* edge_dst /*
                    int dir_norm /*AGX_NORM_* or -1 = skip*/, int dir_rotated, float* out_dir /*DEV E*2*/,
                    double* workspace /*DEV, >= agx_edge_attrs_workspace() doubles*/, void* stream);
 int64_t agx_edge_attrs_workspace(void);
+/* The two halves of agx_edge_attrs, for callers that hold only a SHARD of the edge set (one rank of a
+ * multi-GPU build): _stats reduces the raw values of the local edges to
+ * stats[8] = {len sum, sum of squares, min, max, dir sum, sum of squares, min, max} (float64; an empty shard
+ * gives {0, 0, +1e300, -1e300}); the caller combines the shards' statistics (sum / min / max) and passes the
+ * global ones, with the global edge count, to _apply, which writes the normalised float32 attributes of the
+ * local edges.  want_* select which raw values are reduced (normalise.py:20-55 needs them only for a norm). */
+int agx_edge_attrs_stats(const int32_t* edge_src, const int32_t* edge_dst, int64_t n_edges, const float* src_latlon,
+                         const float* src_xyzc, const float* dst_latlon, const float* dst_xyzc,
+                         const double* dst_quat, int want_len, int want_dir, int dir_rotated,
+                         double* stats /*DEV 8*/, double* workspace, void* stream);
+int agx_edge_attrs_apply(const int32_t* edge_src, const int32_t* edge_dst, int64_t n_edges, const float* src_latlon,
+                         const float* src_xyzc, const float* dst_latlon, const float* dst_xyzc,
+                         const double* dst_quat, int len_norm, int len_invert, float* out_len, int dir_norm,
+                         int dir_rotated, float* out_dir, const double* stats /*DEV 8 or NULL if no norm*/,
+                         int64_t n_edges_global, double* workspace, void* stream);
 
 /* ---- icosphere + multi-scale edges -------------------------------------------------------------------
  * agx_icosphere: replaces trimesh.creation.icosphere (generate/tri_icosahedron.py:121,173):
@@ -128,6 +143,15 @@ int agx_multiscale_tri_count(int max_level, const int32_t* faces_all /*DEV*/, co
                              const int32_t* rank_of_vertex /*DEV nv*/, int32_t* counts /*DEV nv*/,
                              int32_t* scratch /*DEV nv*agx_multiscale_scratch_per_node()*/, void* stream);
 int64_t agx_multiscale_scratch_per_node(int n_levels, int x_hops);
+/* Limited-area / stretched variant (generate/tri_icosahedron.py:177-187,214-215; edges/builder.py:422-432):
+ * the graph has n_nodes nodes that are a SUBSET (or a mix of two levels) of icosphere vertices.
+ * vertex_map[v] (v < nv(max_level)) = graph position of vertex v, or -1 if the vertex is masked out - the
+ * same array serves every level because lower levels are prefixes; node_vertex[l*n_nodes + t] = the vertex
+ * of requested level l that graph node t is, or -1.  Mesh edges with a masked endpoint are not walked.  */
+int agx_multiscale_tri_count_mapped(int max_level, const int32_t* faces_all /*DEV*/, const int32_t* levels /*HOST*/,
+                                    int n_levels, int x_hops, int64_t n_nodes, const int32_t* vertex_map /*DEV*/,
+                                    const int32_t* node_vertex /*DEV n_levels*n_nodes*/, int32_t* counts /*DEV n_nodes*/,
+                                    int32_t* scratch /*DEV n_nodes*agx_multiscale_scratch_per_node()*/, void* stream);
 int agx_multiscale_tri_fill(int64_t n_nodes, const int32_t* counts, const int64_t* offsets /*DEV nv+1*/,
                             const int32_t* scratch, int64_t scratch_per_node, int32_t* out_src,
                             int32_t* out_dst, void* stream);

@@ -1,0 +1,139 @@
+"""Host-side logic that needs no GPU: constructor validation mirrored from the reference's tests
+(tests/edges/test_knn.py:15-31, test_cutoff.py:15-31, test_multiscale_edges.py:21-35,
+tests/generate/test_masks.py), recipe handling, the C-ABI symbol table, shard arithmetic."""
+
+import ctypes
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from anemoi_graphs_b200 import _cabi
+from anemoi_graphs_b200 import device as agx_device
+from anemoi_graphs_b200.config import DotDict, instantiate, resolve_target
+from anemoi_graphs_b200.create import GraphCreator
+from anemoi_graphs_b200.edges import CutOffEdges, KNNEdges, MultiScaleEdges
+from anemoi_graphs_b200.edges.attributes import EdgeDirection, EdgeLength
+from anemoi_graphs_b200.generate.masks import KNNAreaMaskBuilder
+from anemoi_graphs_b200.graph import HeteroData
+from anemoi_graphs_b200.nodes import HexNodes, LatLonNodes, TriNodes
+
+
+def test_knn_init():
+    KNNEdges("test_nodes1", "test_nodes2", 3)
+    for bad in (-1, 4.5, None, "hello"):
+        with pytest.raises(AssertionError):
+            KNNEdges("test_nodes1", "test_nodes2", bad)
+
+
+def test_cutoff_init():
+    CutOffEdges("test_nodes1", "test_nodes2", 0.5)
+    CutOffEdges("test_nodes1", "test_nodes2", 1)
+    for bad in (-0.5, "hello", None):
+        with pytest.raises(AssertionError):
+            CutOffEdges("test_nodes1", "test_nodes2", bad)
+
+
+def test_multiscale_init():
+    assert isinstance(MultiScaleEdges("test_nodes", "test_nodes", 1), MultiScaleEdges)
+    for bad in (-1, 0, 1.5, "1"):
+        with pytest.raises(AssertionError):
+            MultiScaleEdges("test_nodes", "test_nodes", bad)
+    with pytest.raises(AssertionError):
+        MultiScaleEdges("test_nodes1", "test_nodes2", 1)
+
+
+def test_multiscale_rejects_other_node_types():
+    graph = HeteroData()
+    graph["data"].x = torch.zeros((4, 2))
+    graph["data"].node_type = "LatLonNodes"
+    with pytest.raises(AssertionError):
+        MultiScaleEdges("data", "data", 1).update_graph(graph)
+
+
+def test_mask_builder_init():
+    KNNAreaMaskBuilder("nodes", 100)
+    for bad in (-1, "hello", None):
+        with pytest.raises(AssertionError):
+            KNNAreaMaskBuilder("nodes", bad)
+
+
+def test_node_builders_host_side():
+    b = LatLonNodes([0.0, 10.0], [5.0, 350.0], name="n")
+    x = b.get_coordinates()
+    assert x.dtype == torch.float32 and x.shape == (2, 2)
+    np.testing.assert_allclose(x.numpy(), np.deg2rad([[0, 5], [10, 350]]), rtol=1e-6)
+    with pytest.raises(AssertionError):
+        LatLonNodes([0.0], [1.0, 2.0], name="n")
+    assert TriNodes(3, "h").resolutions == [0, 1, 2, 3]
+    assert TriNodes([1, 3], "h").resolutions == [1, 3]
+    with pytest.raises(NotImplementedError, match="h3"):
+        HexNodes(1, "h").create_nodes()
+
+
+def test_attribute_ctor_and_norm_validation():
+    assert EdgeLength(norm="l1", invert=True).invert is True
+    assert EdgeDirection(luse_rotated_features=False).luse_rotated_features is False
+
+
+def test_recipe_targets_resolve_to_this_package():
+    for target, cls in (
+        ("anemoi.graphs.edges.KNNEdges", KNNEdges),
+        ("anemoi.graphs.edges.CutOffEdges", CutOffEdges),
+        ("anemoi.graphs.edges.MultiScaleEdges", MultiScaleEdges),
+        ("anemoi.graphs.edges.attributes.EdgeLength", EdgeLength),
+        ("anemoi.graphs.edges.attributes.EdgeDirection", EdgeDirection),
+        ("anemoi.graphs.nodes.TriNodes", TriNodes),
+        ("anemoi.graphs.nodes.LatLonNodes", LatLonNodes),
+    ):
+        assert resolve_target(target) is cls
+    k = instantiate(DotDict({"_target_": "anemoi.graphs.edges.KNNEdges", "num_nearest_neighbours": 4}),
+                    source_name="a", target_name="b")  # fmt: skip
+    assert isinstance(k, KNNEdges) and k.name == ("a", "to", "b")
+
+
+def test_graph_creator_legacy_edge_builder_key(tmp_path):
+    recipe = tmp_path / "r.yaml"
+    recipe.write_text(
+        "nodes: {}\n"
+        "edges:\n"
+        "  - source_name: a\n    target_name: b\n"
+        "    edge_builder: {_target_: anemoi.graphs.edges.KNNEdges, num_nearest_neighbours: 3}\n"
+        "    source_mask_attr_name: m\n"
+    )
+    with pytest.warns(DeprecationWarning):
+        creator = GraphCreator(recipe)
+    cfg = creator.config.edges[0].edge_builders[0]
+    assert cfg.source_mask_attr_name == "m" and cfg.target_mask_attr_name is None
+
+
+def test_compute_requires_cuda_no_cpu_fallback():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    graph = HeteroData()
+    graph["a"].x = torch.zeros((4, 2))
+    graph["b"].x = torch.zeros((4, 2))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        KNNEdges("a", "b", 2).update_graph(graph)
+
+
+def test_cabi_exports_every_declared_symbol():
+    header = (_cabi.LIB_PATH.parents[2] / "include" / "agx_b200.h").read_text()
+    declared = set(re.findall(r"\b(agx_[a-z0-9_]+)\s*\(", header)) - {"agx_index"}
+    assert declared == set(_cabi.SIGNATURES), declared ^ set(_cabi.SIGNATURES)
+    lib = _cabi.load_library()
+    for name in declared:
+        assert isinstance(getattr(lib, name), ctypes._CFuncPtr)
+    assert lib.agx_abi_version() == 1
+    assert lib.agx_edge_attrs_workspace() > 16
+    assert lib.agx_multiscale_scratch_per_node(8, 1) == 9 * 7
+
+
+def test_shard_ranges_partition():
+    for n in (0, 1, 7, 163842, 6599680):
+        for w in (1, 2, 3, 8):
+            r = [agx_device.shard_range(n, k, w) for k in range(w)]
+            assert r[0][0] == 0 and r[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(r, r[1:]))
+            assert max(b - a for a, b in r) - min(b - a for a, b in r) <= 1

@@ -1,0 +1,246 @@
+"""GPU parity of the reference-facing builder API (GraphCreator, KNNEdges, CutOffEdges, MultiScaleEdges,
+EdgeLength, EdgeDirection, TriNodes) against golden fixtures produced by the UNMODIFIED reference
+(tests/golden/*.npz, oracle/make_golden.py) and against the oracle.  Reads like the reference's own
+tests (tests/edges/*, tests/test_create.py) but checks values, not just types."""
+
+import numpy as np
+import pytest
+import torch
+
+from anemoi_graphs_b200 import grids
+from oracle import ref_path as R
+
+pytestmark = pytest.mark.gpu
+
+T = "anemoi.graphs."
+ATTR_RTOL = 1e-6
+
+
+def canon(ei):
+    ei = ei.cpu().numpy() if isinstance(ei, torch.Tensor) else np.asarray(ei)
+    return R.canonical_sort(ei)
+
+
+def attr_cfg(norm="unit-std"):
+    return {
+        "edge_length": {"_target_": T + "edges.attributes.EdgeLength", "norm": norm},
+        "edge_dirs": {"_target_": T + "edges.attributes.EdgeDirection", "norm": norm},
+    }
+
+
+def latlon_nodes(lat, lon):
+    return {"node_builder": {"_target_": T + "nodes.LatLonNodes", "latitudes": lat, "longitudes": lon}}
+
+
+def tri_nodes(res):
+    return {"node_builder": {"_target_": T + "nodes.TriNodes", "resolution": res}}
+
+
+def edges(src, dst, builders, attributes=None):
+    return {"source_name": src, "target_name": dst, "edge_builders": builders, "attributes": attributes or {}}
+
+
+def build(nodes, edge_cfgs):
+    from anemoi_graphs_b200.create import GraphCreator
+    from anemoi_graphs_b200.graph import HeteroData
+
+    return GraphCreator({"nodes": nodes, "edges": edge_cfgs}).update_graph(HeteroData())
+
+
+def by_canonical_order(graph, key, name):
+    ei = graph[key].edge_index.numpy()
+    order = np.lexsort((ei[0], ei[1]))
+    return graph[key][name].numpy()[order]
+
+
+def test_tri_nodes_match_reference(golden):
+    g = golden("tri_nodes")
+    for res in range(5):
+        graph = build({"hidden": tri_nodes(res)}, [])
+        x = graph["hidden"].x
+        assert x.dtype == torch.float32 and not x.is_cuda
+        np.testing.assert_array_equal(x.numpy().view(np.int32), g[f"res{res}_x"].view(np.int32))
+        np.testing.assert_array_equal(np.asarray(graph["hidden"]["_node_ordering"]), g[f"res{res}_node_ordering"])
+        assert graph["hidden"].node_type == "TriNodes"
+        for hidden in ("_resolutions", "_nx_graph", "_node_ordering", "_area_mask_builder"):
+            assert hidden in graph["hidden"]  # reference: tests/nodes/test_tri_nodes.py:35-43
+    assert build({"hidden": tri_nodes(2)}, [])["hidden"].x.shape == (162, 2)  # tests/nodes/test_tri_nodes.py:32
+
+
+def test_toy_recipe_matches_reference(golden):
+    g = golden("toy")
+    nodes = {"data": latlon_nodes(g["data_lat_deg"], g["data_lon_deg"]), "hidden": tri_nodes(2)}
+    graph = build(
+        nodes,
+        [
+            edges("data", "hidden", [{"_target_": T + "edges.CutOffEdges", "cutoff_factor": 0.6}], attr_cfg("l2")),
+            edges("hidden", "hidden", [{"_target_": T + "edges.MultiScaleEdges", "x_hops": 1}], attr_cfg("l2")),
+            edges("hidden", "data", [{"_target_": T + "edges.KNNEdges", "num_nearest_neighbours": 3}], attr_cfg("l2")),
+        ],
+    )
+    np.testing.assert_array_equal(graph["data"].x.numpy().view(np.int32), g["data_x"].view(np.int32))
+    np.testing.assert_array_equal(graph["hidden"].x.numpy().view(np.int32), g["hidden_x"].view(np.int32))
+    cases = (
+        (("data", "to", "hidden"), "cutoff", "CutOffEdges"),
+        (("hidden", "to", "hidden"), "multiscale1", "MultiScaleEdges"),
+        (("hidden", "to", "data"), "knn3", "KNNEdges"),
+    )
+    for key, tag, edge_type in cases:
+        store = graph[key]
+        assert store.edge_index.dtype == torch.int32 and store.edge_type == edge_type
+        ref = g[f"{tag}_edge_index"]
+        np.testing.assert_array_equal(canon(store.edge_index), canon(ref))
+        order = np.lexsort((ref[0], ref[1]))
+        short = {"cutoff": "cutoff", "multiscale1": "ms1", "knn3": "knn3"}[tag]
+        want = g[f"{short}_len_l2"][order]
+        np.testing.assert_allclose(by_canonical_order(graph, key, "edge_length"), want, rtol=ATTR_RTOL, atol=0)
+        want = g[f"{short}_dir_rot_l2"][order]
+        got = by_canonical_order(graph, key, "edge_dirs")
+        np.testing.assert_allclose(got, want, rtol=ATTR_RTOL, atol=ATTR_RTOL * np.abs(want).max())
+        assert store.edge_length.dtype == torch.float32 and store.edge_length.shape == (ref.shape[1], 1)
+        assert store.edge_dirs.shape == (ref.shape[1], 2)
+
+
+def test_x_hops_2_and_merged_builders(golden):
+    g = golden("toy")
+    nodes = {"data": latlon_nodes(g["data_lat_deg"], g["data_lon_deg"]), "hidden": tri_nodes(2)}
+    graph = build(nodes, [edges("hidden", "hidden", [{"_target_": T + "edges.MultiScaleEdges", "x_hops": 2}])])
+    np.testing.assert_array_equal(canon(graph[("hidden", "to", "hidden")].edge_index), canon(g["multiscale2_edge_index"]))
+    graph = build(
+        nodes,
+        [
+            edges(
+                "data",
+                "hidden",
+                [
+                    {"_target_": T + "edges.CutOffEdges", "cutoff_factor": 0.6},
+                    {"_target_": T + "edges.KNNEdges", "num_nearest_neighbours": 5},
+                ],
+            ),
+        ],
+    )
+    store = graph[("data", "to", "hidden")]
+    # concat_edges: columns sorted lexicographically and de-duplicated - ORDER included (utils.py:66-81)
+    np.testing.assert_array_equal(store.edge_index.numpy(), g["cutoff_plus_knn5_edge_index"])
+    assert store.edge_type == str(g["cutoff_plus_knn5_edge_type"])
+
+
+def test_masked_builders_match_reference(golden):
+    from anemoi_graphs_b200.edges import CutOffEdges, KNNEdges
+    from anemoi_graphs_b200.graph import HeteroData
+
+    g = golden("toy")
+    graph = HeteroData()
+    graph["data"].x = torch.from_numpy(g["data_x"])
+    graph["hidden"].x = torch.from_numpy(g["hidden_x"])
+    graph["data"]["m"] = torch.from_numpy(g["data_mask"])
+    graph["hidden"]["m"] = torch.from_numpy(g["hidden_mask"])
+    KNNEdges("hidden", "data", 3, source_mask_attr_name="m", target_mask_attr_name="m").update_graph(graph)
+    CutOffEdges("data", "hidden", 0.6, source_mask_attr_name="m", target_mask_attr_name="m").update_graph(graph)
+    np.testing.assert_array_equal(canon(graph[("hidden", "to", "data")].edge_index), canon(g["masked_knn3_edge_index"]))
+    np.testing.assert_array_equal(canon(graph[("data", "to", "hidden")].edge_index), canon(g["masked_cutoff_edge_index"]))
+
+
+def test_o96_res5_full_recipe(golden):
+    """Config 1 of BASELINE.json: the documented 62 980 / 81 900 / 120 960 edges, bit-exact index sets."""
+    g = golden("o96_res5")
+    lat, lon = grids.octahedral_grid(96)
+    graph = build(
+        {"data": latlon_nodes(lat, lon), "hidden": tri_nodes(5)},
+        [
+            edges("data", "hidden", [{"_target_": T + "edges.CutOffEdges", "cutoff_factor": 0.6}], attr_cfg()),
+            edges("hidden", "hidden", [{"_target_": T + "edges.MultiScaleEdges", "x_hops": 1}], attr_cfg()),
+            edges("hidden", "data", [{"_target_": T + "edges.KNNEdges", "num_nearest_neighbours": 3}], attr_cfg()),
+        ],
+    )
+    np.testing.assert_array_equal(graph["hidden"].x.numpy().view(np.int32), g["hidden_x"].view(np.int32))
+    cut = canon(graph[("data", "to", "hidden")].edge_index)
+    ms = canon(graph[("hidden", "to", "hidden")].edge_index)
+    knn = canon(graph[("hidden", "to", "data")].edge_index)
+    assert (cut.shape[1], ms.shape[1], knn.shape[1]) == (62980, 81900, 120960)
+    np.testing.assert_array_equal(cut, g["cutoff_edge_index"])
+    np.testing.assert_array_equal(ms, g["multiscale_edge_index"])
+    want, info = R.knn_edges_canonical(g["hidden_x"], graph["data"].x.numpy(), 3)
+    np.testing.assert_array_equal(knn, want)
+    ref = g["knn3_edge_index"]
+    tied = info["tied_queries"]
+    np.testing.assert_array_equal(knn[:, ~np.isin(knn[1], tied)], ref[:, ~np.isin(ref[1], tied)])
+    stride = int(g["attr_sample_stride"])
+    for key, tag in ((("data", "to", "hidden"), "cutoff"), (("hidden", "to", "hidden"), "multiscale")):
+        got = by_canonical_order(graph, key, "edge_length")[::stride]
+        np.testing.assert_allclose(got, g[f"{tag}_edge_length_sample"], rtol=ATTR_RTOL, atol=0)
+        want_d = g[f"{tag}_edge_dirs_sample"]
+        got = by_canonical_order(graph, key, "edge_dirs")[::stride]
+        np.testing.assert_allclose(got, want_d, rtol=ATTR_RTOL, atol=ATTR_RTOL * np.abs(want_d).max())
+
+
+def test_device_resident_graph_stays_on_gpu(golden):
+    from anemoi_graphs_b200 import device as agx_device
+
+    g = golden("toy")
+    prev = agx_device.set_resident(True)
+    try:
+        nodes = {"data": latlon_nodes(g["data_lat_deg"], g["data_lon_deg"]), "hidden": tri_nodes(2)}
+        graph = build(
+            nodes, [edges("hidden", "data", [{"_target_": T + "edges.KNNEdges", "num_nearest_neighbours": 3}], attr_cfg())]
+        )
+    finally:
+        agx_device.set_resident(prev)
+    store = graph[("hidden", "to", "data")]
+    assert graph["data"].x.is_cuda and store.edge_index.is_cuda and store.edge_length.is_cuda and store.edge_dirs.is_cuda
+    np.testing.assert_array_equal(canon(store.edge_index), canon(g["knn3_edge_index"]))
+
+
+def test_clean_save_reload(tmp_path, golden):
+    """tests/test_create.py:20-56 of the reference: dtypes, no private attributes after clean, file reloads."""
+    from anemoi_graphs_b200.create import GraphCreator
+
+    g = golden("toy")
+    recipe = {
+        "nodes": {"data": latlon_nodes(g["data_lat_deg"], g["data_lon_deg"]), "hidden": tri_nodes(2)},
+        "edges": [
+            edges("hidden", "data", [{"_target_": T + "edges.KNNEdges", "num_nearest_neighbours": 3}], attr_cfg()),
+            edges("hidden", "hidden", [{"_target_": T + "edges.MultiScaleEdges", "x_hops": 1}], attr_cfg()),
+        ],
+    }
+    path = tmp_path / "graph.pt"
+    graph = GraphCreator(recipe).create(save_path=path)
+    for name in graph.node_types:
+        assert graph[name].x.dtype == torch.float32
+        assert not [a for a in graph[name] if a.startswith("_")]
+    for key in graph.edge_types:
+        assert graph[key].edge_index.dtype == torch.int32
+        assert not [a for a in graph[key] if a.startswith("_")]
+        for a in ("edge_length", "edge_dirs"):
+            assert graph[key][a].dtype == torch.float32
+    loaded = torch.load(path, weights_only=False)
+    assert loaded.node_types == graph.node_types and loaded.edge_types == graph.edge_types
+    np.testing.assert_array_equal(
+        loaded[("hidden", "to", "data")].edge_index.numpy(), graph[("hidden", "to", "data")].edge_index.numpy()
+    )
+
+
+def test_attribute_api(golden):
+    """tests/edges/test_edge_attributes.py of the reference + values."""
+    from anemoi_graphs_b200.edges.attributes import EdgeDirection, EdgeLength
+    from anemoi_graphs_b200.graph import HeteroData
+
+    g = golden("toy")
+    graph = HeteroData()
+    graph["data"].x = torch.from_numpy(g["data_x"])
+    graph["hidden"].x = torch.from_numpy(g["hidden_x"])
+    graph[("hidden", "to", "data")].edge_index = torch.from_numpy(g["knn3_edge_index"])
+    key = ("hidden", "to", "data")
+    for norm in ["l1", "l2", "unit-max", "unit-std"]:
+        for rot in (True, False):
+            v = EdgeDirection(norm=norm, luse_rotated_features=rot).compute(graph, key)
+            assert isinstance(v, torch.Tensor) and v.dtype == torch.float32
+        v = EdgeLength(norm=norm).compute(graph, key)
+        n = norm.replace("-", "_")
+        np.testing.assert_allclose(v.numpy(), g[f"knn3_len_{n}"], rtol=ATTR_RTOL, atol=0)
+    v = EdgeLength(norm="unit-max", invert=True).compute(graph, key)
+    np.testing.assert_allclose(v.numpy(), g["knn3_len_inv_unit_max"], rtol=0, atol=ATTR_RTOL)
+    with pytest.raises(AssertionError):
+        EdgeLength().compute(graph, ("hidden", "to", "nope"))
+    with pytest.raises(ValueError):
+        EdgeLength(norm="bogus").compute(graph, key)
