@@ -238,21 +238,36 @@ __global__ void __launch_bounds__(ATTR_THREADS) k_edge_attrs(
     }
 }
 
-// Fold the per-block partials in block order (deterministic) into stats[8] =
-// {len sum, sumsq, min, max, dir sum, sumsq, min, max}.
-__global__ void k_attr_fold(const double* __restrict__ ws, int n_blocks, double* __restrict__ stats) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+// Fold the per-block partials into stats[8] = {len sum, sumsq, min, max, dir sum, sumsq, min, max}.
+// One 256-thread block: thread t folds partials t, t+256, ... in order, then a fixed shuffle/shared tree -
+// the association order depends only on n_blocks, so the result is reproducible run to run.
+__global__ void __launch_bounds__(256) k_attr_fold(const double* __restrict__ ws, int n_blocks, double* __restrict__ stats) {
     Stat4 L, D;
     L.init();
     D.init();
-    for (int b = 0; b < n_blocks; ++b) {
+    for (int b = threadIdx.x; b < n_blocks; b += 256) {
         const double* p = ws + (int64_t)ATTR_STAT_FIELDS * (2 + b);
         Stat4 l = {p[0], p[1], p[2], p[3]}, d = {p[4], p[5], p[6], p[7]};
         L.merge(l);
         D.merge(d);
     }
-    stats[0] = L.sum; stats[1] = L.sumsq; stats[2] = L.mn; stats[3] = L.mx;
-    stats[4] = D.sum; stats[5] = D.sumsq; stats[6] = D.mn; stats[7] = D.mx;
+    __shared__ Stat4 sm[2][8];
+    L = warp_reduce(L);
+    D = warp_reduce(D);
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) {
+        sm[0][warp] = L;
+        sm[1][warp] = D;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) {
+            L.merge(sm[0][w]);
+            D.merge(sm[1][w]);
+        }
+        stats[0] = L.sum; stats[1] = L.sumsq; stats[2] = L.mn; stats[3] = L.mx;
+        stats[4] = D.sum; stats[5] = D.sumsq; stats[6] = D.mn; stats[7] = D.mx;
+    }
 }
 
 // Global statistics -> normalisation parameters (normalise.py:33-52).
@@ -323,7 +338,7 @@ extern "C" int agx_edge_attrs_stats(const int32_t* edge_src, const int32_t* edge
             workspace);
         agx_note_launch(1);
     }
-    k_attr_fold<<<1, 32, 0, stream>>>(workspace, grid, stats);  // grid == 0: the empty statistics (a rank with no edges)
+    k_attr_fold<<<1, 256, 0, stream>>>(workspace, grid, stats);  // grid == 0: the empty statistics (a rank with no edges)
     AGX_LAUNCH_OK();
     agx_note_launch(1);
     return AGX_OK;

@@ -15,6 +15,7 @@
 // ------------------------------------------------------------------------------------------------
 void agx_set_error(const char* fmt, ...);
 void agx_note_launch(int n);  // bench.py "gpu_launches" accounting
+void agx_pool_keep_warm(void);  // raise the release threshold of the device's cudaMallocAsync pool (once)
 
 #define AGX_CUDA_OK(expr)                                                                   \
     do {                                                                                    \

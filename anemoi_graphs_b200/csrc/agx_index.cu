@@ -87,6 +87,7 @@ extern "C" int agx_index_build(const float* latlon, int64_t n, int cells_per_fac
     AGX_REQUIRE(n > 0 && latlon != nullptr, AGX_ERR_ARG, "agx_index_build: need n > 0 reference points (got %lld)", (long long)n);
     AGX_REQUIRE(n < (int64_t)2147483647, AGX_ERR_ARG, "agx_index_build: n must fit int32 (edge_index is int32)");
     AGX_REQUIRE(cells_per_face >= 0 && cells_per_face <= 2048, AGX_ERR_ARG, "agx_index_build: cells_per_face out of [0, 2048]");
+    agx_pool_keep_warm();
     int dev = 0;
     AGX_CUDA_OK(cudaGetDevice(&dev));
     int cells = cells_per_face > 0 ? cells_per_face : choose_cells(n, hint_k, hint_radius);

@@ -115,24 +115,38 @@ __global__ void k_ico_latlon(const double* __restrict__ vert, int64_t nv, float2
     }
 }
 
+struct IcoBase {
+    double v[36];
+    int32_t f[60];
+};
+
+__global__ void k_ico_base(IcoBase b, double* __restrict__ vert, int32_t* __restrict__ faces) {
+    int t = threadIdx.x;
+    if (t < 36) vert[t] = b.v[t];
+    if (t < 60) faces[t] = b.f[t];
+}
+
 extern "C" int agx_icosphere(int max_level, double* vertices, int32_t* faces_all, float* latlon, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     AGX_REQUIRE(max_level >= 0 && max_level <= 12, AGX_ERR_ARG, "agx_icosphere: level %d out of [0, 12]", max_level);
     AGX_REQUIRE(vertices && faces_all, AGX_ERR_ARG, "agx_icosphere: NULL buffer");
-    // trimesh.creation.icosahedron
-    const double t = (1.0 + sqrt(5.0)) / 2.0;
-    const double s = sqrt(2.0 + t);
-    const double raw[36] = {-1, t, 0, 1, t, 0, -1, -t, 0, 1, -t, 0, 0, -1, t, 0, 1, t,
-                            0, -1, -t, 0, 1, -t, t, 0, -1, t, 0, 1, -t, 0, -1, -t, 0, 1};
-    static const int32_t f0[60] = {0, 11, 5, 0, 5, 1, 0, 1, 7, 0, 7, 10, 0, 10, 11, 1, 5, 9, 5, 11, 4, 11, 10, 2, 10, 7, 6, 7, 1, 8,
-                                   3, 9, 4, 3, 4, 2, 3, 2, 6, 3, 6, 8, 3, 8, 9, 4, 9, 5, 2, 4, 11, 6, 2, 10, 8, 6, 7, 9, 8, 1};
-    double v0[36];
-    for (int i = 0; i < 36; ++i) v0[i] = raw[i] / s;
-    AGX_CUDA_OK(cudaMemcpyAsync(vertices, v0, sizeof(v0), cudaMemcpyHostToDevice, stream));
-    AGX_CUDA_OK(cudaMemcpyAsync(faces_all, f0, sizeof(f0), cudaMemcpyHostToDevice, stream));
-    AGX_CUDA_OK(cudaStreamSynchronize(stream));  // v0 lives on this stack frame
+    // trimesh.creation.icosahedron: the tables travel as a kernel argument (no host staging, no sync)
+    IcoBase base0;
+    {
+        const double t = (1.0 + sqrt(5.0)) / 2.0;
+        const double s = sqrt(2.0 + t);
+        const double raw[36] = {-1, t, 0, 1, t, 0, -1, -t, 0, 1, -t, 0, 0, -1, t, 0, 1, t,
+                                0, -1, -t, 0, 1, -t, t, 0, -1, t, 0, 1, -t, 0, -1, -t, 0, 1};
+        static const int32_t f0[60] = {0, 11, 5, 0, 5, 1, 0, 1, 7, 0, 7, 10, 0, 10, 11, 1, 5, 9, 5, 11, 4, 11, 10, 2, 10, 7, 6, 7, 1, 8,
+                                       3, 9, 4, 3, 4, 2, 3, 2, 6, 3, 6, 8, 3, 8, 9, 4, 9, 5, 2, 4, 11, 6, 2, 10, 8, 6, 7, 9, 8, 1};
+        for (int i = 0; i < 36; ++i) base0.v[i] = raw[i] / s;
+        for (int i = 0; i < 60; ++i) base0.f[i] = f0[i];
+    }
+    k_ico_base<<<1, 64, 0, stream>>>(base0, vertices, faces_all);
+    agx_note_launch(1);
 
     int64_t nv_max = ico_nv(max_level);
+    agx_pool_keep_warm();
     int* cnt = nullptr;
     int32_t* lower = nullptr;
     int64_t* base = nullptr;
@@ -279,6 +293,7 @@ static int ms_run(int max_level, const int32_t* faces_all, const int32_t* levels
                   int32_t* scratch, cudaStream_t stream) {
     MsLevels lv;
     lv.n = n_levels;
+    agx_pool_keep_warm();
     int* deg_all = nullptr;
     int32_t* nb_all = nullptr;
     int64_t tot_v = 0;

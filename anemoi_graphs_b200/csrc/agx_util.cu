@@ -18,6 +18,23 @@ void agx_set_error(const char* fmt, ...) {
 
 void agx_note_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+// Scratch buffers come from the stream-ordered allocator.  Its default release threshold is 0: every
+// synchronisation hands freed blocks back to the driver and the next cudaMallocAsync pays for a fresh
+// mapping (milliseconds for the 100 MB binning buffers).  Keep the pool warm instead.
+void agx_pool_keep_warm(void) {
+    static std::atomic<unsigned> done_mask{0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 32) return;
+    unsigned bit = 1u << dev;
+    if (done_mask.load(std::memory_order_relaxed) & bit) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    done_mask.fetch_or(bit, std::memory_order_relaxed);
+}
+
 extern "C" const char* agx_last_error(void) { return g_err; }
 extern "C" int agx_abi_version(void) { return AGX_ABI_VERSION; }
 extern "C" int64_t agx_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
@@ -124,6 +141,7 @@ extern "C" int agx_exclusive_scan(const int32_t* counts, int64_t n, int64_t* off
     }
     int64_t n_tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
     int64_t* tmp = nullptr;
+    agx_pool_keep_warm();
     AGX_CUDA_OK(cudaMallocAsync(&tmp, (n_tiles + 1) * sizeof(int64_t), stream));
     k_scan_tile_sums<<<(unsigned)n_tiles, SCAN_THREADS, 0, stream>>>(counts, n, tmp);
     k_scan_of_sums<<<1, SCAN_THREADS, 0, stream>>>(tmp, n_tiles, tmp + n_tiles);
@@ -188,6 +206,7 @@ extern "C" int agx_max_positive(const double* values, int64_t n, double* out_val
     AGX_REQUIRE(n >= 0 && out_value && out_index, AGX_ERR_ARG, "agx_max_positive: bad arguments");
     int blocks = agx_grid(n, 256, 4);
     MaxPos* part = nullptr;
+    agx_pool_keep_warm();
     AGX_CUDA_OK(cudaMallocAsync(&part, (blocks + 1) * sizeof(MaxPos), stream));
     k_max_positive<<<blocks, 256, 0, stream>>>(values, n, part, 0, nullptr);
     k_max_positive<<<1, 256, 0, stream>>>(nullptr, blocks, part + blocks, 1, part);

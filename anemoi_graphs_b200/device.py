@@ -89,15 +89,36 @@ def maybe_flush() -> None:
         flush()
 
 
+_copy_streams: dict = {}
+
+
+def _copy_stream(device: torch.device) -> torch.cuda.Stream:
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    if key not in _copy_streams:
+        _copy_streams[key] = torch.cuda.Stream(device=device)
+    return _copy_streams[key]
+
+
 def to_host(t: torch.Tensor) -> torch.Tensor:
-    """Asynchronous copy of a CUDA tensor into a pinned host tensor (awaited by ``flush``)."""
+    """Asynchronous copy of a CUDA tensor into a pinned host tensor (awaited by ``flush``).
+
+    The copy runs on a dedicated stream behind an event recorded on the producing stream, so the PCIe transfer
+    of one edge set overlaps the kernels of the next."""
     if not t.is_cuda:
         return t
     out = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
-    out.copy_(t, non_blocking=True)
-    ev = torch.cuda.Event()
-    ev.record()
-    _pending.append(ev)
+    if t.numel() == 0:
+        return out
+    ready = torch.cuda.Event()
+    ready.record()
+    side = _copy_stream(t.device)
+    with torch.cuda.stream(side):
+        side.wait_event(ready)
+        out.copy_(t, non_blocking=True)
+        done = torch.cuda.Event()
+        done.record(side)
+    t.record_stream(side)
+    _pending.append(done)
     return out
 
 
@@ -127,12 +148,19 @@ EDGE_ATTR = "_agx_edge_index"
 
 def node_state(nodes) -> NodeState:
     """Device copy of ``nodes.x`` (uploaded once per node set; re-uploaded if ``x`` was replaced or modified)."""
-    flush()  # x may be a pinned tensor one of our own copies is still filling
     x = nodes["x"]
     st = nodes.get(STATE_ATTR, None) if hasattr(nodes, "get") else None
     if isinstance(st, NodeState) and st.key == _key(x):
         return st
+    flush()  # x may be a pinned tensor one of our own copies is still filling
     st = NodeState(key=_key(x), x=to_device(x, torch.float32))
+    nodes[STATE_ATTR] = st
+    return st
+
+
+def seed_node_state(nodes, x_dev: torch.Tensor) -> NodeState:
+    """Install an already-resident device copy of ``nodes.x`` (e.g. coordinates generated on the GPU)."""
+    st = NodeState(key=_key(nodes["x"]), x=x_dev.contiguous())
     nodes[STATE_ATTR] = st
     return st
 

@@ -31,9 +31,6 @@ class DeviceMesh:
         return {"icosphere": None, "node_ordering": self.node_ordering}
 
 
-_ICO_CACHE: dict = {}
-
-
 def get_icosphere(resolution: int) -> ops.Icosphere:
     """Device icosphere of ``resolution`` (all levels 0..resolution)."""
     return ops.Icosphere(int(resolution))
@@ -44,37 +41,42 @@ def get_latlon_coords_icosphere(resolution: int) -> np.ndarray:
     return get_icosphere(resolution).latlon.cpu().numpy()
 
 
+def _ordering_of(latlon_dev: torch.Tensor) -> np.ndarray:
+    """Host node ordering of device coordinates: one (2, N) column-major copy, two numpy argsorts."""
+    soa = latlon_dev.t().contiguous().cpu().numpy()
+    return get_coordinates_ordering(lat=soa[0], lon=soa[1])
+
+
 def create_tri_nodes(resolution: int, area_mask_builder=None):
     """Global (or area-limited) mesh nodes from a refined icosahedron (tri_icosahedron.py:24-58).
 
-    Returns ``(mesh, coords_rad, node_ordering)``: the device mesh, the float32 vertex coordinates (not
-    ordered) and the order that sorts them by latitude and longitude."""
+    Returns ``(mesh, coords_rad, node_ordering)``: the device mesh, the float32 vertex coordinates (CUDA tensor,
+    not ordered) and the order that sorts them by latitude and longitude (numpy, host)."""
     ico = get_icosphere(resolution)
-    coords_rad = ico.latlon.cpu().numpy()
-    node_ordering = get_coordinates_ordering(coords_rad)
+    node_ordering = _ordering_of(ico.latlon)
 
     if area_mask_builder is not None:
         area_mask = area_mask_builder.get_mask_device(ico.latlon).cpu().numpy()
         node_ordering = node_ordering[area_mask[node_ordering]]
 
-    return DeviceMesh(ico, node_ordering), coords_rad, node_ordering
+    return DeviceMesh(ico, node_ordering), ico.latlon, node_ordering
 
 
 def create_stretched_tri_nodes(base_resolution: int, lam_resolution: int, area_mask_builder=None):
     """Global mesh with two resolution levels (tri_icosahedron.py:61-105): ``base_resolution`` outside the
     area of interest, ``lam_resolution`` inside."""
     assert area_mask_builder is not None, "AOI mask builder must be provided to build refined grid."
-    ico = get_icosphere(max(base_resolution, lam_resolution))
-    lam = ico if lam_resolution == ico.max_level else get_icosphere(lam_resolution)
-    n_base = ops.ico_num_vertices(base_resolution)
-    # lower levels are prefixes of the finest one; if base > lam (unusual) generate it separately
-    base_latlon = ico.latlon[:n_base] if base_resolution <= ico.max_level else get_icosphere(base_resolution).latlon
+    lam = get_icosphere(lam_resolution)
+    # lower levels are prefixes of the finer one; a base level above the lam level (unusual) is generated apart
+    if base_resolution <= lam_resolution:
+        base_latlon = lam.latlon[: ops.ico_num_vertices(base_resolution)]
+    else:
+        base_latlon = get_icosphere(base_resolution).latlon
     base_area_mask = ~area_mask_builder.get_mask_device(base_latlon)
-    lam_latlon = lam.latlon[: ops.ico_num_vertices(lam_resolution)]
-    lam_area_mask = area_mask_builder.get_mask_device(lam_latlon)
+    lam_area_mask = area_mask_builder.get_mask_device(lam.latlon)
 
-    coords_rad = torch.cat([base_latlon[base_area_mask], lam_latlon[lam_area_mask]]).cpu().numpy()
-    node_ordering = get_coordinates_ordering(coords_rad)
+    coords_rad = torch.cat([base_latlon[base_area_mask], lam.latlon[lam_area_mask]])
+    node_ordering = _ordering_of(coords_rad)
     return DeviceMesh(lam, node_ordering), coords_rad, node_ordering
 
 

@@ -15,6 +15,7 @@ from abc import abstractmethod
 import numpy as np
 import torch
 
+from ... import device as _device
 from ...generate.masks import KNNAreaMaskBuilder
 from ...generate.tri_icosahedron import create_stretched_tri_nodes
 from ...generate.tri_icosahedron import create_tri_nodes
@@ -55,7 +56,17 @@ class IcosahedralNodes(BaseNodeBuilder, ABC):
     def get_coordinates(self) -> torch.Tensor:
         """float32 (num_nodes, 2) coordinates in radians, in graph order."""
         self.nx_graph, coords_rad, self.node_ordering = self.create_nodes()
-        return torch.tensor(coords_rad[self.node_ordering], dtype=torch.float32)
+        order = torch.from_numpy(np.ascontiguousarray(self.node_ordering)).to(coords_rad.device, non_blocking=True)
+        self._x_device = coords_rad[order]  # == coords_rad[node_ordering], gathered on the device
+        return self._x_device if _device.is_resident() else _device.to_host(self._x_device)
+
+    def register_nodes(self, graph):
+        graph = super().register_nodes(graph)
+        nodes = graph[self.name]
+        # the device copy already exists: seed the per-node-set state so no builder uploads x again
+        _device.seed_node_state(nodes, self._x_device)
+        _device.maybe_flush()
+        return graph
 
     @abstractmethod
     def create_nodes(self) -> tuple[object, np.ndarray, np.ndarray]: ...

@@ -17,6 +17,9 @@ product code is on that path, only ``anemoi_graphs_b200.grids`` for the syntheti
                      samples + float64 sums.
 * ``tri_nodes.npz``  TriNodes coordinates + node ordering for resolutions 0-4, multi-scale edges
                      for resolution 3 with x_hops 1, 2, 3.
+* ``lam.npz``        config 4 in miniature: limited-area patch + global points with a ``cutout`` mask;
+                     LimitedAreaTriNodes / StretchedTriNodes coordinates, multi-scale edges (x_hops 1, 2),
+                     masked KNN and cut-off edges.
 * ``attr_vectors.npz`` SURVEY appendix-B style edge cases for EdgeLength / EdgeDirection.
 """
 
@@ -211,6 +214,69 @@ def make_tri() -> None:
     print("tri_nodes.npz", {k: v.shape for k, v in out.items()})
 
 
+def make_lam() -> None:
+    """Config 4 in miniature: a 40 x 40 limited-area patch (25 km spacing, centred 50N 10E) plus 1 500 global
+    points; ``cutout`` marks the patch.  LimitedAreaTriNodes(4) and StretchedTriNodes(2 -> 5) hidden meshes with
+    MultiScaleEdges (x_hops 1 and 2), KNN k=4 decoder and CutOff encoder through the reference's own classes."""
+    from torch_geometric.data import HeteroData  # shim
+
+    from anemoi.graphs.edges import CutOffEdges, KNNEdges, MultiScaleEdges
+    from anemoi.graphs.nodes import LimitedAreaTriNodes, StretchedTriNodes
+
+    lam_lat, lam_lon = grids.lam_patch(40, 40, 25.0)
+    glob_lat, glob_lon = grids.uniform_sphere(1500, seed=3)
+    lat = np.concatenate([lam_lat, glob_lat])
+    lon = np.concatenate([lam_lon, glob_lon])
+    x = grids.latlon_deg_to_x(lat, lon)
+    cutout = torch.zeros((x.shape[0], 1), dtype=torch.bool)
+    cutout[: lam_lat.size] = True
+    out: dict[str, np.ndarray] = {"data_x": x.numpy(), "cutout": cutout.numpy()}
+
+    def base_graph():
+        g = HeteroData()
+        g["data"].x = x
+        g["data"].node_type = "LatLonNodes"
+        g["data"]["cutout"] = cutout
+        return g
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        # limited-area mesh
+        g = base_graph()
+        g = LimitedAreaTriNodes(4, "data", "lam", mask_attr_name="cutout", margin_radius_km=100.0).update_graph(g, {})
+        out["lam_x"] = g["lam"].x.numpy()
+        out["lam_node_ordering"] = np.asarray(g["lam"]["_node_ordering"], dtype=np.int64)
+        for hops in (1, 2):
+            gg = base_graph()
+            gg = LimitedAreaTriNodes(4, "data", "lam", mask_attr_name="cutout", margin_radius_km=100.0).update_graph(gg, {})
+            MultiScaleEdges("lam", "lam", hops).update_graph(gg)
+            out[f"lam_hops{hops}_edge_index"] = canon(gg[("lam", "to", "lam")].edge_index.numpy())
+        KNNEdges("lam", "data", 4, target_mask_attr_name="cutout").update_graph(g)
+        CutOffEdges("data", "lam", 0.6, source_mask_attr_name="cutout").update_graph(g)
+        out["lam_knn4_edge_index"] = g[("lam", "to", "data")].edge_index.numpy()
+        out["lam_cutoff_edge_index"] = g[("data", "to", "lam")].edge_index.numpy()
+        # stretched mesh
+        g = base_graph()
+        g = StretchedTriNodes(2, 5, "str", "data", "cutout", margin_radius_km=100.0).update_graph(g, {})
+        out["str_x"] = g["str"].x.numpy()
+        out["str_node_ordering"] = np.asarray(g["str"]["_node_ordering"], dtype=np.int64)
+        for hops in (1, 2):
+            gg = base_graph()
+            gg = StretchedTriNodes(2, 5, "str", "data", "cutout", margin_radius_km=100.0).update_graph(gg, {})
+            MultiScaleEdges("str", "str", hops).update_graph(gg)
+            out[f"str_hops{hops}_edge_index"] = canon(gg[("str", "to", "str")].edge_index.numpy())
+        KNNEdges("str", "data", 4).update_graph(g)
+        CutOffEdges("data", "str", 0.6).update_graph(g)
+        out["str_knn4_edge_index"] = g[("str", "to", "data")].edge_index.numpy()
+        out["str_cutoff_edge_index"] = g[("data", "to", "str")].edge_index.numpy()
+        from anemoi.graphs.utils import get_grid_reference_distance
+
+        out["str_reference_distance"] = np.array(get_grid_reference_distance(g["str"].x), dtype=np.float64)
+        out["lam_reference_distance"] = np.array(get_grid_reference_distance(torch.from_numpy(out["lam_x"])), dtype=np.float64)
+    np.savez_compressed(OUT / "lam.npz", **out)
+    print("lam.npz", {k: v.shape for k, v in out.items()})
+
+
 def make_attr_vectors() -> None:
     h = np.float32(np.pi / 2)
     src = np.array(
@@ -234,7 +300,8 @@ def make_attr_vectors() -> None:
 
 if __name__ == "__main__":
     OUT.mkdir(parents=True, exist_ok=True)
-    make_attr_vectors()
-    make_tri()
-    make_toy()
-    make_o96()
+    only = sys.argv[1:]
+    for name, fn in (("attr_vectors", make_attr_vectors), ("tri", make_tri), ("toy", make_toy), ("o96", make_o96),
+                     ("lam", make_lam)):  # fmt: skip
+        if not only or name in only:
+            fn()

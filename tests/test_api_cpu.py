@@ -137,3 +137,18 @@ def test_shard_ranges_partition():
             assert r[0][0] == 0 and r[-1][1] == n
             assert all(a[1] == b[0] for a, b in zip(r, r[1:]))
             assert max(b - a for a, b in r) - min(b - a for a, b in r) <= 1
+
+
+def test_node_ordering_equals_reference_expression():
+    """generate/utils.py:30-33 of the reference, restated in oracle/ref_path.py, vs the contiguous-column form."""
+    from anemoi_graphs_b200.generate.utils import get_coordinates_ordering
+    from oracle import ref_path as R
+    from oracle import trimesh_icosphere as TM
+
+    for res in range(7):
+        coords = R.cartesian_to_latlon_rad(TM.icosphere(res)[0])
+        want = R.coordinates_ordering(coords)
+        np.testing.assert_array_equal(get_coordinates_ordering(coords), want)
+        np.testing.assert_array_equal(
+            get_coordinates_ordering(lat=np.ascontiguousarray(coords[:, 0]), lon=np.ascontiguousarray(coords[:, 1])), want
+        )

@@ -1,0 +1,76 @@
+"""World-size-2 gloo tests (CPU) of the host logic of the multi-GPU path: shard ranges, the in-place
+variable-length all-gather of per-rank edge blocks, and the rank-order combination of the attribute
+statistics.  The kernels themselves need a GPU; here the per-rank blocks are produced with numpy."""
+
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from anemoi_graphs_b200 import device as agx_device
+
+
+def _free_port() -> int:
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank: int, world: int, port: int, out_dir: str) -> None:
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        assert agx_device.world() == (rank, world)
+        # --- KNN-like fixed-size blocks: 11 queries x k=3 --------------------------------------------
+        nq, k = 11, 3
+        lo, hi = agx_device.shard_range(nq)
+        full = torch.full((2, nq * k), -1, dtype=torch.int32)
+        q = torch.arange(lo, hi, dtype=torch.int32).repeat_interleave(k)
+        full[0, lo * k : hi * k] = 100 + q * 7 % 13
+        full[1, lo * k : hi * k] = q
+        counts = [(b - a) * k for a, b in (agx_device.shard_range(nq, r, world) for r in range(world))]
+        agx_device.all_gather_v(full, counts, dim=1)
+        allq = torch.arange(nq, dtype=torch.int32).repeat_interleave(k)
+        assert torch.equal(full[1], allq) and torch.equal(full[0], 100 + allq * 7 % 13)
+        # --- cut-off-like variable-size blocks ------------------------------------------------------
+        mine = 5 if rank == 0 else 2
+        counts = agx_device.all_gather_counts(mine, torch.device("cpu"))
+        assert counts == [5, 2]
+        full = torch.zeros((2, sum(counts)), dtype=torch.int32)
+        off = sum(counts[:rank])
+        full[:, off : off + mine] = rank + 1
+        agx_device.all_gather_v(full, counts, dim=1)
+        assert full[0].tolist() == [1] * 5 + [2] * 2 and full[1].tolist() == [1] * 5 + [2] * 2
+        # --- an empty rank block --------------------------------------------------------------------
+        counts = agx_device.all_gather_counts(0 if rank == 1 else 4, torch.device("cpu"))
+        full = torch.zeros((sum(counts), 2), dtype=torch.float32)
+        if rank == 0:
+            full[:4] = 3.5
+        agx_device.all_gather_v(full, counts, dim=0)
+        assert torch.equal(full, torch.full((4, 2), 3.5))
+        # --- attribute statistics: sums add, minima / maxima combine, identical on every rank --------
+        rng = np.random.default_rng(5)
+        v = rng.random(1000)
+        lo, hi = agx_device.shard_range(1000)
+        part = v[lo:hi]
+        st = torch.tensor([part.sum(), (part**2).sum(), part.min(), part.max()] * 2, dtype=torch.float64)
+        tot = agx_device.all_gather_stats(st)
+        np.testing.assert_allclose(tot[0].item(), v.sum(), rtol=1e-14)
+        np.testing.assert_allclose(tot[5].item(), (v**2).sum(), rtol=1e-14)
+        assert tot[2].item() == v.min() and tot[7].item() == v.max()
+        torch.save(tot, os.path.join(out_dir, f"stats{rank}.pt"))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_two_rank_gather_and_stats(tmp_path):
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    a, b = torch.load(tmp_path / "stats0.pt"), torch.load(tmp_path / "stats1.pt")
+    assert torch.equal(a, b)  # bitwise identical normalisation constants on every rank
