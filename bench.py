@@ -209,6 +209,7 @@ def bench_b200(args) -> dict:
         start.record()
         out = None
         for _ in range(steps):
+            out = None  # drop the previous step's graph first: one live output set, as in the warm-up
             out = fn()
         end.record()
         torch.cuda.synchronize()
@@ -222,9 +223,12 @@ def bench_b200(args) -> dict:
 
     # ---- device-resident: `value` -------------------------------------------------------------------
     agx_device.set_resident(True)
+    graph = None
     for _ in range(args.warmup):
+        graph = None
         graph = run_step(creator, x_dev)
     n_edges = graph_edges(graph)
+    graph = None
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
@@ -244,9 +248,11 @@ def bench_b200(args) -> dict:
 
     # ---- end to end with host buffers: `e2e` ---------------------------------------------------------
     agx_device.set_resident(False)
-    for _ in range(max(2, args.warmup // 2)):
+    for _ in range(args.warmup):
+        graph = None
         graph = run_step(creator, x_host)
     d2h = output_bytes(graph)
+    graph = None
     e2e_steps = max(1, min(args.steps, 5))
     ms_e2e, graph = timed(lambda: run_step(creator, x_host), e2e_steps)
     e2e_value = n_edges / (ms_e2e / e2e_steps * 1e-3)
