@@ -45,12 +45,12 @@ SIGNATURES = {
     "agx_edge_attrs_stats": (
         c_int,
         [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
-         c_void_p, c_void_p],
+         c_void_p, c_void_p, c_void_p, c_void_p],
     ),  # fmt: skip
     "agx_edge_attrs_apply": (
         c_int,
         [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int,
-         c_int, c_void_p, c_void_p, c_int64, c_void_p, c_void_p],
+         c_int, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p],
     ),  # fmt: skip
     "agx_icosphere": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "agx_multiscale_tri_count": (

@@ -80,6 +80,26 @@ extern "C" int agx_node_tables(const float* latlon, int64_t n, float* xyzc, doub
 // ------------------------------------------------------------------------------------------------
 // per-edge raw values
 // ------------------------------------------------------------------------------------------------
+// atan2(ra, rb) for ra, rb >= 0 in float64.  Edges are short, so ra/rb = tan(d/2) is tiny: below 1/16 the odd
+// Taylor series to t^11 is exact to < 3e-16 relative (next term t^12/13) and costs a handful of DFMAs instead of
+// the library's ~150-instruction path.  The quotient uses a float reciprocal seed + two Newton steps (1e-14
+// relative); the result is rounded to float32 by the caller, so this cannot be told from the exact quotient.
+__device__ __forceinline__ double atan2_short(double ra, double rb) {
+    if (ra <= 0.0625 * rb) {
+        double r = (double)__frcp_rn((float)rb);
+        r = r * (2.0 - rb * r);
+        r = r * (2.0 - rb * r);
+        double t = ra * r, t2 = t * t;
+        double p = fma(t2, -1.0 / 11.0, 1.0 / 9.0);
+        p = fma(t2, -p, 1.0 / 7.0);
+        p = fma(t2, -p, 1.0 / 5.0);
+        p = fma(t2, -p, 1.0 / 3.0);
+        p = fma(t2, -p, 1.0);
+        return t * p;
+    }
+    return atan2(ra, rb);  // long edges, and NaN (a > 1 in float32: antipodal pairs, as in the reference)
+}
+
 // utils.haversine_distance in float32 (numpy), last step in float64 then rounded.
 __device__ __forceinline__ float edge_length_raw(float2 s, float cs, float2 t, float ct) {
     float dlat = __fsub_rn(t.x, s.x), dlon = __fsub_rn(t.y, s.y);
@@ -88,12 +108,12 @@ __device__ __forceinline__ float edge_length_raw(float2 s, float cs, float2 t, f
     agx_np_sincosf(__fmul_rn(dlon, 0.5f), sh_lon, unused);
     float a = __fadd_rn(__fmul_rn(sh_lat, sh_lat), __fmul_rn(__fmul_rn(cs, ct), __fmul_rn(sh_lon, sh_lon)));
     float ra = __fsqrt_rn(a), rb = __fsqrt_rn(__fsub_rn(1.0f, a));
-    return __fmul_rn(2.0f, (float)atan2((double)ra, (double)rb));
+    return __fmul_rn(2.0f, (float)atan2_short((double)ra, (double)rb));
 }
 
 // compute_directions (edges/directional.py:40-65) for one edge; q = R(target) * source_xyz
-__device__ __forceinline__ void edge_direction_rotated(float4 sxyz, double4 tq, double& o0, double& o1) {
-    double x = tq.x, y = tq.y, w = tq.z;  // z component of the quaternion is exactly 0
+__device__ __forceinline__ void edge_direction_rotated(float4 sxyz, double x, double y, double w, double& o0, double& o1) {
+    // z component of the quaternion is exactly 0
     double x2 = x * x, y2 = y * y, w2 = w * w, xy = x * y, yw = y * w, xw = x * w;
     double sx = (double)sxyz.x, sy = (double)sxyz.y, sz = (double)sxyz.z;
     // scipy as_matrix rows 0 and 1 with z = 0
@@ -110,7 +130,10 @@ __device__ __forceinline__ void edge_direction_rotated(float4 sxyz, double4 tq, 
     }
     double inv = rsqrt(vn);
     double d0 = qy * inv, d1 = -qx * inv;
-    double inv2 = rsqrt(d0 * d0 + d1 * d1);  // the final renormalisation (edges/directional.py:65)
+    // the final renormalisation (edges/directional.py:65): |d|^2 = 1 + O(1e-16), so one Newton step of
+    // rsqrt about 1 (1.5 - 0.5 s) is exact to 1e-31
+    double inv2 = fma(-0.5, d0 * d0 + d1 * d1, 1.5);
+    if (!(vn > 0.0)) inv2 = rsqrt(d0 * d0 + d1 * d1);  // NaN / inf propagate as the reference's division would
     o0 = d0 * inv2;
     o1 = d1 * inv2;
 }
@@ -150,69 +173,49 @@ __device__ __forceinline__ Stat4 warp_reduce(Stat4 s) {
     return s;
 }
 
-struct NormParams {  // out = (v - shift) * mul   (float64 path)   /   (v - shift) / div  (float32 path)
-    double shift, mul;
-    float shift32, div32;
-};
-
-template <bool STATS>
+// MODE 0: statistics only (a shard whose outputs are written later by the apply pass of another call)
+// MODE 1: write raw float32 values (and, if STATS, reduce them) - the normalisation follows as an in-place
+//         scaling pass (k_attr_scale), so the trigonometry and the gathers run ONCE per edge
+template <bool STATS, bool WRITE>
 __global__ void __launch_bounds__(ATTR_THREADS) k_edge_attrs(
     const int32_t* __restrict__ esrc, const int32_t* __restrict__ edst, int64_t n_edges,
     const float2* __restrict__ s_ll, const float4* __restrict__ s_xyzc, const float2* __restrict__ t_ll,
-    const float4* __restrict__ t_xyzc, const double2* __restrict__ t_quat, int want_len, int len_invert,
+    const float4* __restrict__ t_xyzc, const double2* __restrict__ t_quat, int want_len, int len_invert_now,
     float* __restrict__ out_len, int want_dir, int dir_rotated, float* __restrict__ out_dir,
     double* __restrict__ ws) {
     Stat4 st_len, st_dir;
     st_len.init();
     st_dir.init();
-    NormParams np_len, np_dir;
-    if (!STATS) {
-        np_len.shift32 = (float)ws[0];
-        np_len.div32 = (float)ws[1];
-        np_dir.shift = ws[2];
-        np_dir.mul = ws[3];
-        np_dir.shift32 = (float)ws[4];
-        np_dir.div32 = (float)ws[5];
-    }
-    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n_edges; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n_edges; e += stride) {
         int s = __ldg(esrc + e), t = __ldg(edst + e);
         float2 sl = __ldg(s_ll + s), tl = __ldg(t_ll + t);
         float4 sx = __ldg(s_xyzc + s);
         if (want_len) {
             float ct = __ldg(&t_xyzc[t].w);
             float v = edge_length_raw(sl, sx.w, tl, ct);
-            if (STATS) {
-                st_len.add((double)v);
-            } else {
-                v = __fdiv_rn(__fsub_rn(v, np_len.shift32), np_len.div32);
-                if (len_invert) v = __fsub_rn(1.0f, v);
-                out_len[e] = v;
-            }
+            if (STATS) st_len.add((double)v);
+            if (WRITE) out_len[e] = len_invert_now ? __fsub_rn(1.0f, v) : v;
         }
         if (want_dir) {
             if (dir_rotated) {
-                double2 qa = __ldg(t_quat + 2 * (int64_t)t), qb = __ldg(t_quat + 2 * (int64_t)t + 1);
-                double4 tq = make_double4(qa.x, qa.y, qb.x, 0.0);
+                double2 qa = __ldg(t_quat + 2 * (int64_t)t);
+                double qw = __ldg(&t_quat[2 * (int64_t)t + 1].x);
                 double d0, d1;
-                edge_direction_rotated(sx, tq, d0, d1);
+                edge_direction_rotated(sx, qa.x, qa.y, qw, d0, d1);
                 if (STATS) {
                     st_dir.add(d0);
                     st_dir.add(d1);
-                } else {
-                    float2 o = make_float2((float)((d0 - np_dir.shift) * np_dir.mul), (float)((d1 - np_dir.shift) * np_dir.mul));
-                    reinterpret_cast<float2*>(out_dir)[e] = o;
                 }
+                if (WRITE) reinterpret_cast<float2*>(out_dir)[e] = make_float2((float)d0, (float)d1);
             } else {
                 // directional_edge_features(..., relative_to_rotated_target=False): loc2 - loc1 in float32
                 float d0 = __fsub_rn(tl.x, sl.x), d1 = __fsub_rn(tl.y, sl.y);
                 if (STATS) {
                     st_dir.add((double)d0);
                     st_dir.add((double)d1);
-                } else {
-                    float2 o = make_float2(__fdiv_rn(__fsub_rn(d0, np_dir.shift32), np_dir.div32),
-                                           __fdiv_rn(__fsub_rn(d1, np_dir.shift32), np_dir.div32));
-                    reinterpret_cast<float2*>(out_dir)[e] = o;
                 }
+                if (WRITE) reinterpret_cast<float2*>(out_dir)[e] = make_float2(d0, d1);
             }
         }
     }
@@ -235,6 +238,54 @@ __global__ void __launch_bounds__(ATTR_THREADS) k_edge_attrs(
             p[0] = st_len.sum; p[1] = st_len.sumsq; p[2] = st_len.mn; p[3] = st_len.mx;
             p[4] = st_dir.sum; p[5] = st_dir.sumsq; p[6] = st_dir.mn; p[7] = st_dir.mx;
         }
+    }
+}
+
+// In-place normalisation of the raw float32 attributes: out = (v - shift) / div (+ optional 1 - v).
+// EdgeLength and non-rotated directions are float32 arrays in the reference, so the division is float32
+// (normalise.py on a float32 array); rotated directions are float64 there and cast last, so the arithmetic is
+// float64 on the stored float32 value (one extra rounding, <= 6e-8 relative).  A flat array of n floats is
+// processed as 128-bit vectors between an aligned head and tail.
+template <bool F64>
+__device__ __forceinline__ float scale_one(float v, float shift32, float div32, double shift, double mul, int invert) {
+    float r = F64 ? (float)(((double)v - shift) * mul) : __fdiv_rn(__fsub_rn(v, shift32), div32);
+    return invert ? __fsub_rn(1.0f, r) : r;
+}
+
+template <bool F64>
+__device__ __forceinline__ void scale_array(float* __restrict__ a, int64_t n, float shift32, float div32, double shift,
+                                            double mul, int invert) {
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t head = ((16 - ((uintptr_t)a & 15)) & 15) >> 2;  // floats before the first 16-byte boundary
+    if (head > n) head = n;
+    int64_t n_vec = (n - head) >> 2;
+    float4* v4 = reinterpret_cast<float4*>(a + head);
+    for (int64_t i = tid; i < n_vec; i += stride) {
+        float4 v = v4[i];
+        v.x = scale_one<F64>(v.x, shift32, div32, shift, mul, invert);
+        v.y = scale_one<F64>(v.y, shift32, div32, shift, mul, invert);
+        v.z = scale_one<F64>(v.z, shift32, div32, shift, mul, invert);
+        v.w = scale_one<F64>(v.w, shift32, div32, shift, mul, invert);
+        v4[i] = v;
+    }
+    int64_t tail0 = head + (n_vec << 2);
+    for (int64_t i = tid; i < head + (n - tail0); i += stride) {
+        int64_t j = i < head ? i : tail0 + (i - head);
+        a[j] = scale_one<F64>(a[j], shift32, div32, shift, mul, invert);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_attr_scale(float* __restrict__ out_len, int64_t n_len, int len_scale,
+                                                     int len_invert, float* __restrict__ out_dir, int64_t n_dir,
+                                                     int dir_scale, int dir_f64, const double* __restrict__ ws) {
+    if (out_len != nullptr && (len_scale || len_invert))
+        scale_array<false>(out_len, n_len, len_scale ? (float)ws[0] : 0.0f, len_scale ? (float)ws[1] : 1.0f, 0.0, 1.0,
+                           len_invert);
+    if (out_dir != nullptr && dir_scale) {
+        if (dir_f64)
+            scale_array<true>(out_dir, n_dir, 0.0f, 1.0f, ws[2], ws[3], 0);
+        else
+            scale_array<false>(out_dir, n_dir, (float)ws[4], (float)ws[5], 0.0, 1.0, 0);
     }
 }
 
@@ -320,35 +371,77 @@ static inline int attrs_grid(int64_t n_edges) {
     return grid > ATTR_MAX_BLOCKS ? ATTR_MAX_BLOCKS : grid;
 }
 
+#define ATTR_KERNEL_ARGS                                                                                             \
+    edge_src, edge_dst, n_edges, (const float2*)src_latlon, (const float4*)src_xyzc, (const float2*)dst_latlon,      \
+        (const float4*)dst_xyzc, (const double2*)dst_quat
+
+// pass A: raw values of the local edges -> out_* (float32) and/or stats[8]
+static int attrs_raw(const int32_t* edge_src, const int32_t* edge_dst, int64_t n_edges, const float* src_latlon,
+                     const float* src_xyzc, const float* dst_latlon, const float* dst_xyzc, const double* dst_quat,
+                     int want_len, int len_invert_now, float* out_len, int want_dir, int dir_rotated, float* out_dir,
+                     bool write, double* stats, double* workspace, cudaStream_t stream) {
+    int grid = 0;
+    if (n_edges > 0 && (want_len || want_dir)) {
+        grid = attrs_grid(n_edges);
+        if (stats && write)
+            k_edge_attrs<true, true><<<grid, ATTR_THREADS, 0, stream>>>(ATTR_KERNEL_ARGS, want_len, len_invert_now, out_len,
+                                                                       want_dir, dir_rotated, out_dir, workspace);
+        else if (stats)
+            k_edge_attrs<true, false><<<grid, ATTR_THREADS, 0, stream>>>(ATTR_KERNEL_ARGS, want_len, 0, nullptr, want_dir,
+                                                                        dir_rotated, nullptr, workspace);
+        else
+            k_edge_attrs<false, true><<<grid, ATTR_THREADS, 0, stream>>>(ATTR_KERNEL_ARGS, want_len, len_invert_now, out_len,
+                                                                        want_dir, dir_rotated, out_dir, workspace);
+        agx_note_launch(1);
+    }
+    if (stats) {
+        k_attr_fold<<<1, 256, 0, stream>>>(workspace, grid, stats);  // grid == 0: the empty statistics
+        agx_note_launch(1);
+    }
+    AGX_LAUNCH_OK();
+    return AGX_OK;
+}
+
+// pass B: statistics -> parameters, in-place scaling of the raw values
+static int attrs_scale(int64_t n_edges, int len_norm, int len_invert, float* out_len, int dir_norm, int dir_rotated,
+                       float* out_dir, const double* stats, int64_t n_edges_global, double* workspace,
+                       cudaStream_t stream) {
+    int want_len = len_norm >= 0, want_dir = dir_norm >= 0;
+    bool len_scale = want_len && len_norm > 0, dir_scale = want_dir && dir_norm > 0;
+    if (n_edges == 0 || !(len_scale || dir_scale || (want_len && len_invert))) return AGX_OK;
+    k_attr_params<<<1, 32, 0, stream>>>(workspace, stats, n_edges_global, want_len ? len_norm : 0, want_dir ? dir_norm : 0);
+    int64_t work = (n_edges * (want_dir ? 2 : 1) + 3) / 4;
+    k_attr_scale<<<agx_grid(work, 256, 8), 256, 0, stream>>>(want_len ? out_len : nullptr, n_edges, len_scale, len_invert,
+                                                           want_dir ? out_dir : nullptr, 2 * n_edges, dir_scale,
+                                                           dir_rotated, workspace);
+    AGX_LAUNCH_OK();
+    agx_note_launch(2);
+    return AGX_OK;
+}
+
 extern "C" int agx_edge_attrs_stats(const int32_t* edge_src, const int32_t* edge_dst, int64_t n_edges,
                                     const float* src_latlon, const float* src_xyzc, const float* dst_latlon,
                                     const float* dst_xyzc, const double* dst_quat, int want_len, int want_dir,
-                                    int dir_rotated, double* stats, double* workspace, void* stream_) {
+                                    int dir_rotated, float* out_len, float* out_dir, double* stats, double* workspace,
+                                    void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     AGX_REQUIRE(stats != nullptr, AGX_ERR_ARG, "agx_edge_attrs_stats: stats is NULL");
     int rc = attrs_check(edge_src, edge_dst, n_edges, src_latlon, src_xyzc, dst_latlon, dst_xyzc, dst_quat, want_dir,
                          dir_rotated, workspace);
     if (rc) return rc;
-    int grid = 0;
-    if (n_edges > 0 && (want_len || want_dir)) {
-        grid = attrs_grid(n_edges);
-        k_edge_attrs<true><<<grid, ATTR_THREADS, 0, stream>>>(
-            edge_src, edge_dst, n_edges, (const float2*)src_latlon, (const float4*)src_xyzc, (const float2*)dst_latlon,
-            (const float4*)dst_xyzc, (const double2*)dst_quat, want_len, 0, nullptr, want_dir, dir_rotated, nullptr,
-            workspace);
-        agx_note_launch(1);
-    }
-    k_attr_fold<<<1, 256, 0, stream>>>(workspace, grid, stats);  // grid == 0: the empty statistics (a rank with no edges)
-    AGX_LAUNCH_OK();
-    agx_note_launch(1);
-    return AGX_OK;
+    AGX_REQUIRE(workspace != nullptr, AGX_ERR_ARG, "agx_edge_attrs_stats: workspace is NULL");
+    bool write = (want_len && out_len) || (want_dir && out_dir);
+    AGX_REQUIRE(!write || ((!want_len || out_len) && (!want_dir || out_dir)), AGX_ERR_ARG,
+                "agx_edge_attrs_stats: give every requested output buffer or none");
+    return attrs_raw(edge_src, edge_dst, n_edges, src_latlon, src_xyzc, dst_latlon, dst_xyzc, dst_quat, want_len, 0,
+                     out_len, want_dir, dir_rotated, out_dir, write, stats, workspace, stream);
 }
 
 extern "C" int agx_edge_attrs_apply(const int32_t* edge_src, const int32_t* edge_dst, int64_t n_edges,
                                     const float* src_latlon, const float* src_xyzc, const float* dst_latlon,
                                     const float* dst_xyzc, const double* dst_quat, int len_norm, int len_invert,
                                     float* out_len, int dir_norm, int dir_rotated, float* out_dir, const double* stats,
-                                    int64_t n_edges_global, double* workspace, void* stream_) {
+                                    int64_t n_edges_global, int raw_present, double* workspace, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     int want_len = len_norm >= 0, want_dir = dir_norm >= 0;
     AGX_REQUIRE(len_norm <= AGX_NORM_UNIT_STD && dir_norm <= AGX_NORM_UNIT_STD, AGX_ERR_ARG, "agx_edge_attrs: unknown norm code");
@@ -361,14 +454,13 @@ extern "C" int agx_edge_attrs_apply(const int32_t* edge_src, const int32_t* edge
     bool need_stats = (want_len && len_norm > 0) || (want_dir && dir_norm > 0);
     AGX_REQUIRE(!need_stats || stats, AGX_ERR_ARG, "agx_edge_attrs_apply: this normalisation needs the global statistics");
     AGX_REQUIRE(n_edges_global >= n_edges, AGX_ERR_ARG, "agx_edge_attrs_apply: n_edges_global < n_edges");
-    k_attr_params<<<1, 32, 0, stream>>>(workspace, stats, n_edges_global, want_len ? len_norm : 0, want_dir ? dir_norm : 0);
-    k_edge_attrs<false><<<attrs_grid(n_edges), ATTR_THREADS, 0, stream>>>(
-        edge_src, edge_dst, n_edges, (const float2*)src_latlon, (const float4*)src_xyzc, (const float2*)dst_latlon,
-        (const float4*)dst_xyzc, (const double2*)dst_quat, want_len, len_invert, out_len, want_dir, dir_rotated, out_dir,
-        workspace);
-    AGX_LAUNCH_OK();
-    agx_note_launch(2);
-    return AGX_OK;
+    if (!raw_present) {
+        rc = attrs_raw(edge_src, edge_dst, n_edges, src_latlon, src_xyzc, dst_latlon, dst_xyzc, dst_quat, want_len, 0,
+                       out_len, want_dir, dir_rotated, out_dir, true, nullptr, workspace, stream);
+        if (rc) return rc;
+    }
+    return attrs_scale(n_edges, len_norm, len_invert, out_len, dir_norm, dir_rotated, out_dir, stats, n_edges_global,
+                       workspace, stream);
 }
 
 extern "C" int agx_edge_attrs(const int32_t* edge_src, const int32_t* edge_dst, int64_t n_edges,
@@ -376,16 +468,21 @@ extern "C" int agx_edge_attrs(const int32_t* edge_src, const int32_t* edge_dst, 
                               const float* dst_xyzc, const double* dst_quat, int len_norm, int len_invert,
                               float* out_len, int dir_norm, int dir_rotated, float* out_dir, double* workspace,
                               void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
     int want_len = len_norm >= 0, want_dir = dir_norm >= 0;
+    AGX_REQUIRE(len_norm <= AGX_NORM_UNIT_STD && dir_norm <= AGX_NORM_UNIT_STD, AGX_ERR_ARG, "agx_edge_attrs: unknown norm code");
+    int rc = attrs_check(edge_src, edge_dst, n_edges, src_latlon, src_xyzc, dst_latlon, dst_xyzc, dst_quat, want_dir,
+                         dir_rotated, workspace);
+    if (rc) return rc;
+    if (n_edges == 0 || (!want_len && !want_dir)) return AGX_OK;
+    AGX_REQUIRE(!want_len || out_len, AGX_ERR_ARG, "agx_edge_attrs: out_len is NULL");
+    AGX_REQUIRE(!want_dir || out_dir, AGX_ERR_ARG, "agx_edge_attrs: out_dir is NULL");
     bool need_stats = (want_len && len_norm > 0) || (want_dir && dir_norm > 0);
-    double* stats = workspace ? workspace + 6 : nullptr;  // ws[6..13]: between the parameters and the block partials
-    if (need_stats && n_edges > 0) {
-        int rc = agx_edge_attrs_stats(edge_src, edge_dst, n_edges, src_latlon, src_xyzc, dst_latlon, dst_xyzc, dst_quat,
-                                      want_len && len_norm > 0, want_dir && dir_norm > 0, dir_rotated, stats, workspace,
-                                      stream_);
-        if (rc) return rc;
-    }
-    return agx_edge_attrs_apply(edge_src, edge_dst, n_edges, src_latlon, src_xyzc, dst_latlon, dst_xyzc, dst_quat,
-                                len_norm, len_invert, out_len, dir_norm, dir_rotated, out_dir, stats, n_edges, workspace,
-                                stream_);
+    double* stats = need_stats ? workspace + 6 : nullptr;  // ws[6..13]: between the parameters and the block partials
+    // no normalisation: the raw pass writes the final values (an inversion needs no statistics)
+    rc = attrs_raw(edge_src, edge_dst, n_edges, src_latlon, src_xyzc, dst_latlon, dst_xyzc, dst_quat, want_len,
+                   need_stats ? 0 : len_invert, out_len, want_dir, dir_rotated, out_dir, true, stats, workspace, stream);
+    if (rc || !need_stats) return rc;
+    return attrs_scale(n_edges, len_norm, len_invert, out_len, dir_norm, dir_rotated, out_dir, stats, n_edges, workspace,
+                       stream);
 }

@@ -66,7 +66,7 @@ static int choose_cells(int64_t n, int hint_k, double hint_radius) {
     if (hint_radius > 0.0) {
         width = hint_radius;  // radius search: a 3x3 window of radius-wide cells covers the cap
     } else if (hint_k > 0) {
-        width = 3.0 * sqrt((double)hint_k / (double)(n > 0 ? n : 1));  // ~ the k-NN radius at mean density
+        width = 2.0 * sqrt((double)hint_k / (double)(n > 0 ? n : 1));  // ~ 0.6x the k-NN search radius
     } else {
         width = sqrt(12.566370614359172 / (double)(n > 0 ? n : 1)) * 1.5;
     }

@@ -1,18 +1,35 @@
 // K2: k-nearest-neighbour search over the cell-binned index.
 //
 // Replaces sklearn's BallTree.query as driven by KNNEdges.get_adjacency_matrix
-// (/root/reference/src/anemoi/graphs/edges/builder.py:259-265) and utils.get_grid_reference_distance
-// (utils.py:62).  One thread per query:
-//   1. FP32 filter: scan the cells the search cap touches, squared chord on the FMA pipe, keep the
-//      k+1 best (d, index) in registers.  The cap grows until it provably holds the k-th neighbour.
-//   2. If the (k+1)-th candidate is within the FP32 error margin of the k-th, the set is decided in
-//      float64 with the reference's own haversine formula (tie rule: lower index within 2^-40).
-// The edge SET is what parity is judged on, so the filter only has to isolate the k members;
-// their float64 distances are evaluated only on request (out_rdist).
+// (/root/reference/src/anemoi/graphs/edges/builder.py:259-265), utils.get_grid_reference_distance
+// (utils.py:62) and KNNAreaMaskBuilder.get_mask (generate/masks.py:97).
+//
+// Main path - one WARP per tile of 32 consecutive queries (grids store neighbouring points next to
+// each other, so a tile's search caps overlap almost completely):
+//   1. every lane turns its query into a unit vector and a per-face cell window for the first search cap;
+//      the warp takes the union window per cube face (REDUX min / max);
+//   2. each window row is ONE contiguous run of 16-byte records in the cell-sorted array; one lane per row
+//      issues a 1-D bulk async copy (TMA, cp.async.bulk -> UBLKCP) of the run into the warp's shared-memory
+//      stage, completion tracked by an mbarrier (expect_tx / complete_tx);
+//   3. every lane scans the staged candidates with broadcast LDS.128: squared chord on the FP32 FMA pipe,
+//      top-(k+1) kept in registers;
+//   4. a lane whose k-th distance (+ margins) does not fit inside the first cap, and tiles whose window does
+//      not fit the stage, fall back to the per-thread search (cap growth until it provably holds the k-th
+//      neighbour);
+//   5. if the (k+1)-th candidate is within the FP32 error margin of the k-th, the set is decided in float64
+//      with the reference's own haversine formula (tie rule: lower index within 2^-40).
+// The edge SET is what parity is judged on, so the filter only has to isolate the k members; their float64
+// distances are evaluated only on request (out_rdist).
+#include <stdlib.h>
+
 #include "agx_search.cuh"
 
+#define KNN_WARPS 4
+#define KNN_STAGE 320  // candidate records per warp stage (5 KB)
+#define KNN_MAX_ROWS 32
+
 template <int CAP>
-struct TopF {  // ascending (d, idx), CAP entries in registers
+struct TopF {  // ascending d, CAP entries in registers (ties in arbitrary but deterministic scan order)
     float d[CAP];
     int id[CAP];
     __device__ __forceinline__ void reset() {
@@ -35,10 +52,12 @@ struct TopF {  // ascending (d, idx), CAP entries in registers
         for (int s = 1; s < CAP; ++s) r = (i == s) ? id[s] : r;
         return r;
     }
+    // exact FP32 ties at the k / k+1 boundary are always inside the error margin and are re-decided in float64,
+    // so the filter does not need an index tie-break
     __device__ __forceinline__ void insert(float cd, int ci) {
 #pragma unroll
         for (int s = 0; s < CAP; ++s) {
-            bool lt = (cd < d[s]) || (cd == d[s] && ci < id[s]);
+            bool lt = cd < d[s];
             float td = d[s];
             int ti = id[s];
             d[s] = lt ? cd : td;
@@ -46,6 +65,9 @@ struct TopF {  // ascending (d, idx), CAP entries in registers
             cd = lt ? td : cd;
             ci = lt ? ti : ci;
         }
+    }
+    __device__ __forceinline__ void offer(float cd, int ci) {
+        if (cd < d[CAP - 1]) insert(cd, ci);
     }
 };
 
@@ -84,121 +106,284 @@ struct TopD {  // ascending under agx_tie_less
             ci = lt ? ti : ci;
         }
     }
+    __device__ __forceinline__ void offer(double cr, int ci) {
+        if (agx_tie_less(cr, ci, r[CAP - 1], id[CAP - 1])) insert(cr, ci);
+    }
 };
 
-// CAP >= k + 1.  Entries beyond k + 1 are carried but never read.
+struct KnnArgs {
+    const float4* pts;
+    const int* cell_start;
+    const float2* ref_latlon;
+    int cells;
+    float chord2_init;
+    const float2* q_latlon;
+    int64_t nq;
+    int k;
+    int32_t* out_src;
+    int32_t* out_dst;
+    int64_t dst_base;
+    double* out_rdist;
+    unsigned long long* stats;
+};
+
+__device__ __forceinline__ float chord2(float3 q, float4 c) {
+    float dx = q.x - c.x, dy = q.y - c.y, dz = q.z - c.z;
+    return fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+}
+
+// true if the top list proves that the cap of squared chord t2 contains the k nearest neighbours
 template <int CAP>
-__global__ void __launch_bounds__(128) k_knn(const float4* __restrict__ pts, const int* __restrict__ cell_start,
-                                             const float2* __restrict__ ref_latlon, int cells, float chord2_init,
-                                             const float2* __restrict__ q_latlon, int64_t nq, int k,
-                                             int32_t* __restrict__ out_src, int32_t* __restrict__ out_dst,
-                                             int64_t dst_base, double* __restrict__ out_rdist,
-                                             unsigned long long* __restrict__ stats) {
-    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (int64_t)gridDim.x * blockDim.x) {
-        const float2 ql = q_latlon[q];
-        const float3 qv = agx_search_xyz(ql);
-        TopF<CAP> top;
-        float t2 = chord2_init;
-        bool widened = false;
-        AgxCap cap;
-        while (true) {
-            top.reset();
-            cap = agx_make_cap(t2);
-            for (int face = 0; face < 6; ++face) {
-                int i0, i1, j0, j1;
-                if (!agx_face_window(face, qv, cap, cells, i0, i1, j0, j1)) continue;
-                for (int i = i0; i <= i1; ++i) {
-                    int row = (face * cells + i) * cells;
-                    int s = __ldg(cell_start + row + j0), e = __ldg(cell_start + row + j1 + 1);
-                    for (int p = s; p < e; ++p) {
-                        float4 c = __ldg(pts + p);
-                        float dx = qv.x - c.x, dy = qv.y - c.y, dz = qv.z - c.z;
-                        float d = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
-                        int ci = __float_as_int(c.w);
-                        if (d < top.d[CAP - 1] || (d == top.d[CAP - 1] && ci < top.id[CAP - 1])) top.insert(d, ci);
-                    }
+__device__ __forceinline__ bool knn_cap_sufficient(const TopF<CAP>& top, int k, float t2, float& need) {
+    float dk = top.d_at(k - 1);
+    bool have_k = top.id_at(k - 1) != 0x7fffffff;
+    need = dk + 3.75f * agx_chord2_margin(dk);  // d_k + 3 margins (margin taken 1.25x)
+    return have_k && need <= t2;
+}
+
+// Per-thread search straight from global memory: grow the cap until it provably holds the k-th neighbour.
+template <int CAP>
+__device__ __forceinline__ void knn_thread_search(const KnnArgs& a, float3 qv, float t2, TopF<CAP>& top, AgxCap& cap) {
+    while (true) {
+        top.reset();
+        cap = agx_make_cap(t2);
+        for (int face = 0; face < 6; ++face) {
+            int i0, i1, j0, j1;
+            if (!agx_face_window(face, qv, cap, a.cells, i0, i1, j0, j1)) continue;
+            for (int i = i0; i <= i1; ++i) {
+                int row = (face * a.cells + i) * a.cells;
+                int s = __ldg(a.cell_start + row + j0), e = __ldg(a.cell_start + row + j1 + 1);
+                for (int p = s; p < e; ++p) {
+                    float4 c = __ldg(a.pts + p);
+                    top.offer(chord2(qv, c), __float_as_int(c.w));
                 }
-            }
-            if (cap.everything) break;
-            float dk = top.d_at(k - 1);
-            bool have_k = top.id_at(k - 1) != 0x7fffffff;
-            float need = dk + 3.75f * agx_chord2_margin(dk);  // d_k + 3 margins (margin taken 1.25x)
-            if (have_k && need <= t2) break;
-            widened = true;
-            t2 = have_k ? fmaxf(need * 1.0001f, t2 * 1.5f) : t2 * 4.0f;
-        }
-        // ---- decide the set ------------------------------------------------------------------
-        float dk = top.d_at(k - 1);
-        float amb = dk + 2.5f * agx_chord2_margin(dk);  // d_k + 2 margins
-        bool ambiguous = (CAP > 1) && (top.id_at(k) != 0x7fffffff) && (top.d_at(k) <= amb);
-        int32_t* os = out_src + q * k;
-        if (!ambiguous) {
-            if (out_rdist == nullptr) {
-#pragma unroll
-                for (int s = 0; s < CAP - 1; ++s)
-                    if (s < k) os[s] = top.id[s];
-            } else {
-                TopD<CAP> fin;
-                fin.reset();
-#pragma unroll
-                for (int s = 0; s < CAP - 1; ++s)
-                    if (s < k) fin.insert(agx_rdist64(ql, ref_latlon[top.id[s]]), top.id[s]);
-#pragma unroll
-                for (int s = 0; s < CAP - 1; ++s)
-                    if (s < k) {
-                        os[s] = fin.id[s];
-                        out_rdist[q * k + s] = fin.r[s];
-                    }
-            }
-        } else {
-            // float64 re-decision over every candidate the filter could not separate
-            TopD<CAP> fin;
-            fin.reset();
-            for (int face = 0; face < 6; ++face) {
-                int i0, i1, j0, j1;
-                if (!agx_face_window(face, qv, cap, cells, i0, i1, j0, j1)) continue;
-                for (int i = i0; i <= i1; ++i) {
-                    int row = (face * cells + i) * cells;
-                    int s = __ldg(cell_start + row + j0), e = __ldg(cell_start + row + j1 + 1);
-                    for (int p = s; p < e; ++p) {
-                        float4 c = __ldg(pts + p);
-                        float dx = qv.x - c.x, dy = qv.y - c.y, dz = qv.z - c.z;
-                        float d = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
-                        if (d <= amb) {
-                            int ci = __float_as_int(c.w);
-                            double r = agx_rdist64(ql, ref_latlon[ci]);
-                            if (agx_tie_less(r, ci, fin.r[CAP - 1], fin.id[CAP - 1])) fin.insert(r, ci);
-                        }
-                    }
-                }
-            }
-#pragma unroll
-            for (int s = 0; s < CAP - 1; ++s)
-                if (s < k) {
-                    os[s] = fin.id[s];
-                    if (out_rdist) out_rdist[q * k + s] = fin.r[s];
-                }
-            if (stats) {
-                atomicAdd(stats + 0, 1ull);
-                double rk = fin.r_at(k - 1), rn = fin.r_at(k);
-                if (fin.id_at(k) != 0x7fffffff && fabs(rn - rk) <= AGX_TIE_TAU * fmax(rn, rk)) atomicAdd(stats + 1, 1ull);
             }
         }
-        if (stats && widened) atomicAdd(stats + 2, 1ull);
-        if (out_dst) {
-            int32_t* od = out_dst + q * k;
-            int32_t t = (int32_t)(dst_base + q);
-            for (int s = 0; s < k; ++s) od[s] = t;
+        if (cap.everything) break;
+        float need;
+        if (knn_cap_sufficient(top, a.k, t2, need)) break;
+        bool have_k = top.id_at(a.k - 1) != 0x7fffffff;
+        t2 = have_k ? fmaxf(need * 1.0001f, t2 * 1.5f) : t2 * 4.0f;
+    }
+}
+
+// float64 re-decision over every candidate the filter could not separate (d <= amb), candidates from global memory
+template <int CAP>
+__device__ __forceinline__ void knn_redecide_global(const KnnArgs& a, float2 ql, float3 qv, const AgxCap& cap, float amb,
+                                                 TopD<CAP>& fin) {
+    for (int face = 0; face < 6; ++face) {
+        int i0, i1, j0, j1;
+        if (!agx_face_window(face, qv, cap, a.cells, i0, i1, j0, j1)) continue;
+        for (int i = i0; i <= i1; ++i) {
+            int row = (face * a.cells + i) * a.cells;
+            int s = __ldg(a.cell_start + row + j0), e = __ldg(a.cell_start + row + j1 + 1);
+            for (int p = s; p < e; ++p) {
+                float4 c = __ldg(a.pts + p);
+                if (chord2(qv, c) <= amb) {
+                    int ci = __float_as_int(c.w);
+                    fin.offer(agx_rdist64(ql, a.ref_latlon[ci]), ci);
+                }
+            }
         }
     }
 }
 
+// ... candidates from the warp's shared-memory stage (a superset of the lane's cap)
 template <int CAP>
-static void launch_knn(const agx_index* ix, float chord2_init, const float* q, int64_t nq, int k, int32_t* out_src,
-                       int32_t* out_dst, int64_t dst_base, double* out_rdist, int64_t* stats, cudaStream_t stream) {
-    int grid = agx_grid(nq, 128, 16);
-    k_knn<CAP><<<grid, 128, 0, stream>>>(ix->pts, ix->cell_start, ix->latlon, ix->cells, chord2_init, (const float2*)q,
-                                         nq, k, out_src, out_dst, dst_base, out_rdist, (unsigned long long*)stats);
+__device__ __forceinline__ void knn_redecide_stage(const KnnArgs& a, float2 ql, float3 qv, const float4* stage, int m,
+                                                float amb, TopD<CAP>& fin) {
+    for (int p = 0; p < m; ++p) {
+        float4 c = stage[p];
+        if (chord2(qv, c) <= amb) {
+            int ci = __float_as_int(c.w);
+            fin.offer(agx_rdist64(ql, a.ref_latlon[ci]), ci);
+        }
+    }
+}
+
+// ---- mbarrier / bulk-copy primitives (PTX) --------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_addr(bar)),
+        "r"(phase)
+        : "memory");
+}
+// 1-D bulk async copy global -> shared (TMA engine; 16-byte aligned, size a multiple of 16)
+__device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_addr(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// CAP >= k + 1.  Entries beyond k + 1 are carried but never read.
+template <int CAP>
+__global__ void __launch_bounds__(KNN_WARPS * 32) k_knn(KnnArgs a) {
+    __shared__ __align__(128) float4 stage_all[KNN_WARPS][KNN_STAGE];
+    __shared__ __align__(8) uint64_t bars[KNN_WARPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float4* stage = stage_all[warp];
+    uint64_t* bar = &bars[warp];
+    if (lane == 0) mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncwarp();
+    uint32_t phase = 0;
+    const int k = a.k;
+    const int64_t n_tiles = (a.nq + 31) >> 5;
+    const int64_t warps_total = (int64_t)gridDim.x * KNN_WARPS;
+    for (int64_t tile = (int64_t)blockIdx.x * KNN_WARPS + warp; tile < n_tiles; tile += warps_total) {
+        const int64_t q = tile * 32 + lane;
+        const bool active = q < a.nq;
+        const float2 ql = a.q_latlon[active ? q : a.nq - 1];
+        const float3 qv = agx_search_xyz(ql);
+        const float t2 = a.chord2_init;
+        AgxCap cap = agx_make_cap(t2);
+        // ---- union window of the tile per face, rows -> lanes ---------------------------------------
+        int n_rows = 0;      // rows of the union window over all faces (uniform across the warp)
+        int my_row = -1, my_j0 = 0, my_j1 = 0;
+        bool fits = !cap.everything;
+        if (fits) {
+            for (int face = 0; face < 6; ++face) {
+                int i0, i1, j0, j1;
+                bool ok = agx_face_window(face, qv, cap, a.cells, i0, i1, j0, j1);
+                if (!__any_sync(0xffffffffu, ok)) continue;
+                i0 = __reduce_min_sync(0xffffffffu, ok ? i0 : 0x7fffffff);
+                j0 = __reduce_min_sync(0xffffffffu, ok ? j0 : 0x7fffffff);
+                i1 = __reduce_max_sync(0xffffffffu, ok ? i1 : -1);
+                j1 = __reduce_max_sync(0xffffffffu, ok ? j1 : -1);
+                int rows = i1 - i0 + 1;
+                int slot = lane - n_rows;
+                if (slot >= 0 && slot < rows) {
+                    my_row = (face * a.cells + i0 + slot) * a.cells;
+                    my_j0 = j0;
+                    my_j1 = j1;
+                }
+                n_rows += rows;
+            }
+            fits = n_rows <= KNN_MAX_ROWS;
+        }
+        int m_total = 0;
+        if (fits) {
+            int s = 0, cnt = 0;
+            if (my_row >= 0) {
+                s = __ldg(a.cell_start + my_row + my_j0);
+                cnt = __ldg(a.cell_start + my_row + my_j1 + 1) - s;
+            }
+            // exclusive prefix of the row lengths = each row's offset in the stage
+            int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            m_total = __shfl_sync(0xffffffffu, incl, 31);
+            fits = m_total <= KNN_STAGE;
+            if (fits && m_total > 0) {
+                // previous tile's generic-proxy reads of the stage are complete (program order + __syncwarp below);
+                // order them before the async-proxy writes of this tile
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)m_total * 16u);
+                if (cnt > 0) bulk_copy_g2s(stage + (incl - cnt), a.pts + s, (uint32_t)cnt * 16u, bar);
+                mbar_wait(bar, phase);
+                phase ^= 1;
+            }
+            if (a.stats && lane == 0) atomicAdd(a.stats + 3, (unsigned long long)m_total);  // staged candidates
+        }
+        // ---- scan ------------------------------------------------------------------------------------
+        TopF<CAP> top;
+        bool staged = fits;
+        float t2_thread = t2;
+        if (fits) {
+            top.reset();
+#pragma unroll 4
+            for (int p = 0; p < m_total; ++p) {
+                float4 c = stage[p];
+                top.offer(chord2(qv, c), __float_as_int(c.w));
+            }
+            float need;
+            if (!knn_cap_sufficient(top, k, t2, need)) {
+                // this lane needs a wider cap than the tile staged: finish it on its own
+                bool have_k = top.id_at(k - 1) != 0x7fffffff;
+                t2_thread = have_k ? fmaxf(need * 1.0001f, t2 * 1.5f) : t2 * 4.0f;
+                staged = false;
+                if (a.stats && active) atomicAdd(a.stats + 2, 1ull);
+            }
+        }
+        if (!staged) knn_thread_search<CAP>(a, qv, t2_thread, top, cap);
+        // ---- decide the set --------------------------------------------------------------------------
+        float dk = top.d_at(k - 1);
+        float amb = dk + 2.5f * agx_chord2_margin(dk);  // d_k + 2 margins
+        bool ambiguous = (CAP > 1) && (top.id_at(k) != 0x7fffffff) && (top.d_at(k) <= amb);
+        if (active) {
+            int32_t* os = a.out_src + q * k;
+            if (!ambiguous) {
+                if (a.out_rdist == nullptr) {
+#pragma unroll
+                    for (int s = 0; s < CAP - 1; ++s)
+                        if (s < k) os[s] = top.id[s];
+                } else {
+                    TopD<CAP> fin;
+                    fin.reset();
+#pragma unroll
+                    for (int s = 0; s < CAP - 1; ++s)
+                        if (s < k) fin.insert(agx_rdist64(ql, a.ref_latlon[top.id[s]]), top.id[s]);
+#pragma unroll
+                    for (int s = 0; s < CAP - 1; ++s)
+                        if (s < k) {
+                            os[s] = fin.id[s];
+                            a.out_rdist[q * k + s] = fin.r[s];
+                        }
+                }
+            } else {
+                TopD<CAP> fin;
+                fin.reset();
+                if (staged)
+                    knn_redecide_stage<CAP>(a, ql, qv, stage, m_total, amb, fin);
+                else
+                    knn_redecide_global<CAP>(a, ql, qv, cap, amb, fin);
+#pragma unroll
+                for (int s = 0; s < CAP - 1; ++s)
+                    if (s < k) {
+                        os[s] = fin.id[s];
+                        if (a.out_rdist) a.out_rdist[q * k + s] = fin.r[s];
+                    }
+                if (a.stats) {
+                    atomicAdd(a.stats + 0, 1ull);
+                    double rk = fin.r_at(k - 1), rn = fin.r_at(k);
+                    if (fin.id_at(k) != 0x7fffffff && fabs(rn - rk) <= AGX_TIE_TAU * fmax(rn, rk)) atomicAdd(a.stats + 1, 1ull);
+                }
+            }
+            if (a.out_dst) {
+                int32_t* od = a.out_dst + q * k;
+                int32_t t = (int32_t)(a.dst_base + q);
+                for (int s = 0; s < k; ++s) od[s] = t;
+            }
+        }
+        __syncwarp();  // every lane is done with the stage before the next tile overwrites it
+    }
+}
+
+template <int CAP>
+static void launch_knn(const KnnArgs& a, cudaStream_t stream) {
+    int64_t tiles = (a.nq + 31) / 32;
+    int64_t blocks = (tiles + KNN_WARPS - 1) / KNN_WARPS;
+    int64_t cap = (int64_t)agx_sm_count() * 16;
+    int grid = (int)(blocks < cap ? blocks : cap);
+    k_knn<CAP><<<grid, KNN_WARPS * 32, 0, stream>>>(a);
 }
 
 extern "C" int agx_knn(const agx_index_t* ix, const float* q_latlon, int64_t nq, int k, int32_t* out_src,
@@ -214,20 +399,36 @@ extern "C" int agx_knn(const agx_index_t* ix, const float* q_latlon, int64_t nq,
     AGX_REQUIRE(dst_base + nq < (int64_t)2147483647, AGX_ERR_ARG, "agx_knn: target index exceeds int32");
     if (nq == 0) return AGX_OK;
     AGX_REQUIRE(q_latlon && out_src, AGX_ERR_ARG, "agx_knn: NULL buffer");
-    // first cap: ~1.5x the k-NN radius at mean density, chord^2 ~ rho^2 = 9 * (k+1) / n
-    double t2 = 9.0 * (double)(k + 1) / (double)ix->n;
+    // first cap: chord^2 = 6 (k+1) / n, i.e. 1.5 (k+1) expected points at mean density - 1.7x the k-th
+    // neighbour's squared distance on a triangular mesh (measured on O1280 -> res 7: no query needs widening)
+    double cap_scale = 6.0;
+    if (const char* env = getenv("AGX_KNN_CAP_SCALE")) cap_scale = atof(env);  // tuning knob
+    double t2 = cap_scale * (double)(k + 1) / (double)ix->n;
     if (t2 > 4.0) t2 = 4.0;
-    float chord2_init = (float)t2;
+    KnnArgs a;
+    a.pts = ix->pts;
+    a.cell_start = ix->cell_start;
+    a.ref_latlon = ix->latlon;
+    a.cells = ix->cells;
+    a.chord2_init = (float)t2;
+    a.q_latlon = (const float2*)q_latlon;
+    a.nq = nq;
+    a.k = k;
+    a.out_src = out_src;
+    a.out_dst = out_dst;
+    a.dst_base = dst_base;
+    a.out_rdist = out_rdist;
+    a.stats = (unsigned long long*)stats;
     if (k <= 3)
-        launch_knn<4>(ix, chord2_init, q_latlon, nq, k, out_src, out_dst, dst_base, out_rdist, stats, stream);
+        launch_knn<4>(a, stream);
     else if (k <= 7)
-        launch_knn<8>(ix, chord2_init, q_latlon, nq, k, out_src, out_dst, dst_base, out_rdist, stats, stream);
+        launch_knn<8>(a, stream);
     else if (k <= 16)
-        launch_knn<17>(ix, chord2_init, q_latlon, nq, k, out_src, out_dst, dst_base, out_rdist, stats, stream);
+        launch_knn<17>(a, stream);
     else if (k <= 32)
-        launch_knn<33>(ix, chord2_init, q_latlon, nq, k, out_src, out_dst, dst_base, out_rdist, stats, stream);
+        launch_knn<33>(a, stream);
     else
-        launch_knn<65>(ix, chord2_init, q_latlon, nq, k, out_src, out_dst, dst_base, out_rdist, stats, stream);
+        launch_knn<65>(a, stream);
     AGX_LAUNCH_OK();
     agx_note_launch(1);
     return AGX_OK;

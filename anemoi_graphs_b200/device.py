@@ -242,9 +242,13 @@ def all_gather_v(full: torch.Tensor, counts: list[int], dim: int) -> torch.Tenso
         rows = [full[r] for r in range(full.shape[0])]
         dim = 0
     backend = dist.get_backend()
+    equal = len(set(counts)) == 1 and counts[0] > 0
     for row in rows:
         views = [row.narrow(dim, offs[r], counts[r]) for r in range(w)]
-        if backend == "nccl":
+        if equal and row.is_contiguous():
+            # equal blocks: NCCL's in-place all-gather (send buffer = this rank's slot of the receive buffer)
+            dist.all_gather_into_tensor(row, views[rank])
+        elif backend == "nccl":
             # unequal sizes: ProcessGroupNCCL falls back to one grouped ncclBroadcast per rank, still in place
             dist.all_gather(views, views[rank])
         else:  # gloo (CPU tests): broadcasts

@@ -86,7 +86,7 @@ class KNNAreaMaskBuilder:
         assert self._reference is not None, f"{self.__class__.__name__} must be fitted first."
         q = _device.to_device(coords_rad, torch.float32)
         with ops.NeighbourIndex(self._reference, hint_k=1) as index:
-            _, rdist = index.knn(q, 1, return_rdist=True)
+            _, rdist = index.knn(q, 1, return_rdist=True, tag="knn_mask")
         dist = 2.0 * torch.asin(torch.sqrt(rdist[:, 0]))  # HaversineDistance64._rdist_to_dist
         return dist * EARTH_RADIUS <= self.margin_radius_km
 

@@ -103,7 +103,7 @@ def multiscale_edges(nodes, resolutions, x_hops: int = 1, area_mask_builder=None
     nv = ops.ico_num_vertices(max(resolutions))
     coords = ico.latlon[:nv]
     with ops.NeighbourIndex(st.x, hint_k=1) as index:
-        nearest = index.knn(coords, 1)[0]
+        nearest = index.knn(coords, 1, tag="knn_vertex_map")[0]
     if area_mask_builder is not None:
         valid = area_mask_builder.get_mask_device(coords)
         vertex_map = torch.where(valid, nearest, torch.full_like(nearest, -1))

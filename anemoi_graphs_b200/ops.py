@@ -119,6 +119,7 @@ class NeighbourIndex:
         stats: torch.Tensor | None = None,
         out: torch.Tensor | None = None,
         out_offset: int = 0,
+        tag: str = "knn",
     ):
         """``edge_index`` (2, nq*k) int32 - row 0 the k nearest reference points of each query, row 1
         ``dst_base + query`` - and optionally the float64 ``rdist`` (nq, k).  With ``out`` (a larger
@@ -132,7 +133,7 @@ class NeighbourIndex:
         assert 0 <= out_offset and out_offset + nq * k <= out.shape[1]
         rdist = torch.empty((nq, k), dtype=torch.float64, device=q.device) if return_rdist else None
         row = out.shape[1] * 4
-        with _span("knn", nq * k):
+        with _span(tag, nq * k):
             check(
                 self.lib.agx_knn(
                     self.handle, ptr(q), nq, int(k), out.data_ptr() + 4 * out_offset,
@@ -202,7 +203,7 @@ def grid_reference_distance(x: torch.Tensor) -> float:
     xd = _dev_x(x)
     lib = load_library()
     with NeighbourIndex(xd, hint_k=2) as index:
-        ei, rdist = index.knn(xd, 2, return_rdist=True)
+        ei, rdist = index.knn(xd, 2, return_rdist=True, tag="knn_refdist")
     value, flat = c_double(), c_int64()
     check(lib.agx_max_positive(ptr(rdist), rdist.numel(), byref(value), byref(flat), current_stream()))
     if flat.value < 0:
@@ -289,26 +290,30 @@ def edge_attributes(
     lo, hi = _device.shard_range(n_edges, rank, w)
     m = hi - lo
     e_src, e_dst = edge_index[0].data_ptr() + 4 * lo, edge_index[1].data_ptr() + 4 * lo
+    o_len = out_len.data_ptr() + 4 * lo if length else None
+    o_dir = out_dir.data_ptr() + 8 * lo if direction else None
     stats = None
+    raw_present = 0
     if len_code > 0 or dir_code > 0:
+        # one pass over the local edges: raw float32 values into this rank's slot + the local statistics
         stats = torch.empty(8, dtype=torch.float64, device=dev)
         with _span("edge_attrs_stats", m):
-          check(
-            lib.agx_edge_attrs_stats(
-                e_src, e_dst, m, ptr(src.x), ptr(src.xyzc), ptr(dst.x), ptr(dst.xyzc), ptr(dst.quat), int(len_code > 0),
-                int(dir_code > 0), int(bool(direction_rotated)), ptr(stats), ptr(ws), stream,
+            check(
+                lib.agx_edge_attrs_stats(
+                    e_src, e_dst, m, ptr(src.x), ptr(src.xyzc), ptr(dst.x), ptr(dst.xyzc), ptr(dst.quat), int(length),
+                    int(direction), int(bool(direction_rotated)), o_len, o_dir, ptr(stats), ptr(ws), stream,
+                )
+            )  # fmt: skip
+        stats = _device.all_gather_stats(stats)
+        raw_present = 1
+    with _span("edge_attrs_apply", m):
+        check(
+            lib.agx_edge_attrs_apply(
+                e_src, e_dst, m, ptr(src.x), ptr(src.xyzc), ptr(dst.x), ptr(dst.xyzc), ptr(dst.quat), len_code,
+                int(bool(length_invert)), o_len, dir_code, int(bool(direction_rotated)), o_dir, ptr(stats), n_edges,
+                raw_present, ptr(ws), stream,
             )
         )  # fmt: skip
-        stats = _device.all_gather_stats(stats)
-    with _span("edge_attrs_apply", m):
-      check(
-        lib.agx_edge_attrs_apply(
-            e_src, e_dst, m, ptr(src.x), ptr(src.xyzc), ptr(dst.x), ptr(dst.xyzc), ptr(dst.quat), len_code,
-            int(bool(length_invert)), out_len.data_ptr() + 4 * lo if length else None, dir_code,
-            int(bool(direction_rotated)), out_dir.data_ptr() + 8 * lo if direction else None, ptr(stats), n_edges, ptr(ws),
-            stream,
-        )
-    )  # fmt: skip
     counts = [_device.shard_range(n_edges, r, w) for r in range(w)]
     counts = [b - a for a, b in counts]
     if length:

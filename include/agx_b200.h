@@ -68,7 +68,7 @@ int agx_index_info(const agx_index_t* index, int64_t* n, int* cells_per_face);
  * (sklearn _dist_metrics.pyx.tp:2639-2648); ties within 2^-40 relative go to the lower index.
  * out_rdist (optional, nq*k) receives the float64 rdist of every neighbour.
  * stats (optional, DEV int64[4]) += {queries refined in float64, queries with a tie at the k-th
- * boundary, queries needing a wider search, 0}.                                                 */
+ * boundary, queries needing a wider search, candidate records staged in shared memory (x32 = FP32 pairs)}. */
 int agx_knn(const agx_index_t* index, const float* q_latlon /*DEV nq*2*/, int64_t nq, int k,
             int32_t* out_src /*DEV*/, int32_t* out_dst /*DEV or NULL*/, int64_t dst_base,
             double* out_rdist /*DEV or NULL*/, int64_t* stats /*DEV or NULL*/, void* stream);
@@ -99,8 +99,9 @@ int agx_max_positive(const double* values /*DEV n*/, int64_t n, double* out_valu
  * the rotation taking the node to the north pole (edges/directional.py:19-37, ε-nudge of
  * generate/transforms.py:133-140 included).
  * agx_edge_attrs: replaces EdgeLength.compute / EdgeDirection.compute (edges/attributes.py:42-157):
- * raw values -> global normalisation -> float32.  want_len/want_dir select outputs;
- * dir_rotated = luse_rotated_features.  Two passes when a norm needs global statistics.        */
+ * raw values (float32 store) + global statistics in one pass over the edges, then - if a norm was asked for -
+ * an in-place scaling pass.  len_norm / dir_norm = AGX_NORM_* or -1 to skip the attribute;
+ * dir_rotated = luse_rotated_features.                                                          */
 int agx_node_tables(const float* latlon /*DEV n*2*/, int64_t n, float* xyzc /*DEV n*4*/,
                     double* quat /*DEV n*4 or NULL*/, void* stream);
 int agx_edge_attrs(const int32_t* edge_src /*DEV E*/, const int32_t* edge_dst /*DEV E*/, int64_t n_edges,
@@ -111,20 +112,22 @@ int agx_edge_attrs(const int32_t* edge_src /*DEV E*/, const int32_t* edge_dst /*
                    double* workspace /*DEV, >= agx_edge_attrs_workspace() doubles*/, void* stream);
 int64_t agx_edge_attrs_workspace(void);
 /* The two halves of agx_edge_attrs, for callers that hold only a SHARD of the edge set (one rank of a
- * multi-GPU build): _stats reduces the raw values of the local edges to
+ * multi-GPU build).  _stats evaluates the raw values of the local edges ONCE: it writes them (float32, not yet
+ * normalised) to out_len / out_dir when those are given, and reduces them to
  * stats[8] = {len sum, sum of squares, min, max, dir sum, sum of squares, min, max} (float64; an empty shard
- * gives {0, 0, +1e300, -1e300}); the caller combines the shards' statistics (sum / min / max) and passes the
- * global ones, with the global edge count, to _apply, which writes the normalised float32 attributes of the
- * local edges.  want_* select which raw values are reduced (normalise.py:20-55 needs them only for a norm). */
+ * gives {0, 0, +1e300, -1e300}).  The caller combines the shards' statistics (sum / min / max) and passes the
+ * global ones, with the global edge count, to _apply, which normalises the local block in place
+ * (raw_present = 1) or evaluates the raw values first (raw_present = 0).  normalise.py:20-55.              */
 int agx_edge_attrs_stats(const int32_t* edge_src, const int32_t* edge_dst, int64_t n_edges, const float* src_latlon,
                          const float* src_xyzc, const float* dst_latlon, const float* dst_xyzc,
                          const double* dst_quat, int want_len, int want_dir, int dir_rotated,
+                         float* out_len /*DEV E or NULL*/, float* out_dir /*DEV E*2 or NULL*/,
                          double* stats /*DEV 8*/, double* workspace, void* stream);
 int agx_edge_attrs_apply(const int32_t* edge_src, const int32_t* edge_dst, int64_t n_edges, const float* src_latlon,
                          const float* src_xyzc, const float* dst_latlon, const float* dst_xyzc,
                          const double* dst_quat, int len_norm, int len_invert, float* out_len, int dir_norm,
                          int dir_rotated, float* out_dir, const double* stats /*DEV 8 or NULL if no norm*/,
-                         int64_t n_edges_global, double* workspace, void* stream);
+                         int64_t n_edges_global, int raw_present, double* workspace, void* stream);
 
 /* ---- icosphere + multi-scale edges -------------------------------------------------------------------
  * agx_icosphere: replaces trimesh.creation.icosphere (generate/tri_icosahedron.py:121,173):

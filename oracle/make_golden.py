@@ -216,7 +216,7 @@ def make_tri() -> None:
 
 def make_lam() -> None:
     """Config 4 in miniature: a 40 x 40 limited-area patch (25 km spacing, centred 50N 10E) plus 1 500 global
-    points; ``cutout`` marks the patch.  LimitedAreaTriNodes(4) and StretchedTriNodes(2 -> 5) hidden meshes with
+    points; ``cutout`` marks the patch.  LimitedAreaTriNodes(6) and StretchedTriNodes(2 -> 6) hidden meshes with
     MultiScaleEdges (x_hops 1 and 2), KNN k=4 decoder and CutOff encoder through the reference's own classes."""
     from torch_geometric.data import HeteroData  # shim
 
@@ -243,12 +243,12 @@ def make_lam() -> None:
         warnings.simplefilter("ignore")
         # limited-area mesh
         g = base_graph()
-        g = LimitedAreaTriNodes(4, "data", "lam", mask_attr_name="cutout", margin_radius_km=100.0).update_graph(g, {})
+        g = LimitedAreaTriNodes(6, "data", "lam", mask_attr_name="cutout", margin_radius_km=100.0).update_graph(g, {})
         out["lam_x"] = g["lam"].x.numpy()
         out["lam_node_ordering"] = np.asarray(g["lam"]["_node_ordering"], dtype=np.int64)
         for hops in (1, 2):
             gg = base_graph()
-            gg = LimitedAreaTriNodes(4, "data", "lam", mask_attr_name="cutout", margin_radius_km=100.0).update_graph(gg, {})
+            gg = LimitedAreaTriNodes(6, "data", "lam", mask_attr_name="cutout", margin_radius_km=100.0).update_graph(gg, {})
             MultiScaleEdges("lam", "lam", hops).update_graph(gg)
             out[f"lam_hops{hops}_edge_index"] = canon(gg[("lam", "to", "lam")].edge_index.numpy())
         KNNEdges("lam", "data", 4, target_mask_attr_name="cutout").update_graph(g)
@@ -257,12 +257,12 @@ def make_lam() -> None:
         out["lam_cutoff_edge_index"] = g[("data", "to", "lam")].edge_index.numpy()
         # stretched mesh
         g = base_graph()
-        g = StretchedTriNodes(2, 5, "str", "data", "cutout", margin_radius_km=100.0).update_graph(g, {})
+        g = StretchedTriNodes(2, 6, "str", "data", "cutout", margin_radius_km=100.0).update_graph(g, {})
         out["str_x"] = g["str"].x.numpy()
         out["str_node_ordering"] = np.asarray(g["str"]["_node_ordering"], dtype=np.int64)
         for hops in (1, 2):
             gg = base_graph()
-            gg = StretchedTriNodes(2, 5, "str", "data", "cutout", margin_radius_km=100.0).update_graph(gg, {})
+            gg = StretchedTriNodes(2, 6, "str", "data", "cutout", margin_radius_km=100.0).update_graph(gg, {})
             MultiScaleEdges("str", "str", hops).update_graph(gg)
             out[f"str_hops{hops}_edge_index"] = canon(gg[("str", "to", "str")].edge_index.numpy())
         KNNEdges("str", "data", 4).update_graph(g)

@@ -237,6 +237,54 @@ def tri_nodes(resolution: int) -> tuple[np.ndarray, np.ndarray]:
     return coords[order], order
 
 
+def lam_tri_nodes(resolution: int, reference_x: np.ndarray, margin_radius_km: float):
+    """LimitedAreaTriNodes (nodes/builders/from_refined_icosahedron.py:72-136, generate/tri_icosahedron.py:24-58):
+    ``(x, node_ordering, all vertex coords)`` keeping the vertices within the margin of the reference nodes."""
+    verts, _ = _tm.icosphere(resolution)
+    coords = cartesian_to_latlon_rad(verts)
+    order = coordinates_ordering(coords)
+    mask = knn_area_mask(reference_x, coords, margin_radius_km)
+    order = order[mask[order]]
+    return coords[order], order, coords
+
+
+def stretched_tri_nodes(base_resolution: int, lam_resolution: int, reference_x: np.ndarray, margin_radius_km: float):
+    """StretchedTriNodes (generate/tri_icosahedron.py:61-105): base-level vertices outside the area of
+    interest + lam-level vertices inside it."""
+    base = cartesian_to_latlon_rad(_tm.icosphere(base_resolution)[0])
+    lam = cartesian_to_latlon_rad(_tm.icosphere(lam_resolution)[0])
+    base_mask = ~knn_area_mask(reference_x, base, margin_radius_km)
+    lam_mask = knn_area_mask(reference_x, lam, margin_radius_km)
+    coords = np.concatenate([base[base_mask], lam[lam_mask]])
+    order = coordinates_ordering(coords)
+    return coords[order], order, coords
+
+
+def multiscale_edges_tri_masked(resolutions, x_hops: int, x: np.ndarray, mask_reference_x: np.ndarray, margin_km: float):
+    """``add_edges_to_nx_graph`` with an area mask (generate/tri_icosahedron.py:138-224,274-310) for limited-area
+    (mask reference = the cut-out data nodes, margin = the builder's) and stretched (mask reference = the graph
+    nodes themselves, margin 1 km, edges/builder.py:422-432) tri nodes; graph indices are positions in ``x``.
+    networkx ego graphs on the valid sub-mesh of every level, vertices mapped to nodes by haversine 1-NN."""
+    tree = BallTree(x, metric="haversine")
+    pairs = set()
+    for resolution in resolutions:
+        verts, faces = _tm.icosphere(resolution)
+        r_vertices_rad = cartesian_to_latlon_rad(verts)
+        valid = np.where(knn_area_mask(mask_reference_x, r_vertices_rad, margin_km))[0]
+        edges = _tm.edges_unique(faces)
+        edges = edges[np.isin(edges, valid).all(axis=1)]
+        g = nx.from_edgelist(edges)
+        _, vmap = tree.query(r_vertices_rad, k=1)
+        for i in valid:
+            if i not in g:
+                continue
+            for nb in nx.ego_graph(g, i, radius=x_hops, center=False):
+                if nb != i:
+                    pairs.add((int(vmap[i][0]), int(vmap[nb][0])))  # (target, source)
+    ei = np.array(sorted(pairs), dtype=np.int64).reshape(-1, 2)
+    return np.stack([ei[:, 1], ei[:, 0]], axis=0).astype(np.int32)
+
+
 # ----------------------------------------------------------------------------------------
 # MultiScaleEdges (tri)     edges/builder.py:412-455; generate/tri_icosahedron.py:138-310
 # ----------------------------------------------------------------------------------------

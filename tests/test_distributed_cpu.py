@@ -36,6 +36,11 @@ def _worker(rank: int, world: int, port: int, out_dir: str) -> None:
         agx_device.all_gather_v(full, counts, dim=1)
         allq = torch.arange(nq, dtype=torch.int32).repeat_interleave(k)
         assert torch.equal(full[1], allq) and torch.equal(full[0], 100 + allq * 7 % 13)
+        # --- equal blocks (in-place all_gather_into_tensor path) -----------------------------------
+        full = torch.full((2, 8), -1, dtype=torch.int32)
+        full[:, rank * 4 : rank * 4 + 4] = torch.arange(4, dtype=torch.int32) + 10 * rank
+        agx_device.all_gather_v(full, [4, 4], dim=1)
+        assert full[0].tolist() == [0, 1, 2, 3, 10, 11, 12, 13] and torch.equal(full[0], full[1])
         # --- cut-off-like variable-size blocks ------------------------------------------------------
         mine = 5 if rank == 0 else 2
         counts = agx_device.all_gather_counts(mine, torch.device("cpu"))

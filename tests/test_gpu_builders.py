@@ -244,3 +244,53 @@ def test_attribute_api(golden):
         EdgeLength().compute(graph, ("hidden", "to", "nope"))
     with pytest.raises(ValueError):
         EdgeLength(norm="bogus").compute(graph, key)
+
+
+def _lam_graph(g):
+    from anemoi_graphs_b200.graph import HeteroData
+
+    graph = HeteroData()
+    graph["data"].x = torch.from_numpy(g["data_x"])
+    graph["data"].node_type = "LatLonNodes"
+    graph["data"]["cutout"] = torch.from_numpy(g["cutout"])
+    return graph
+
+
+@pytest.mark.parametrize("hops", [1, 2])
+def test_limited_area_tri_nodes_and_edges(golden, hops):
+    """BASELINE config 4 in miniature: LimitedAreaTriNodes + MultiScaleEdges + masked KNN / CutOff vs the reference."""
+    from anemoi_graphs_b200.edges import CutOffEdges, KNNEdges, MultiScaleEdges
+    from anemoi_graphs_b200.nodes import LimitedAreaTriNodes
+
+    g = golden("lam")
+    graph = _lam_graph(g)
+    graph = LimitedAreaTriNodes(6, "data", "lam", mask_attr_name="cutout", margin_radius_km=100.0).update_graph(graph, {})
+    assert graph["lam"].node_type == "LimitedAreaTriNodes"
+    np.testing.assert_array_equal(graph["lam"].x.numpy().view(np.int32), g["lam_x"].view(np.int32))
+    np.testing.assert_array_equal(np.asarray(graph["lam"]["_node_ordering"]), g["lam_node_ordering"])
+    MultiScaleEdges("lam", "lam", hops).update_graph(graph)
+    np.testing.assert_array_equal(canon(graph[("lam", "to", "lam")].edge_index), g[f"lam_hops{hops}_edge_index"])
+    KNNEdges("lam", "data", 4, target_mask_attr_name="cutout").update_graph(graph)
+    CutOffEdges("data", "lam", 0.6, source_mask_attr_name="cutout").update_graph(graph)
+    np.testing.assert_array_equal(canon(graph[("lam", "to", "data")].edge_index), canon(g["lam_knn4_edge_index"]))
+    np.testing.assert_array_equal(canon(graph[("data", "to", "lam")].edge_index), canon(g["lam_cutoff_edge_index"]))
+
+
+@pytest.mark.parametrize("hops", [1, 2])
+def test_stretched_tri_nodes_and_edges(golden, hops):
+    from anemoi_graphs_b200.edges import CutOffEdges, KNNEdges, MultiScaleEdges
+    from anemoi_graphs_b200.nodes import StretchedTriNodes
+    from anemoi_graphs_b200.utils import get_grid_reference_distance
+
+    g = golden("lam")
+    graph = _lam_graph(g)
+    graph = StretchedTriNodes(2, 6, "str", "data", "cutout", margin_radius_km=100.0).update_graph(graph, {})
+    np.testing.assert_array_equal(graph["str"].x.numpy().view(np.int32), g["str_x"].view(np.int32))
+    np.testing.assert_array_equal(np.asarray(graph["str"]["_node_ordering"]), g["str_node_ordering"])
+    MultiScaleEdges("str", "str", hops).update_graph(graph)
+    np.testing.assert_array_equal(canon(graph[("str", "to", "str")].edge_index), g[f"str_hops{hops}_edge_index"])
+    assert get_grid_reference_distance(graph["str"].x) == float(g["str_reference_distance"])
+    KNNEdges("str", "data", 4).update_graph(graph)
+    CutOffEdges("data", "str", 0.6).update_graph(graph)
+    np.testing.assert_array_equal(canon(graph[("str", "to", "data")].edge_index), canon(g["str_knn4_edge_index"]))
+    np.testing.assert_array_equal(canon(graph[("data", "to", "str")].edge_index), canon(g["str_cutoff_edge_index"]))

@@ -1,0 +1,121 @@
+"""Full-size (BASELINE config 3: O1280 -> TriNodes 7) checks on the GPU.  The oracle cannot build the whole graph in
+seconds, so parity is checked (a) against the oracle on random SAMPLES of the queries / edges and (b) through
+size-independent properties: published edge-count formula, k distinct neighbours per target, symmetry of the
+multi-scale edge set, grouped-by-target order, statistics of the normalised attributes."""
+
+import numpy as np
+import pytest
+import torch
+
+from anemoi_graphs_b200 import grids
+from oracle import ref_path as R
+
+pytestmark = pytest.mark.gpu
+T = "anemoi.graphs."
+
+
+@pytest.fixture(scope="module")
+def o1280_graph():
+    from anemoi_graphs_b200.create import GraphCreator
+    from anemoi_graphs_b200.graph import HeteroData
+
+    lat, lon = grids.octahedral_grid(1280)
+    x = grids.latlon_deg_to_x(lat, lon)
+    assert x.shape == (6599680, 2)
+    attrs = {
+        "edge_length": {"_target_": T + "edges.attributes.EdgeLength", "norm": "unit-std"},
+        "edge_dirs": {"_target_": T + "edges.attributes.EdgeDirection", "norm": "unit-std"},
+    }
+    recipe = {
+        "nodes": {"hidden": {"node_builder": {"_target_": T + "nodes.TriNodes", "resolution": 7}}},
+        "edges": [
+            {"source_name": "data", "target_name": "hidden", "attributes": attrs,
+             "edge_builders": [{"_target_": T + "edges.CutOffEdges", "cutoff_factor": 0.6}]},
+            {"source_name": "hidden", "target_name": "hidden", "attributes": attrs,
+             "edge_builders": [{"_target_": T + "edges.MultiScaleEdges", "x_hops": 1}]},
+            {"source_name": "hidden", "target_name": "data", "attributes": attrs,
+             "edge_builders": [{"_target_": T + "edges.KNNEdges", "num_nearest_neighbours": 3}]},
+        ],
+    }  # fmt: skip
+    graph = HeteroData()
+    graph["data"].x = x
+    graph["data"].node_type = "LatLonNodes"
+    return GraphCreator(recipe).update_graph(graph)
+
+
+def test_o1280_hidden_nodes_and_counts(o1280_graph):
+    g = o1280_graph
+    hx, order = R.tri_nodes(7)
+    np.testing.assert_array_equal(g["hidden"].x.numpy().view(np.int32), hx.view(np.int32))
+    np.testing.assert_array_equal(np.asarray(g["hidden"]["_node_ordering"]), order)
+    assert g[("hidden", "to", "data")].edge_index.shape == (2, 3 * 6599680)
+    # docs/graphs/edges/tri_refined_edges.csv: multilevel edges = sum_r 60 * 4^r
+    assert g[("hidden", "to", "hidden")].edge_index.shape[1] == sum(60 * 4**r for r in range(8)) == 1310700
+    assert g[("data", "to", "hidden")].edge_index.shape[1] == 10394844  # SURVEY section 6, measured on the reference
+
+
+def test_o1280_knn_sample_vs_oracle_and_properties(o1280_graph):
+    g = o1280_graph
+    ei = g[("hidden", "to", "data")].edge_index.numpy()
+    dst = ei[1].reshape(-1, 3)
+    assert (dst == np.arange(6599680, dtype=np.int32)[:, None]).all()  # grouped by target, k per target
+    src = np.sort(ei[0].reshape(-1, 3), axis=1)
+    assert (np.diff(src, axis=1) > 0).all()  # k DISTINCT neighbours
+    rng = np.random.default_rng(0)
+    sample = np.sort(rng.choice(6599680, size=60000, replace=False))
+    hx, dx = g["hidden"].x.numpy(), g["data"].x.numpy()
+    want, info = R.knn_edges_canonical(hx, dx[sample], 3)
+    assert info["untied_mismatch"].size == 0
+    np.testing.assert_array_equal(src[sample], np.sort(want[0].reshape(-1, 3), axis=1))
+
+
+def test_o1280_cutoff_sample_vs_oracle(o1280_graph):
+    g = o1280_graph
+    ei = g[("data", "to", "hidden")].edge_index.numpy()
+    assert (np.diff(ei[1]) >= 0).all()  # grouped by target
+    hx, dx = g["hidden"].x.numpy(), g["data"].x.numpy()
+    radius = R.cutoff_radius(hx, 0.6)
+    rng = np.random.default_rng(1)
+    sample = np.sort(rng.choice(hx.shape[0], size=8000, replace=False))
+    from sklearn.neighbors import NearestNeighbors
+
+    nn = NearestNeighbors(metric="haversine", n_jobs=-1).fit(dx)
+    ind = nn.radius_neighbors(hx[sample], radius=radius, return_distance=False)
+    starts = np.searchsorted(ei[1], sample, side="left")
+    ends = np.searchsorted(ei[1], sample, side="right")
+    for t, (s, e) in enumerate(zip(starts, ends)):
+        np.testing.assert_array_equal(np.sort(ei[0, s:e]), np.sort(ind[t]))
+    counts = np.bincount(ei[1], minlength=hx.shape[0])
+    assert counts.min() >= 1 and 49 <= counts.min() and counts.max() <= 140  # 49-140 per target
+
+
+def test_o1280_multiscale_symmetric(o1280_graph):
+    ei = o1280_graph[("hidden", "to", "hidden")].edge_index.numpy().astype(np.int64)
+    fwd = np.sort(ei[0] * 163842 + ei[1])
+    bwd = np.sort(ei[1] * 163842 + ei[0])
+    np.testing.assert_array_equal(fwd, bwd)  # u -> v implies v -> u
+    assert (ei[0] != ei[1]).all() and np.unique(fwd).size == fwd.size
+
+
+def test_o1280_attribute_samples_and_statistics(o1280_graph):
+    g = o1280_graph
+    rng = np.random.default_rng(2)
+    for key in (("data", "to", "hidden"), ("hidden", "to", "data"), ("hidden", "to", "hidden")):
+        store = g[key]
+        ei = store.edge_index.numpy()
+        sx, tx = g[key[0]].x.numpy(), g[key[2]].x.numpy()
+        ln, dr = store["edge_length"].numpy(), store["edge_dirs"].numpy()
+        assert ln.shape == (ei.shape[1], 1) and dr.shape == (ei.shape[1], 2)
+        # unit-std: the population standard deviation of the normalised values is 1
+        np.testing.assert_allclose(ln.astype(np.float64).std(), 1.0, rtol=2e-6)
+        np.testing.assert_allclose(dr.astype(np.float64).std(), 1.0, rtol=2e-6)
+        # a sample of edges against the oracle's raw values, scaled by the full-array statistics
+        pick = np.sort(rng.choice(ei.shape[1], size=200000, replace=False))
+        sub = ei[:, pick]
+        raw_len = R.haversine_distance(sx[sub[0]], tx[sub[1]])
+        raw_dir = R.edge_directions_raw(sx[sub[0]].T, tx[sub[1]].T, True).T
+        scale_len = ln[pick, 0].astype(np.float64) / raw_len.astype(np.float64)
+        np.testing.assert_allclose(scale_len, np.median(scale_len), rtol=2e-6)  # one global divisor
+        big = np.abs(raw_dir) > 1e-3
+        scale_dir = dr[pick].astype(np.float64)[big] / raw_dir[big]
+        np.testing.assert_allclose(scale_dir, np.median(scale_dir), rtol=2e-6)

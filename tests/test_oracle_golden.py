@@ -148,3 +148,26 @@ def test_o96_res5_tie_enumeration(golden):
     ref = g["knn3_edge_index"]
     untied = ~np.isin(ref[1], info["tied_queries"])
     np.testing.assert_array_equal(ei[:, ~np.isin(ei[1], info["tied_queries"])], ref[:, untied])
+
+
+def test_lam_and_stretched_match_reference(golden):
+    """Config 4 in miniature (tests/golden/lam.npz): LimitedAreaTriNodes / StretchedTriNodes and their
+    MultiScaleEdges, masked KNN / CutOff, from the unmodified reference."""
+    g = golden("lam")
+    dx, cut = g["data_x"], g["cutout"].squeeze()
+    lam_x, lam_order, _ = R.lam_tri_nodes(6, dx[cut], 100.0)
+    np.testing.assert_array_equal(lam_order, g["lam_node_ordering"])
+    np.testing.assert_array_equal(lam_x.view(np.int32), g["lam_x"].view(np.int32))
+    str_x, str_order, _ = R.stretched_tri_nodes(2, 6, dx[cut], 100.0)
+    np.testing.assert_array_equal(str_order, g["str_node_ordering"])
+    np.testing.assert_array_equal(str_x.view(np.int32), g["str_x"].view(np.int32))
+    for hops in (1, 2):
+        ei = R.multiscale_edges_tri_masked(range(7), hops, lam_x, dx[cut], 100.0)
+        np.testing.assert_array_equal(ei, g[f"lam_hops{hops}_edge_index"])
+        ei = R.multiscale_edges_tri_masked(range(7), hops, str_x, str_x, 1.0)
+        np.testing.assert_array_equal(ei, g[f"str_hops{hops}_edge_index"])
+    np.testing.assert_array_equal(R.masked_edges("knn", lam_x, dx, None, g["cutout"], 4), g["lam_knn4_edge_index"])
+    np.testing.assert_array_equal(R.masked_edges("cutoff", dx, lam_x, g["cutout"], None, 0.6), g["lam_cutoff_edge_index"])
+    np.testing.assert_array_equal(R.knn_edges(str_x, dx, 4), g["str_knn4_edge_index"])
+    np.testing.assert_array_equal(R.cutoff_edges(dx, str_x, 0.6), g["str_cutoff_edge_index"])
+    assert R.grid_reference_distance(str_x) == float(g["str_reference_distance"])
