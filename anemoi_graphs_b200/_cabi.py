@@ -30,6 +30,7 @@ SIGNATURES = {
     "agx_index_build": (c_int, [c_void_p, c_int64, c_int, c_int, c_double, c_void_p, POINTER(c_void_p)]),
     "agx_index_free": (c_int, [c_void_p, c_void_p]),
     "agx_index_info": (c_int, [c_void_p, POINTER(c_int64), POINTER(c_int)]),
+    "agx_search_vectors": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "agx_knn": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "agx_radius_count": (c_int, [c_void_p, c_void_p, c_int64, c_double, c_void_p, c_void_p]),
     "agx_exclusive_scan": (c_int, [c_void_p, c_int64, c_void_p, POINTER(c_int64), c_void_p]),
@@ -38,19 +39,19 @@ SIGNATURES = {
     "agx_node_tables": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "agx_edge_attrs": (
         c_int,
-        [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int,
-         c_int, c_void_p, c_void_p, c_void_p],
+        [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p,
+         c_void_p],
     ),  # fmt: skip
     "agx_edge_attrs_workspace": (c_int64, []),
     "agx_edge_attrs_stats": (
         c_int,
-        [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
-         c_void_p, c_void_p, c_void_p, c_void_p],
+        [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+         c_void_p],
     ),  # fmt: skip
     "agx_edge_attrs_apply": (
         c_int,
-        [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int,
-         c_int, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p],
+        [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p,
+         c_int64, c_int, c_void_p, c_void_p],
     ),  # fmt: skip
     "agx_icosphere": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "agx_multiscale_tri_count": (

@@ -10,7 +10,14 @@
 //  * float64 stage (numpy/scipy): cross products, arccos, scipy Rotation.from_rotvec (small-angle
 //    series for angle <= 1e-3), as_matrix, apply, the two epsilon nudges of direction_vec.
 // Everything that depends on ONE node only (xyz, cos lat, the rotation quaternion of a target) is
-// tabulated per node; the per-edge kernel is gather + ~60 flops + 12-byte store, HBM-bound.
+// tabulated per node in ONE 32-byte record per role, so an edge costs exactly two gathered sectors:
+//   source record  float[8]  = (x, y, z, cos lat, lat, lon, 0, 0)
+//   target record  double[4] = (quat x, quat y, quat w, bits(lat, lon))   (quat z is exactly 0)
+// The per-edge kernel works on warp tiles of 32*J consecutive edges: J coalesced index loads per lane, then
+// all 2*J record gathers (LDG.128 pairs) in flight before the arithmetic - the kernel is latency-bound on
+// the dependent index -> record chain, so memory-level parallelism per warp is what buys bandwidth.
+#include <stdlib.h>
+
 #include "agx_common.cuh"
 
 #define ATTR_THREADS 256
@@ -23,7 +30,7 @@ extern "C" int64_t agx_edge_attrs_workspace(void) { return (int64_t)ATTR_STAT_FI
 // per-node tables
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_node_tables(const float2* __restrict__ latlon, int64_t n,
-                                                      float4* __restrict__ xyzc, double* __restrict__ quat) {
+                                                      float4* __restrict__ src_rec, double4* __restrict__ dst_rec) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         float2 ll = latlon[i];
         float sl, cl, so, co;
@@ -31,8 +38,11 @@ __global__ void __launch_bounds__(256) k_node_tables(const float2* __restrict__ 
         agx_np_sincosf(ll.y, so, co);
         // latlon_rad_to_cartesian (generate/transforms.py:106-110), radius = 1.0: float32 products
         float x = __fmul_rn(cl, co), y = __fmul_rn(cl, so), z = sl;
-        xyzc[i] = make_float4(x, y, z, cl);
-        if (quat != nullptr) {
+        if (src_rec != nullptr) {
+            src_rec[2 * i] = make_float4(x, y, z, cl);
+            src_rec[2 * i + 1] = make_float4(ll.x, ll.y, 0.0f, 0.0f);
+        }
+        if (dst_rec != nullptr) {
             // get_rotation_from_unit_vecs(points=this node as TARGET, reference=(0,0,1))
             // direction_vec: v = cross(p, z^) = (p_y, -p_x, 0) in float64 from the float32 components
             double v0 = (double)y, v1 = -(double)x;
@@ -59,19 +69,21 @@ __global__ void __launch_bounds__(256) k_node_tables(const float2* __restrict__ 
             } else {
                 scale = sin(angle / 2.0) / angle;
             }
-            double4 qd = make_double4(scale * r0, scale * r1, cos(angle / 2.0), 0.0);
-            reinterpret_cast<double4*>(quat)[i] = qd;
+            long long packed = ((long long)__float_as_int(ll.y) << 32) | (unsigned int)__float_as_int(ll.x);
+            dst_rec[i] = make_double4(scale * r0, scale * r1, cos(angle / 2.0), __longlong_as_double(packed));
         }
     }
 }
 
-extern "C" int agx_node_tables(const float* latlon, int64_t n, float* xyzc, double* quat, void* stream_) {
+extern "C" int agx_node_tables(const float* latlon, int64_t n, float* src_rec, double* dst_rec, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     AGX_REQUIRE(n >= 0, AGX_ERR_ARG, "agx_node_tables: n < 0");
     if (n == 0) return AGX_OK;
-    AGX_REQUIRE(latlon && xyzc, AGX_ERR_ARG, "agx_node_tables: NULL buffer");
+    AGX_REQUIRE(latlon && (src_rec || dst_rec), AGX_ERR_ARG, "agx_node_tables: NULL buffer");
+    AGX_REQUIRE(((uintptr_t)src_rec & 15) == 0 && ((uintptr_t)dst_rec & 31) == 0, AGX_ERR_ARG,
+                "agx_node_tables: records must be 16-byte (source) / 32-byte (target) aligned");
     int grid = agx_grid(n, 256, 8);
-    k_node_tables<<<grid, 256, 0, stream>>>((const float2*)latlon, n, (float4*)xyzc, quat);
+    k_node_tables<<<grid, 256, 0, stream>>>((const float2*)latlon, n, (float4*)src_rec, (double4*)dst_rec);
     AGX_LAUNCH_OK();
     agx_note_launch(1);
     return AGX_OK;
@@ -84,9 +96,12 @@ extern "C" int agx_node_tables(const float* latlon, int64_t n, float* xyzc, doub
 // Taylor series to t^11 is exact to < 3e-16 relative (next term t^12/13) and costs a handful of DFMAs instead of
 // the library's ~150-instruction path.  The quotient uses a float reciprocal seed + two Newton steps (1e-14
 // relative); the result is rounded to float32 by the caller, so this cannot be told from the exact quotient.
-__device__ __forceinline__ double atan2_short(double ra, double rb) {
+__device__ __forceinline__ double atan2_short(float ra32, float rb32) {
+    double ra = (double)ra32, rb = (double)rb32;
     if (ra <= 0.0625 * rb) {
-        double r = (double)__frcp_rn((float)rb);
+        float seed;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(seed) : "f"(rb32));  // 2^-23 relative; two Newton steps -> 2^-90
+        double r = (double)seed;
         r = r * (2.0 - rb * r);
         r = r * (2.0 - rb * r);
         double t = ra * r, t2 = t * t;
@@ -103,42 +118,74 @@ __device__ __forceinline__ double atan2_short(double ra, double rb) {
 // utils.haversine_distance in float32 (numpy), last step in float64 then rounded.
 __device__ __forceinline__ float edge_length_raw(float2 s, float cs, float2 t, float ct) {
     float dlat = __fsub_rn(t.x, s.x), dlon = __fsub_rn(t.y, s.y);
-    float sh_lat, sh_lon, unused;
-    agx_np_sincosf(__fmul_rn(dlat, 0.5f), sh_lat, unused);
-    agx_np_sincosf(__fmul_rn(dlon, 0.5f), sh_lon, unused);
+    float sh_lat = agx_np_sinf_short(__fmul_rn(dlat, 0.5f));
+    float sh_lon = agx_np_sinf_short(__fmul_rn(dlon, 0.5f));
     float a = __fadd_rn(__fmul_rn(sh_lat, sh_lat), __fmul_rn(__fmul_rn(cs, ct), __fmul_rn(sh_lon, sh_lon)));
     float ra = __fsqrt_rn(a), rb = __fsqrt_rn(__fsub_rn(1.0f, a));
-    return __fmul_rn(2.0f, (float)atan2_short((double)ra, (double)rb));
+    return __fmul_rn(2.0f, (float)atan2_short(ra, rb));
 }
 
-// compute_directions (edges/directional.py:40-65) for one edge; q = R(target) * source_xyz
+// compute_directions (edges/directional.py:40-65) for one edge; q = R(target) * source_xyz.
+// For the unit quaternion (x, y, 0, w) scipy's as_matrix rows 0 and 1 are (1 - 2y^2, 2xy, 2yw) and
+// (2xy, 1 - 2x^2, -2xw) (it writes them as x^2 - y^2 + w^2 etc., equal to 1e-16), so with
+// T = x s_y - y s_x + w s_z:  q_x = s_x + 2 y T,  q_y = s_y - 2 x T  - seven float64 operations.  For nearby
+// endpoints q_x, q_y are O(separation) differences of O(1) terms; each rounding is <= 1.1e-16 absolute, i.e.
+// <= 1e-12 relative at the shortest edges of an O1280 graph (separation 1e-3).
 __device__ __forceinline__ void edge_direction_rotated(float4 sxyz, double x, double y, double w, double& o0, double& o1) {
-    // z component of the quaternion is exactly 0
-    double x2 = x * x, y2 = y * y, w2 = w * w, xy = x * y, yw = y * w, xw = x * w;
     double sx = (double)sxyz.x, sy = (double)sxyz.y, sz = (double)sxyz.z;
-    // scipy as_matrix rows 0 and 1 with z = 0
-    double m00 = x2 - y2 + w2, m01 = 2.0 * xy, m02 = 2.0 * yw;
-    double m10 = 2.0 * xy, m11 = -x2 + y2 + w2, m12 = -2.0 * xw;
-    double qx = m00 * sx + m01 * sy + m02 * sz;
-    double qy = m10 * sx + m11 * sy + m12 * sz;
+    double T2 = 2.0 * fma(x, sy, fma(-y, sx, w * sz));
+    double qx = fma(y, T2, sx);
+    double qy = fma(-x, T2, sy);
     // direction_vec(q, z^): v = (q_y, -q_x, 0); nudge in float64 when |v|^2 < 1e-10
-    double vn = qy * qy + qx * qx;
+    double vn = fma(qy, qy, qx * qx);
     if (vn < 10e-11) {
         qx += 10e-11;
         qy += 10e-11;
-        vn = qy * qy + qx * qx;
+        vn = fma(qy, qy, qx * qx);
     }
+    // v / |v|; the reference normalises once more (edges/directional.py:65), which moves a unit vector by at most
+    // an ulp of float64 - invisible after the float32 cast.  NaN inputs propagate as they do there.
     double inv = rsqrt(vn);
-    double d0 = qy * inv, d1 = -qx * inv;
-    // the final renormalisation (edges/directional.py:65): |d|^2 = 1 + O(1e-16), so one Newton step of
-    // rsqrt about 1 (1.5 - 0.5 s) is exact to 1e-31
-    double inv2 = fma(-0.5, d0 * d0 + d1 * d1, 1.5);
-    if (!(vn > 0.0)) inv2 = rsqrt(d0 * d0 + d1 * d1);  // NaN / inf propagate as the reference's division would
-    o0 = d0 * inv2;
-    o1 = d1 * inv2;
+    o0 = qy * inv;
+    o1 = -qx * inv;
 }
 
+// Running statistics of one attribute.  Sums are float64 (the reference reduces a float64 array for directions and
+// numpy's pairwise float32 sum for lengths - both within 1e-7 of this).  Minimum / maximum are tracked on the
+// float32 value that is stored, one FMNMX each: for lengths that IS the reference's value; for rotated directions
+// the reference takes them on the float64 array, whose float32 rounding differs by <= 6e-8 relative.
 struct Stat4 {
+    double sum, sumsq;
+    float mn, mx;
+    __device__ __forceinline__ void init() {
+        sum = 0.0;
+        sumsq = 0.0;
+        mn = __int_as_float(0x7f800000);
+        mx = __int_as_float(0xff800000);
+    }
+    __device__ __forceinline__ void add(double v, float v32) {
+        sum += v;
+        sumsq = fma(v, v, sumsq);
+        mn = fminf(mn, v32);
+        mx = fmaxf(mx, v32);
+    }
+    __device__ __forceinline__ void merge(const Stat4& o) {
+        sum += o.sum;
+        sumsq += o.sumsq;
+        mn = fminf(mn, o.mn);
+        mx = fmaxf(mx, o.mx);
+    }
+    // the workspace / C-ABI form: {sum, sumsq, min, max} as doubles, +-1e300 for "no value"
+    __device__ __forceinline__ void store(double* p) const {
+        p[0] = sum;
+        p[1] = sumsq;
+        p[2] = mn == __int_as_float(0x7f800000) ? 1e300 : (double)mn;
+        p[3] = mx == __int_as_float(0xff800000) ? -1e300 : (double)mx;
+    }
+};
+
+// the same four fields in float64, for folding per-block partials
+struct Stat4D {
     double sum, sumsq, mn, mx;
     __device__ __forceinline__ void init() {
         sum = 0.0;
@@ -146,13 +193,7 @@ struct Stat4 {
         mn = 1e300;
         mx = -1e300;
     }
-    __device__ __forceinline__ void add(double v) {
-        sum += v;
-        sumsq += v * v;
-        mn = fmin(mn, v);
-        mx = fmax(mx, v);
-    }
-    __device__ __forceinline__ void merge(const Stat4& o) {
+    __device__ __forceinline__ void merge(const Stat4D& o) {
         sum += o.sum;
         sumsq += o.sumsq;
         mn = fmin(mn, o.mn);
@@ -160,10 +201,11 @@ struct Stat4 {
     }
 };
 
-__device__ __forceinline__ Stat4 warp_reduce(Stat4 s) {
+template <class S>
+__device__ __forceinline__ S warp_reduce(S s) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-        Stat4 t;
+        S t;
         t.sum = __shfl_down_sync(0xffffffffu, s.sum, o);
         t.sumsq = __shfl_down_sync(0xffffffffu, s.sumsq, o);
         t.mn = __shfl_down_sync(0xffffffffu, s.mn, o);
@@ -173,49 +215,73 @@ __device__ __forceinline__ Stat4 warp_reduce(Stat4 s) {
     return s;
 }
 
-// MODE 0: statistics only (a shard whose outputs are written later by the apply pass of another call)
-// MODE 1: write raw float32 values (and, if STATS, reduce them) - the normalisation follows as an in-place
-//         scaling pass (k_attr_scale), so the trigonometry and the gathers run ONCE per edge
-template <bool STATS, bool WRITE>
-__global__ void __launch_bounds__(ATTR_THREADS) k_edge_attrs(
+// STATS: reduce the raw values (a shard's statistics, or the single-GPU first pass).
+// WRITE: store the raw float32 values - the normalisation follows as an in-place scaling pass (k_attr_scale), so
+//        the trigonometry and the gathers run ONCE per edge.
+// J edges per lane, interleaved by 32 so that every index load / store of the warp is one contiguous run.
+template <bool STATS, bool WRITE, int J>
+__global__ void __launch_bounds__(ATTR_THREADS, J == 4 ? 2 : (J == 2 ? 3 : 4)) k_edge_attrs(
     const int32_t* __restrict__ esrc, const int32_t* __restrict__ edst, int64_t n_edges,
-    const float2* __restrict__ s_ll, const float4* __restrict__ s_xyzc, const float2* __restrict__ t_ll,
-    const float4* __restrict__ t_xyzc, const double2* __restrict__ t_quat, int want_len, int len_invert_now,
-    float* __restrict__ out_len, int want_dir, int dir_rotated, float* __restrict__ out_dir,
-    double* __restrict__ ws) {
+    const float4* __restrict__ s_rec, const double2* __restrict__ t_rec, int want_len, int len_invert_now,
+    float* __restrict__ out_len, int want_dir, int dir_rotated, float* __restrict__ out_dir, double* __restrict__ ws) {
     Stat4 st_len, st_dir;
     st_len.init();
     st_dir.init();
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n_edges; e += stride) {
-        int s = __ldg(esrc + e), t = __ldg(edst + e);
-        float2 sl = __ldg(s_ll + s), tl = __ldg(t_ll + t);
-        float4 sx = __ldg(s_xyzc + s);
-        if (want_len) {
-            float ct = __ldg(&t_xyzc[t].w);
-            float v = edge_length_raw(sl, sx.w, tl, ct);
-            if (STATS) st_len.add((double)v);
-            if (WRITE) out_len[e] = len_invert_now ? __fsub_rn(1.0f, v) : v;
+    const int lane = threadIdx.x & 31;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t n_tiles = (n_edges + 32 * J - 1) / (32 * J);
+    for (int64_t tile = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; tile < n_tiles; tile += n_warps) {
+        const int64_t base = tile * (32 * J) + lane;
+        int s[J], t[J];
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+            int64_t e = base + 32 * j;
+            e = e < n_edges ? e : n_edges - 1;  // tail lanes repeat the last edge (never stored, never counted)
+            s[j] = __ldg(esrc + e);
+            t[j] = __ldg(edst + e);
         }
-        if (want_dir) {
-            if (dir_rotated) {
-                double2 qa = __ldg(t_quat + 2 * (int64_t)t);
-                double qw = __ldg(&t_quat[2 * (int64_t)t + 1].x);
-                double d0, d1;
-                edge_direction_rotated(sx, qa.x, qa.y, qw, d0, d1);
-                if (STATS) {
-                    st_dir.add(d0);
-                    st_dir.add(d1);
+        float4 sx[J];
+        float2 sl[J];
+        double2 qa[J], qb[J];
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+            sx[j] = __ldg(s_rec + 2 * (int64_t)s[j]);
+            sl[j] = __ldg(reinterpret_cast<const float2*>(s_rec + 2 * (int64_t)s[j] + 1));
+            qa[j] = __ldg(t_rec + 2 * (int64_t)t[j]);
+            qb[j] = __ldg(t_rec + 2 * (int64_t)t[j] + 1);
+        }
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+            const int64_t e = base + 32 * j;
+            const bool live = e < n_edges;
+            long long packed = __double_as_longlong(qb[j].y);
+            float2 tl = make_float2(__int_as_float((int)(packed & 0xffffffffll)), __int_as_float((int)(packed >> 32)));
+            if (want_len) {
+                float st_unused, ct;
+                agx_np_sincosf(tl.x, st_unused, ct);  // numpy's float32 cos(lat) of the target
+                float v = edge_length_raw(sl[j], sx[j].w, tl, ct);
+                if (STATS && live) st_len.add((double)v, v);
+                if (WRITE && live) out_len[e] = len_invert_now ? __fsub_rn(1.0f, v) : v;
+            }
+            if (want_dir) {
+                if (dir_rotated) {
+                    double d0, d1;
+                    edge_direction_rotated(sx[j], qa[j].x, qa[j].y, qb[j].x, d0, d1);
+                    float f0 = (float)d0, f1 = (float)d1;
+                    if (STATS && live) {
+                        st_dir.add(d0, f0);
+                        st_dir.add(d1, f1);
+                    }
+                    if (WRITE && live) reinterpret_cast<float2*>(out_dir)[e] = make_float2(f0, f1);
+                } else {
+                    // directional_edge_features(..., relative_to_rotated_target=False): loc2 - loc1 in float32
+                    float d0 = __fsub_rn(tl.x, sl[j].x), d1 = __fsub_rn(tl.y, sl[j].y);
+                    if (STATS && live) {
+                        st_dir.add((double)d0, d0);
+                        st_dir.add((double)d1, d1);
+                    }
+                    if (WRITE && live) reinterpret_cast<float2*>(out_dir)[e] = make_float2(d0, d1);
                 }
-                if (WRITE) reinterpret_cast<float2*>(out_dir)[e] = make_float2((float)d0, (float)d1);
-            } else {
-                // directional_edge_features(..., relative_to_rotated_target=False): loc2 - loc1 in float32
-                float d0 = __fsub_rn(tl.x, sl.x), d1 = __fsub_rn(tl.y, sl.y);
-                if (STATS) {
-                    st_dir.add((double)d0);
-                    st_dir.add((double)d1);
-                }
-                if (WRITE) reinterpret_cast<float2*>(out_dir)[e] = make_float2(d0, d1);
             }
         }
     }
@@ -223,7 +289,7 @@ __global__ void __launch_bounds__(ATTR_THREADS) k_edge_attrs(
         __shared__ Stat4 sm[2][ATTR_THREADS / 32];
         st_len = warp_reduce(st_len);
         st_dir = warp_reduce(st_dir);
-        int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        int warp = threadIdx.x >> 5;
         if (lane == 0) {
             sm[0][warp] = st_len;
             sm[1][warp] = st_dir;
@@ -235,8 +301,8 @@ __global__ void __launch_bounds__(ATTR_THREADS) k_edge_attrs(
                 st_dir.merge(sm[1][w]);
             }
             double* p = ws + (int64_t)ATTR_STAT_FIELDS * (2 + blockIdx.x);
-            p[0] = st_len.sum; p[1] = st_len.sumsq; p[2] = st_len.mn; p[3] = st_len.mx;
-            p[4] = st_dir.sum; p[5] = st_dir.sumsq; p[6] = st_dir.mn; p[7] = st_dir.mx;
+            st_len.store(p);
+            st_dir.store(p + 4);
         }
     }
 }
@@ -293,16 +359,16 @@ __global__ void __launch_bounds__(256) k_attr_scale(float* __restrict__ out_len,
 // One 256-thread block: thread t folds partials t, t+256, ... in order, then a fixed shuffle/shared tree -
 // the association order depends only on n_blocks, so the result is reproducible run to run.
 __global__ void __launch_bounds__(256) k_attr_fold(const double* __restrict__ ws, int n_blocks, double* __restrict__ stats) {
-    Stat4 L, D;
+    Stat4D L, D;
     L.init();
     D.init();
     for (int b = threadIdx.x; b < n_blocks; b += 256) {
         const double* p = ws + (int64_t)ATTR_STAT_FIELDS * (2 + b);
-        Stat4 l = {p[0], p[1], p[2], p[3]}, d = {p[4], p[5], p[6], p[7]};
+        Stat4D l = {p[0], p[1], p[2], p[3]}, d = {p[4], p[5], p[6], p[7]};
         L.merge(l);
         D.merge(d);
     }
-    __shared__ Stat4 sm[2][8];
+    __shared__ Stat4D sm[2][8];
     L = warp_reduce(L);
     D = warp_reduce(D);
     int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -355,43 +421,70 @@ __global__ void k_attr_params(double* __restrict__ ws, const double* __restrict_
     }
 }
 
-static int attrs_check(const int32_t* edge_src, const int32_t* edge_dst, int64_t n_edges, const float* src_latlon,
-                       const float* src_xyzc, const float* dst_latlon, const float* dst_xyzc, const double* dst_quat,
-                       int want_dir, int dir_rotated, const double* workspace) {
+static int attrs_check(const int32_t* edge_src, const int32_t* edge_dst, int64_t n_edges, const float* src_rec,
+                       const double* dst_rec, const double* workspace) {
     AGX_REQUIRE(n_edges >= 0, AGX_ERR_ARG, "agx_edge_attrs: n_edges < 0");
     if (n_edges == 0) return AGX_OK;
-    AGX_REQUIRE(edge_src && edge_dst && src_latlon && src_xyzc && dst_latlon && dst_xyzc && workspace, AGX_ERR_ARG,
-                "agx_edge_attrs: NULL buffer");
-    AGX_REQUIRE(!(want_dir && dir_rotated) || dst_quat, AGX_ERR_ARG, "agx_edge_attrs: rotated directions need dst_quat");
+    AGX_REQUIRE(edge_src && edge_dst && src_rec && dst_rec && workspace, AGX_ERR_ARG, "agx_edge_attrs: NULL buffer");
+    AGX_REQUIRE(((uintptr_t)src_rec & 15) == 0 && ((uintptr_t)dst_rec & 15) == 0, AGX_ERR_ARG,
+                "agx_edge_attrs: node records must be 16-byte aligned");
     return AGX_OK;
 }
 
-static inline int attrs_grid(int64_t n_edges) {
-    int grid = agx_grid(n_edges, ATTR_THREADS, 8);
+// edges per lane and tile (AGX_ATTR_J=1|2|4 overrides, for tuning)
+static inline int attrs_j() {
+    static int j = 0;
+    if (j == 0) {
+        j = 2;
+        if (const char* env = getenv("AGX_ATTR_J")) {
+            int v = atoi(env);
+            if (v == 1 || v == 2 || v == 4) j = v;
+        }
+    }
+    return j;
+}
+
+static inline int attrs_grid(int64_t n_edges, int j) {
+    int grid = agx_grid((n_edges + j - 1) / j, ATTR_THREADS, j == 4 ? 2 : (j == 2 ? 3 : 4));
     return grid > ATTR_MAX_BLOCKS ? ATTR_MAX_BLOCKS : grid;
 }
 
-#define ATTR_KERNEL_ARGS                                                                                             \
-    edge_src, edge_dst, n_edges, (const float2*)src_latlon, (const float4*)src_xyzc, (const float2*)dst_latlon,      \
-        (const float4*)dst_xyzc, (const double2*)dst_quat
+#define ATTR_KERNEL_ARGS edge_src, edge_dst, n_edges, (const float4*)src_rec, (const double2*)dst_rec
+
+template <int J>
+static void attrs_launch(bool stats, bool write, int grid, cudaStream_t stream, const int32_t* edge_src,
+                         const int32_t* edge_dst, int64_t n_edges, const float* src_rec, const double* dst_rec,
+                         int want_len, int len_invert_now, float* out_len, int want_dir, int dir_rotated, float* out_dir,
+                         double* workspace) {
+    if (stats && write)
+        k_edge_attrs<true, true, J><<<grid, ATTR_THREADS, 0, stream>>>(ATTR_KERNEL_ARGS, want_len, len_invert_now, out_len,
+                                                                      want_dir, dir_rotated, out_dir, workspace);
+    else if (stats)
+        k_edge_attrs<true, false, J><<<grid, ATTR_THREADS, 0, stream>>>(ATTR_KERNEL_ARGS, want_len, 0, nullptr, want_dir,
+                                                                       dir_rotated, nullptr, workspace);
+    else
+        k_edge_attrs<false, true, J><<<grid, ATTR_THREADS, 0, stream>>>(ATTR_KERNEL_ARGS, want_len, len_invert_now, out_len,
+                                                                       want_dir, dir_rotated, out_dir, workspace);
+}
 
 // pass A: raw values of the local edges -> out_* (float32) and/or stats[8]
-static int attrs_raw(const int32_t* edge_src, const int32_t* edge_dst, int64_t n_edges, const float* src_latlon,
-                     const float* src_xyzc, const float* dst_latlon, const float* dst_xyzc, const double* dst_quat,
-                     int want_len, int len_invert_now, float* out_len, int want_dir, int dir_rotated, float* out_dir,
-                     bool write, double* stats, double* workspace, cudaStream_t stream) {
+static int attrs_raw(const int32_t* edge_src, const int32_t* edge_dst, int64_t n_edges, const float* src_rec,
+                     const double* dst_rec, int want_len, int len_invert_now, float* out_len, int want_dir,
+                     int dir_rotated, float* out_dir, bool write, double* stats, double* workspace, cudaStream_t stream) {
     int grid = 0;
     if (n_edges > 0 && (want_len || want_dir)) {
-        grid = attrs_grid(n_edges);
-        if (stats && write)
-            k_edge_attrs<true, true><<<grid, ATTR_THREADS, 0, stream>>>(ATTR_KERNEL_ARGS, want_len, len_invert_now, out_len,
-                                                                       want_dir, dir_rotated, out_dir, workspace);
-        else if (stats)
-            k_edge_attrs<true, false><<<grid, ATTR_THREADS, 0, stream>>>(ATTR_KERNEL_ARGS, want_len, 0, nullptr, want_dir,
-                                                                        dir_rotated, nullptr, workspace);
+        int j = attrs_j();
+        grid = attrs_grid(n_edges, j);
+#define ATTR_LAUNCH(J)                                                                                                \
+    attrs_launch<J>(stats != nullptr, write, grid, stream, edge_src, edge_dst, n_edges, src_rec, dst_rec, want_len,      \
+                    len_invert_now, out_len, want_dir, dir_rotated, out_dir, workspace)
+        if (j == 1)
+            ATTR_LAUNCH(1);
+        else if (j == 2)
+            ATTR_LAUNCH(2);
         else
-            k_edge_attrs<false, true><<<grid, ATTR_THREADS, 0, stream>>>(ATTR_KERNEL_ARGS, want_len, len_invert_now, out_len,
-                                                                        want_dir, dir_rotated, out_dir, workspace);
+            ATTR_LAUNCH(4);
+#undef ATTR_LAUNCH
         agx_note_launch(1);
     }
     if (stats) {
@@ -420,33 +513,29 @@ static int attrs_scale(int64_t n_edges, int len_norm, int len_invert, float* out
 }
 
 extern "C" int agx_edge_attrs_stats(const int32_t* edge_src, const int32_t* edge_dst, int64_t n_edges,
-                                    const float* src_latlon, const float* src_xyzc, const float* dst_latlon,
-                                    const float* dst_xyzc, const double* dst_quat, int want_len, int want_dir,
+                                    const float* src_rec, const double* dst_rec, int want_len, int want_dir,
                                     int dir_rotated, float* out_len, float* out_dir, double* stats, double* workspace,
                                     void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     AGX_REQUIRE(stats != nullptr, AGX_ERR_ARG, "agx_edge_attrs_stats: stats is NULL");
-    int rc = attrs_check(edge_src, edge_dst, n_edges, src_latlon, src_xyzc, dst_latlon, dst_xyzc, dst_quat, want_dir,
-                         dir_rotated, workspace);
-    if (rc) return rc;
     AGX_REQUIRE(workspace != nullptr, AGX_ERR_ARG, "agx_edge_attrs_stats: workspace is NULL");
+    int rc = attrs_check(edge_src, edge_dst, n_edges, src_rec, dst_rec, workspace);
+    if (rc) return rc;
     bool write = (want_len && out_len) || (want_dir && out_dir);
     AGX_REQUIRE(!write || ((!want_len || out_len) && (!want_dir || out_dir)), AGX_ERR_ARG,
                 "agx_edge_attrs_stats: give every requested output buffer or none");
-    return attrs_raw(edge_src, edge_dst, n_edges, src_latlon, src_xyzc, dst_latlon, dst_xyzc, dst_quat, want_len, 0,
-                     out_len, want_dir, dir_rotated, out_dir, write, stats, workspace, stream);
+    return attrs_raw(edge_src, edge_dst, n_edges, src_rec, dst_rec, want_len, 0, out_len, want_dir, dir_rotated, out_dir,
+                     write, stats, workspace, stream);
 }
 
 extern "C" int agx_edge_attrs_apply(const int32_t* edge_src, const int32_t* edge_dst, int64_t n_edges,
-                                    const float* src_latlon, const float* src_xyzc, const float* dst_latlon,
-                                    const float* dst_xyzc, const double* dst_quat, int len_norm, int len_invert,
+                                    const float* src_rec, const double* dst_rec, int len_norm, int len_invert,
                                     float* out_len, int dir_norm, int dir_rotated, float* out_dir, const double* stats,
                                     int64_t n_edges_global, int raw_present, double* workspace, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     int want_len = len_norm >= 0, want_dir = dir_norm >= 0;
     AGX_REQUIRE(len_norm <= AGX_NORM_UNIT_STD && dir_norm <= AGX_NORM_UNIT_STD, AGX_ERR_ARG, "agx_edge_attrs: unknown norm code");
-    int rc = attrs_check(edge_src, edge_dst, n_edges, src_latlon, src_xyzc, dst_latlon, dst_xyzc, dst_quat, want_dir,
-                         dir_rotated, workspace);
+    int rc = attrs_check(edge_src, edge_dst, n_edges, src_rec, dst_rec, workspace);
     if (rc) return rc;
     if (n_edges == 0 || (!want_len && !want_dir)) return AGX_OK;
     AGX_REQUIRE(!want_len || out_len, AGX_ERR_ARG, "agx_edge_attrs: out_len is NULL");
@@ -455,24 +544,21 @@ extern "C" int agx_edge_attrs_apply(const int32_t* edge_src, const int32_t* edge
     AGX_REQUIRE(!need_stats || stats, AGX_ERR_ARG, "agx_edge_attrs_apply: this normalisation needs the global statistics");
     AGX_REQUIRE(n_edges_global >= n_edges, AGX_ERR_ARG, "agx_edge_attrs_apply: n_edges_global < n_edges");
     if (!raw_present) {
-        rc = attrs_raw(edge_src, edge_dst, n_edges, src_latlon, src_xyzc, dst_latlon, dst_xyzc, dst_quat, want_len, 0,
-                       out_len, want_dir, dir_rotated, out_dir, true, nullptr, workspace, stream);
+        rc = attrs_raw(edge_src, edge_dst, n_edges, src_rec, dst_rec, want_len, 0, out_len, want_dir, dir_rotated, out_dir,
+                       true, nullptr, workspace, stream);
         if (rc) return rc;
     }
     return attrs_scale(n_edges, len_norm, len_invert, out_len, dir_norm, dir_rotated, out_dir, stats, n_edges_global,
                        workspace, stream);
 }
 
-extern "C" int agx_edge_attrs(const int32_t* edge_src, const int32_t* edge_dst, int64_t n_edges,
-                              const float* src_latlon, const float* src_xyzc, const float* dst_latlon,
-                              const float* dst_xyzc, const double* dst_quat, int len_norm, int len_invert,
-                              float* out_len, int dir_norm, int dir_rotated, float* out_dir, double* workspace,
-                              void* stream_) {
+extern "C" int agx_edge_attrs(const int32_t* edge_src, const int32_t* edge_dst, int64_t n_edges, const float* src_rec,
+                              const double* dst_rec, int len_norm, int len_invert, float* out_len, int dir_norm,
+                              int dir_rotated, float* out_dir, double* workspace, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     int want_len = len_norm >= 0, want_dir = dir_norm >= 0;
     AGX_REQUIRE(len_norm <= AGX_NORM_UNIT_STD && dir_norm <= AGX_NORM_UNIT_STD, AGX_ERR_ARG, "agx_edge_attrs: unknown norm code");
-    int rc = attrs_check(edge_src, edge_dst, n_edges, src_latlon, src_xyzc, dst_latlon, dst_xyzc, dst_quat, want_dir,
-                         dir_rotated, workspace);
+    int rc = attrs_check(edge_src, edge_dst, n_edges, src_rec, dst_rec, workspace);
     if (rc) return rc;
     if (n_edges == 0 || (!want_len && !want_dir)) return AGX_OK;
     AGX_REQUIRE(!want_len || out_len, AGX_ERR_ARG, "agx_edge_attrs: out_len is NULL");
@@ -480,8 +566,8 @@ extern "C" int agx_edge_attrs(const int32_t* edge_src, const int32_t* edge_dst, 
     bool need_stats = (want_len && len_norm > 0) || (want_dir && dir_norm > 0);
     double* stats = need_stats ? workspace + 6 : nullptr;  // ws[6..13]: between the parameters and the block partials
     // no normalisation: the raw pass writes the final values (an inversion needs no statistics)
-    rc = attrs_raw(edge_src, edge_dst, n_edges, src_latlon, src_xyzc, dst_latlon, dst_xyzc, dst_quat, want_len,
-                   need_stats ? 0 : len_invert, out_len, want_dir, dir_rotated, out_dir, true, stats, workspace, stream);
+    rc = attrs_raw(edge_src, edge_dst, n_edges, src_rec, dst_rec, want_len, need_stats ? 0 : len_invert, out_len, want_dir,
+                   dir_rotated, out_dir, true, stats, workspace, stream);
     if (rc || !need_stats) return rc;
     return attrs_scale(n_edges, len_norm, len_invert, out_len, dir_norm, dir_rotated, out_dir, stats, n_edges, workspace,
                        stream);

@@ -115,16 +115,43 @@ __device__ __forceinline__ int agx_cell_of(float x, float y, float z, int cells)
     return (face * cells + i) * cells + j;
 }
 
-// float32 unit vector for the SEARCH: float64 trig, rounded once (|error| <= 2^-25 per component).
+// sin / cos in float64 to <= 1e-11 absolute (Cody-Waite reduction by pi/2 in two parts, Taylor to r^11 / r^12 on
+// |r| <= pi/4: truncation 7e-12) - a third of the instructions of the correctly rounded library sincos, and 2^-25
+// (the float32 rounding of the result) is all the search needs.
+__device__ __forceinline__ void agx_sincos_search(double x, double& s, double& c) {
+    double k = rint(x * 0.6366197723675814);
+    double r = fma(-k, 1.5707963267948966, x);
+    r = fma(-k, 6.123233995736766e-17, r);
+    double r2 = r * r;
+    double ps = fma(r2, -2.505210838544172e-8, 2.7557319223985893e-6);
+    ps = fma(ps, r2, -1.984126984126984e-4);
+    ps = fma(ps, r2, 8.333333333333333e-3);
+    ps = fma(ps, r2, -1.6666666666666666e-1);
+    double sr = fma(ps * r2, r, r);
+    double pc = fma(r2, 2.08767569878681e-9, -2.755731922398589e-7);
+    pc = fma(pc, r2, 2.48015873015873e-5);
+    pc = fma(pc, r2, -1.388888888888889e-3);
+    pc = fma(pc, r2, 4.1666666666666664e-2);
+    pc = fma(pc, r2, -0.5);
+    double cr = fma(pc, r2, 1.0);
+    int q = (int)k;
+    s = (q & 1) ? cr : sr;
+    c = (q & 1) ? sr : cr;
+    if (q & 2) s = -s;
+    if ((q + 1) & 2) c = -c;
+}
+
+// float32 unit vector for the SEARCH: float64 trig (<= 1e-11), products, rounded once - every component is within
+// 2^-25 + 3e-11 of the exact value.
 __device__ __forceinline__ float3 agx_search_xyz(float2 latlon) {
     double sl, cl, so, co;
-    sincos((double)latlon.x, &sl, &cl);
-    sincos((double)latlon.y, &so, &co);
+    agx_sincos_search((double)latlon.x, sl, cl);
+    agx_sincos_search((double)latlon.y, so, co);
     return make_float3((float)(cl * co), (float)(cl * so), (float)sl);
 }
 
 // Bound on |fp32 chord^2 - exact chord^2| for two search vectors (see DESIGN.md "FP32 filter margin"):
-// each component carries <= 2^-25 absolute error, the differences <= 2^-24 (+ one rounding), so
+// each component carries <= 2^-25 (+ 3e-11) absolute error, the differences <= 2^-24 (+ one rounding), so
 // |err| <= 2*sqrt(3)*2^-24*chord + fp32 evaluation error (<= 4 ulp of chord^2) + 3*2^-48.
 // 4.2e-7*chord + 1e-6*chord^2 + 1e-13 covers it with >2x slack.
 __device__ __forceinline__ float agx_chord2_margin(float d2) {
@@ -184,6 +211,23 @@ __device__ __forceinline__ void agx_np_sincosf(float x, float& s_out, float& c_o
     if (ic & 2) vc = __fsub_rn(0.0f, vc);
     s_out = vs;
     c_out = vc;
+}
+
+// numpy's float32 sin(x), bit for bit, with a short cut for |x| < ~pi/4 (quadrant 0: the argument reduction is the
+// identity and only the sine polynomial is needed) - the half-differences of an edge's endpoints.
+__device__ __forceinline__ float agx_np_sinf_short(float x) {
+    float q = __fsub_rn(__fmaf_rn(x, 0x1.45f306p-1f, 0x1.8p+23f), 0x1.8p+23f);
+    if (q == 0.0f) {
+        float r2 = __fmul_rn(x, x);
+        float s = __fmaf_rn(0x1.7d3bbcp-19f, r2, -0x1.a06bbap-13f);
+        s = __fmaf_rn(s, r2, 0x1.11119ap-07f);
+        s = __fmaf_rn(s, r2, -0x1.555556p-03f);
+        s = __fmaf_rn(s, r2, 0.0f);
+        return __fmaf_rn(s, x, x);
+    }
+    float s, c;
+    agx_np_sincosf(x, s, c);
+    return s;
 }
 
 // warp helpers

@@ -19,6 +19,27 @@ __global__ void __launch_bounds__(256) k_index_cells(const float2* __restrict__ 
     }
 }
 
+// the search vectors on their own (tests pin their error bound, which the FP32 filter margin is derived from)
+__global__ void __launch_bounds__(256) k_search_vectors(const float2* __restrict__ latlon, int64_t n, float* __restrict__ xyz) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float3 p = agx_search_xyz(latlon[i]);
+        xyz[3 * i] = p.x;
+        xyz[3 * i + 1] = p.y;
+        xyz[3 * i + 2] = p.z;
+    }
+}
+
+extern "C" int agx_search_vectors(const float* latlon, int64_t n, float* xyz, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    AGX_REQUIRE(n >= 0, AGX_ERR_ARG, "agx_search_vectors: n < 0");
+    if (n == 0) return AGX_OK;
+    AGX_REQUIRE(latlon && xyz, AGX_ERR_ARG, "agx_search_vectors: NULL buffer");
+    k_search_vectors<<<agx_grid(n, 256, 8), 256, 0, stream>>>((const float2*)latlon, n, xyz);
+    AGX_LAUNCH_OK();
+    agx_note_launch(1);
+    return AGX_OK;
+}
+
 __global__ void __launch_bounds__(256) k_index_scatter(const float4* __restrict__ rec, const int* __restrict__ cell_of,
                                                         int64_t n, const int64_t* __restrict__ cell_start64,
                                                         int* __restrict__ fill, float4* __restrict__ out) {

@@ -12,7 +12,10 @@
 //      issues a 1-D bulk async copy (TMA, cp.async.bulk -> UBLKCP) of the run into the warp's shared-memory
 //      stage, completion tracked by an mbarrier (expect_tx / complete_tx);
 //   3. every lane scans the staged candidates with broadcast LDS.128: squared chord on the FP32 FMA pipe,
-//      top-(k+1) kept in registers;
+//      top-(k+1) kept in registers as ONE 32-bit key per entry - the float bits of chord^2 with the low 9 bits
+//      replaced by the candidate's stage position - so an insertion is a min/max network (2 integer ops per
+//      entry, no compares, no selects).  The 2^-14 relative truncation is added to the ambiguity band; exact
+//      FP32 distances and indices of the k+1 survivors are recovered from the stage afterwards;
 //   4. a lane whose k-th distance (+ margins) does not fit inside the first cap, and tiles whose window does
 //      not fit the stage, fall back to the per-thread search (cap growth until it provably holds the k-th
 //      neighbour);
@@ -68,6 +71,53 @@ struct TopF {  // ascending d, CAP entries in registers (ties in arbitrary but d
     }
     __device__ __forceinline__ void offer(float cd, int ci) {
         if (cd < d[CAP - 1]) insert(cd, ci);
+    }
+    // compare-exchange of entries i < j (no-op for positions the list does not have)
+    __device__ __forceinline__ void order(int i, int j) {
+        if (j >= CAP) return;
+        bool sw = d[j] < d[i];
+        float td = d[i];
+        int ti = id[i];
+        d[i] = sw ? d[j] : td;
+        id[i] = sw ? id[j] : ti;
+        d[j] = sw ? td : d[j];
+        id[j] = sw ? ti : id[j];
+    }
+};
+
+// Packed top list for the staged scan: key = (bits(chord^2) & ~KEY_POS_MASK) | stage position.  chord^2 >= +0 and
+// finite, so unsigned integer order is float order; truncation lowers a value by < 2^-14 relative.
+#define KEY_POS_BITS 9
+#define KEY_POS_MASK ((1u << KEY_POS_BITS) - 1u)
+#define KEY_EMPTY 0x7f800000u  // +inf, position 0: above every real key
+static_assert(KNN_STAGE <= (1 << KEY_POS_BITS), "stage positions must fit the key's position field");
+
+template <int CAP>
+struct TopKey {
+    unsigned key[CAP];
+    __device__ __forceinline__ void reset() {
+#pragma unroll
+        for (int s = 0; s < CAP; ++s) key[s] = KEY_EMPTY;
+    }
+    __device__ __forceinline__ void insert(unsigned c) {
+#pragma unroll
+        for (int s = 0; s < CAP; ++s) {
+            unsigned lo = min(key[s], c);
+            c = max(key[s], c);
+            key[s] = lo;
+        }
+    }
+    __device__ __forceinline__ void offer(unsigned c) {
+        if (CAP <= 4)
+            insert(c);  // 2*CAP integer ops: cheaper than a divergent branch around them
+        else if (c < key[CAP - 1])
+            insert(c);
+    }
+    __device__ __forceinline__ unsigned key_at(int i) const {
+        unsigned r = key[0];
+#pragma unroll
+        for (int s = 1; s < CAP; ++s) r = (i == s) ? key[s] : r;
+        return r;
     }
 };
 
@@ -132,13 +182,11 @@ __device__ __forceinline__ float chord2(float3 q, float4 c) {
     return fmaf(dx, dx, fmaf(dy, dy, dz * dz));
 }
 
-// true if the top list proves that the cap of squared chord t2 contains the k nearest neighbours
-template <int CAP>
-__device__ __forceinline__ bool knn_cap_sufficient(const TopF<CAP>& top, int k, float t2, float& need) {
-    float dk = top.d_at(k - 1);
-    bool have_k = top.id_at(k - 1) != 0x7fffffff;
+// true if k candidates within FP32 chord^2 dk prove that the cap of squared chord t2 contains the k nearest
+// neighbours (dk = +inf: fewer than k candidates found)
+__device__ __forceinline__ bool knn_cap_sufficient(float dk, float t2, float& need) {
     need = dk + 3.75f * agx_chord2_margin(dk);  // d_k + 3 margins (margin taken 1.25x)
-    return have_k && need <= t2;
+    return dk < __int_as_float(0x7f800000) && need <= t2;
 }
 
 // Per-thread search straight from global memory: grow the cap until it provably holds the k-th neighbour.
@@ -161,8 +209,9 @@ __device__ __forceinline__ void knn_thread_search(const KnnArgs& a, float3 qv, f
         }
         if (cap.everything) break;
         float need;
-        if (knn_cap_sufficient(top, a.k, t2, need)) break;
-        bool have_k = top.id_at(a.k - 1) != 0x7fffffff;
+        float dk = top.d_at(a.k - 1);
+        if (knn_cap_sufficient(dk, t2, need)) break;
+        bool have_k = dk < __int_as_float(0x7f800000);
         t2 = have_k ? fmaxf(need * 1.0001f, t2 * 1.5f) : t2 * 4.0f;
     }
 }
@@ -307,27 +356,53 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn(KnnArgs a) {
         TopF<CAP> top;
         bool staged = fits;
         float t2_thread = t2;
+        float dk = __int_as_float(0x7f800000);       // largest FP32 chord^2 among the k chosen candidates
+        float rest_lb = __int_as_float(0x7f800000);  // lower bound of the FP32 chord^2 of every other candidate
         if (fits) {
-            top.reset();
+            TopKey<CAP> tk;
+            tk.reset();
 #pragma unroll 4
             for (int p = 0; p < m_total; ++p) {
                 float4 c = stage[p];
-                top.offer(chord2(qv, c), __float_as_int(c.w));
+                tk.offer((__float_as_uint(chord2(qv, c)) & ~KEY_POS_MASK) | (unsigned)p);
+            }
+            // exact FP32 distance and index of the k survivors, from the stage
+            top.reset();
+            float dmax = 0.0f;
+#pragma unroll
+            for (int s = 0; s < CAP - 1; ++s)
+                if (s < k) {
+                    unsigned key = tk.key[s];
+                    if (key < KEY_EMPTY) {
+                        float4 c = stage[key & KEY_POS_MASK];
+                        top.d[s] = chord2(qv, c);
+                        top.id[s] = __float_as_int(c.w);
+                    }
+                    dmax = fmaxf(dmax, top.d[s]);
+                }
+            dk = dmax;
+            rest_lb = __uint_as_float(tk.key_at(k) & ~KEY_POS_MASK);
+            if (CAP <= 4) {  // ascending exact FP32 distance among the chosen (keys order them only to 2^-14)
+                top.order(0, 1);
+                top.order(1, 2);
+                top.order(0, 1);
             }
             float need;
-            if (!knn_cap_sufficient(top, k, t2, need)) {
+            if (!knn_cap_sufficient(dk, t2, need)) {
                 // this lane needs a wider cap than the tile staged: finish it on its own
-                bool have_k = top.id_at(k - 1) != 0x7fffffff;
-                t2_thread = have_k ? fmaxf(need * 1.0001f, t2 * 1.5f) : t2 * 4.0f;
+                t2_thread = dk < __int_as_float(0x7f800000) ? fmaxf(need * 1.0001f, t2 * 1.5f) : t2 * 4.0f;
                 staged = false;
                 if (a.stats && active) atomicAdd(a.stats + 2, 1ull);
             }
         }
-        if (!staged) knn_thread_search<CAP>(a, qv, t2_thread, top, cap);
+        if (!staged) {
+            knn_thread_search<CAP>(a, qv, t2_thread, top, cap);
+            dk = top.d_at(k - 1);
+            rest_lb = top.d_at(k);  // +inf when there is no (k+1)-th candidate
+        }
         // ---- decide the set --------------------------------------------------------------------------
-        float dk = top.d_at(k - 1);
         float amb = dk + 2.5f * agx_chord2_margin(dk);  // d_k + 2 margins
-        bool ambiguous = (CAP > 1) && (top.id_at(k) != 0x7fffffff) && (top.d_at(k) <= amb);
+        bool ambiguous = (CAP > 1) && (rest_lb <= amb);
         if (active) {
             int32_t* os = a.out_src + q * k;
             if (!ambiguous) {

@@ -169,8 +169,8 @@ def node_tables(nodes, with_rotation: bool):
     from . import ops
 
     st = node_state(nodes)
-    if st.tables is None or (with_rotation and st.tables.quat is None):
-        st.tables = ops.NodeTables(st.x, with_rotation=with_rotation)
+    if st.tables is None:
+        st.tables = ops.NodeTables(st.x)
     return st.tables
 
 

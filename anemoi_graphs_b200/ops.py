@@ -183,6 +183,14 @@ class NeighbourIndex:
         return self.radius_fill(q, radius, offsets, total, out, 0, dst_base, stats)
 
 
+def search_vectors(x: torch.Tensor) -> torch.Tensor:
+    """float32 (n, 3) unit vectors the neighbour search filters with (see ``agx_search_vectors``)."""
+    x = _dev_x(x)
+    out = torch.empty((x.shape[0], 3), dtype=torch.float32, device=x.device)
+    check(load_library().agx_search_vectors(ptr(x), int(x.shape[0]), ptr(out), current_stream()))
+    return out
+
+
 def new_stats(device) -> torch.Tensor:
     return torch.zeros(4, dtype=torch.int64, device=device)
 
@@ -216,16 +224,59 @@ def grid_reference_distance(x: torch.Tensor) -> float:
 
 
 class NodeTables:
-    """Per-node tables for the attribute kernel: float32 (x, y, z, cos lat) and, for target nodes, the
-    float64 rotation quaternion."""
+    """Per-node records of the attribute kernel, one 32-byte record per role, built on first use:
 
-    def __init__(self, x: torch.Tensor, with_rotation: bool) -> None:
+    * ``src_rec`` float32 (n, 8): (x, y, z, cos lat, lat, lon, 0, 0) - the node as an edge SOURCE;
+    * ``dst_rec`` float64 (n, 4): (quat x, quat y, quat w, bits(lat, lon)) - the node as an edge TARGET
+      (rotation to the north pole, edges/directional.py:19-37).
+
+    ``with_rotation`` is accepted for compatibility; the target record always carries the quaternion."""
+
+    def __init__(self, x: torch.Tensor, with_rotation: bool = True) -> None:
         self.x = _dev_x(x)
-        n = int(self.x.shape[0])
-        self.xyzc = torch.empty((n, 4), dtype=torch.float32, device=self.x.device)
-        self.quat = torch.empty((n, 4), dtype=torch.float64, device=self.x.device) if with_rotation else None
-        with _span("node_tables", n):
-            check(load_library().agx_node_tables(ptr(self.x), n, ptr(self.xyzc), ptr(self.quat), current_stream()))
+        self.n = int(self.x.shape[0])
+        self._src = None
+        self._dst = None
+
+    def _build(self, want_src: bool, want_dst: bool) -> None:
+        dev = self.x.device
+        src = torch.empty((self.n, 8), dtype=torch.float32, device=dev) if want_src else None
+        dst = torch.empty((self.n, 4), dtype=torch.float64, device=dev) if want_dst else None
+        with _span("node_tables", self.n):
+            check(load_library().agx_node_tables(ptr(self.x), self.n, ptr(src), ptr(dst), current_stream()))
+        if want_src:
+            self._src = src
+        if want_dst:
+            self._dst = dst
+
+    def prepare(self, as_source: bool = False, as_target: bool = False) -> "NodeTables":
+        """Build the missing records of the requested roles in ONE kernel launch."""
+        need_src, need_dst = as_source and self._src is None, as_target and self._dst is None
+        if self.n and (need_src or need_dst):
+            self._build(need_src, need_dst)
+        elif need_src or need_dst:  # empty node set
+            if need_src:
+                self._src = torch.empty((0, 8), dtype=torch.float32, device=self.x.device)
+            if need_dst:
+                self._dst = torch.empty((0, 4), dtype=torch.float64, device=self.x.device)
+        return self
+
+    @property
+    def src_rec(self) -> torch.Tensor:
+        return self.prepare(as_source=True)._src
+
+    @property
+    def dst_rec(self) -> torch.Tensor:
+        return self.prepare(as_target=True)._dst
+
+    @property
+    def xyzc(self) -> torch.Tensor:
+        """float32 (n, 4) view: unit vector and cos(lat) with numpy's float32 bits."""
+        return self.src_rec[:, :4]
+
+    @property
+    def quat(self) -> torch.Tensor:
+        return self.dst_rec
 
 
 _workspace: dict = {}
@@ -269,9 +320,10 @@ def edge_attributes(
     dev = edge_index.device
     out_len = torch.empty((n_edges, 1), dtype=torch.float32, device=dev) if length else None
     out_dir = torch.empty((n_edges, 2), dtype=torch.float32, device=dev) if direction else None
-    if direction and direction_rotated and dst.quat is None:
-        raise ValueError("rotated directions need target NodeTables built with with_rotation=True")
     lib = load_library()
+    if src is dst:
+        src.prepare(as_source=True, as_target=True)
+    src_rec, dst_rec = src.src_rec, dst.dst_rec
     len_code = NORM_CODES[length_norm] if length else -1
     dir_code = NORM_CODES[direction_norm] if direction else -1
     rank, w = _device.world() if sharded else (0, 1)
@@ -281,9 +333,9 @@ def edge_attributes(
         with _span("edge_attrs", n_edges):
             check(
                 lib.agx_edge_attrs(
-                    edge_index[0].data_ptr(), edge_index[1].data_ptr(), n_edges, ptr(src.x), ptr(src.xyzc), ptr(dst.x),
-                    ptr(dst.xyzc), ptr(dst.quat), len_code, int(bool(length_invert)), ptr(out_len), dir_code,
-                    int(bool(direction_rotated)), ptr(out_dir), ptr(ws), stream,
+                    edge_index[0].data_ptr(), edge_index[1].data_ptr(), n_edges, ptr(src_rec), ptr(dst_rec), len_code,
+                    int(bool(length_invert)), ptr(out_len), dir_code, int(bool(direction_rotated)), ptr(out_dir),
+                    ptr(ws), stream,
                 )
             )  # fmt: skip
         return out_len, out_dir
@@ -300,8 +352,8 @@ def edge_attributes(
         with _span("edge_attrs_stats", m):
             check(
                 lib.agx_edge_attrs_stats(
-                    e_src, e_dst, m, ptr(src.x), ptr(src.xyzc), ptr(dst.x), ptr(dst.xyzc), ptr(dst.quat), int(length),
-                    int(direction), int(bool(direction_rotated)), o_len, o_dir, ptr(stats), ptr(ws), stream,
+                    e_src, e_dst, m, ptr(src_rec), ptr(dst_rec), int(length), int(direction),
+                    int(bool(direction_rotated)), o_len, o_dir, ptr(stats), ptr(ws), stream,
                 )
             )  # fmt: skip
         stats = _device.all_gather_stats(stats)
@@ -309,9 +361,8 @@ def edge_attributes(
     with _span("edge_attrs_apply", m):
         check(
             lib.agx_edge_attrs_apply(
-                e_src, e_dst, m, ptr(src.x), ptr(src.xyzc), ptr(dst.x), ptr(dst.xyzc), ptr(dst.quat), len_code,
-                int(bool(length_invert)), o_len, dir_code, int(bool(direction_rotated)), o_dir, ptr(stats), n_edges,
-                raw_present, ptr(ws), stream,
+                e_src, e_dst, m, ptr(src_rec), ptr(dst_rec), len_code, int(bool(length_invert)), o_len, dir_code,
+                int(bool(direction_rotated)), o_dir, ptr(stats), n_edges, raw_present, ptr(ws), stream,
             )
         )  # fmt: skip
     counts = [_device.shard_range(n_edges, r, w) for r in range(w)]

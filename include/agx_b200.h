@@ -58,6 +58,10 @@ int agx_index_build(const float* latlon /*DEV n*2*/, int64_t n, int cells_per_fa
                     double hint_radius, void* stream, agx_index_t** out);
 int agx_index_free(agx_index_t* index, void* stream);
 int agx_index_info(const agx_index_t* index, int64_t* n, int* cells_per_face);
+/* The float32 unit vectors the neighbour search filters with (float64 trig of the float32 (lat, lon), rounded once;
+ * every component within 2^-25 + 3e-11 of exact - the bound the FP32 filter margin of agx_knn / agx_radius_* is
+ * derived from).  Exposed so that tests can pin that bound; not needed to build a graph.                      */
+int agx_search_vectors(const float* latlon /*DEV n*2*/, int64_t n, float* xyz /*DEV n*3*/, void* stream);
 
 /* ---- KNN --------------------------------------------------------------------------------------
  * Replaces `kneighbors_graph(target, n_neighbors=k)` / `kneighbors(...)` (edges/builder.py:261-265,
@@ -94,19 +98,21 @@ int agx_max_positive(const double* values /*DEV n*/, int64_t n, double* out_valu
                      int64_t* out_index /*HOST*/, void* stream);
 
 /* ---- edge attributes ------------------------------------------------------------------------------
- * agx_node_tables: per node float32 (x, y, z, cos lat) with numpy's float32 sin/cos bits
- * (generate/transforms.py:106-110) and, if quat != NULL, the float64 quaternion (x, y, w, pad; z = 0) of
- * the rotation taking the node to the north pole (edges/directional.py:19-37, ε-nudge of
- * generate/transforms.py:133-140 included).
+ * agx_node_tables: everything the attribute kernel needs from ONE node, as one 32-byte record per role:
+ *   src_rec  float[8]  = (x, y, z, cos lat, lat, lon, 0, 0) - float32 unit vector and cos(lat) with numpy's
+ *            float32 sin/cos bits (generate/transforms.py:106-110, utils.py:84-103);
+ *   dst_rec  double[4] = (qx, qy, qw, bits(lat, lon)) - the float64 quaternion (z = 0) of the rotation taking the
+ *            node to the north pole (edges/directional.py:19-37, epsilon-nudge of generate/transforms.py:133-140
+ *            included); the 4th double carries the node's float32 (lat, lon) bit patterns (lat in the low word).
+ * Either pointer may be NULL (a node set used only as source / only as target).
  * agx_edge_attrs: replaces EdgeLength.compute / EdgeDirection.compute (edges/attributes.py:42-157):
  * raw values (float32 store) + global statistics in one pass over the edges, then - if a norm was asked for -
  * an in-place scaling pass.  len_norm / dir_norm = AGX_NORM_* or -1 to skip the attribute;
  * dir_rotated = luse_rotated_features.                                                          */
-int agx_node_tables(const float* latlon /*DEV n*2*/, int64_t n, float* xyzc /*DEV n*4*/,
-                    double* quat /*DEV n*4 or NULL*/, void* stream);
+int agx_node_tables(const float* latlon /*DEV n*2*/, int64_t n, float* src_rec /*DEV n*8 or NULL*/,
+                    double* dst_rec /*DEV n*4 or NULL, 32-byte aligned*/, void* stream);
 int agx_edge_attrs(const int32_t* edge_src /*DEV E*/, const int32_t* edge_dst /*DEV E*/, int64_t n_edges,
-                   const float* src_latlon, const float* src_xyzc, const float* dst_latlon,
-                   const float* dst_xyzc, const double* dst_quat /*needed for rotated dirs*/,
+                   const float* src_rec /*source node records*/, const double* dst_rec /*target node records*/,
                    int len_norm /*AGX_NORM_* or -1 = skip*/, int len_invert, float* out_len /*DEV E*/,
                    int dir_norm /*AGX_NORM_* or -1 = skip*/, int dir_rotated, float* out_dir /*DEV E*2*/,
                    double* workspace /*DEV, >= agx_edge_attrs_workspace() doubles*/, void* stream);
@@ -118,14 +124,12 @@ int64_t agx_edge_attrs_workspace(void);
  * gives {0, 0, +1e300, -1e300}).  The caller combines the shards' statistics (sum / min / max) and passes the
  * global ones, with the global edge count, to _apply, which normalises the local block in place
  * (raw_present = 1) or evaluates the raw values first (raw_present = 0).  normalise.py:20-55.              */
-int agx_edge_attrs_stats(const int32_t* edge_src, const int32_t* edge_dst, int64_t n_edges, const float* src_latlon,
-                         const float* src_xyzc, const float* dst_latlon, const float* dst_xyzc,
-                         const double* dst_quat, int want_len, int want_dir, int dir_rotated,
+int agx_edge_attrs_stats(const int32_t* edge_src, const int32_t* edge_dst, int64_t n_edges, const float* src_rec,
+                         const double* dst_rec, int want_len, int want_dir, int dir_rotated,
                          float* out_len /*DEV E or NULL*/, float* out_dir /*DEV E*2 or NULL*/,
                          double* stats /*DEV 8*/, double* workspace, void* stream);
-int agx_edge_attrs_apply(const int32_t* edge_src, const int32_t* edge_dst, int64_t n_edges, const float* src_latlon,
-                         const float* src_xyzc, const float* dst_latlon, const float* dst_xyzc,
-                         const double* dst_quat, int len_norm, int len_invert, float* out_len, int dir_norm,
+int agx_edge_attrs_apply(const int32_t* edge_src, const int32_t* edge_dst, int64_t n_edges, const float* src_rec,
+                         const double* dst_rec, int len_norm, int len_invert, float* out_len, int dir_norm,
                          int dir_rotated, float* out_dir, const double* stats /*DEV 8 or NULL if no norm*/,
                          int64_t n_edges_global, int raw_present, double* workspace, void* stream);
 

@@ -32,6 +32,38 @@ def ops():
 
 
 # ------------------------------------------------------------------------------------------------
+# search vectors: the error bound the FP32 filter margin is derived from
+# ------------------------------------------------------------------------------------------------
+def test_search_vectors_within_half_ulp_of_exact(ops):
+    lat, lon = grids.uniform_sphere(300000, seed=3)
+    x = grids.latlon_deg_to_x(lat, lon).numpy()
+    x[:6] = np.array(
+        [[np.pi / 2, 0], [-np.pi / 2, 3], [0, 0], [1.0, 2 * np.pi], [0.5, -np.pi], [-0.25, 700.0]], dtype=np.float32
+    )
+    got = ops.search_vectors(dev(x)).cpu().numpy().astype(np.float64)
+    la, lo = x[:, 0].astype(np.float64), x[:, 1].astype(np.float64)
+    want = np.stack([np.cos(la) * np.cos(lo), np.cos(la) * np.sin(lo), np.sin(la)], axis=1)
+    err = np.abs(got - want)
+    # float32 rounding of a value in [-1, 1] is at most 2^-25; the float64 trig adds < 3e-11
+    assert err.max() <= 2.0**-25 + 3e-11, err.max()
+
+
+def test_node_records_layout(ops):
+    """Source record = (x, y, z, cos lat, lat, lon, 0, 0); target record's 4th double carries the (lat, lon) bits."""
+    lat, lon = grids.uniform_sphere(5000, seed=4)
+    x = grids.latlon_deg_to_x(lat, lon).numpy()
+    t = ops.NodeTables(dev(x))
+    src, dst = t.src_rec.cpu().numpy(), t.dst_rec.cpu().numpy()
+    assert src.shape == (5000, 8) and dst.shape == (5000, 4)
+    np.testing.assert_array_equal(src[:, 4:6].view(np.int32), x.view(np.int32))
+    np.testing.assert_array_equal(src[:, 6:], 0)
+    packed = np.ascontiguousarray(dst[:, 3]).view(np.int32).reshape(-1, 2)
+    np.testing.assert_array_equal(packed, x.view(np.int32))
+    q = dst[:, :3]
+    np.testing.assert_allclose((q**2).sum(axis=1), 1.0, rtol=0, atol=1e-12)  # unit quaternion with z = 0
+
+
+# ------------------------------------------------------------------------------------------------
 # KNN
 # ------------------------------------------------------------------------------------------------
 def test_knn_toy_matches_reference(ops, golden):
