@@ -26,9 +26,11 @@ static inline int64_t ico_face_offset(int level) { return 20 * ((((int64_t)1 << 
 // ---------------------------------------------------------------------------------------------
 // subdivision
 // ---------------------------------------------------------------------------------------------
-__global__ void k_ico_lower_neighbours(const int32_t* __restrict__ faces, int64_t nf, int* __restrict__ cnt,
-                                       int32_t* __restrict__ lower) {
-    for (int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; f < nf; f += (int64_t)gridDim.x * blockDim.x) {
+// Every phase is a __device__ body over a (first, stride) index range so that it serves both the grid-wide
+// kernels of the large levels and the single-CTA kernel that runs all small levels back to back.
+__device__ __forceinline__ void ico_lower_neighbours(const int32_t* __restrict__ faces, int64_t nf, int* __restrict__ cnt,
+                                                     int32_t* __restrict__ lower, int64_t first, int64_t stride) {
+    for (int64_t f = first; f < nf; f += stride) {
         int v[3] = {faces[3 * f], faces[3 * f + 1], faces[3 * f + 2]};
 #pragma unroll
         for (int e = 0; e < 3; ++e) {
@@ -41,8 +43,9 @@ __global__ void k_ico_lower_neighbours(const int32_t* __restrict__ faces, int64_
     }
 }
 
-__global__ void k_ico_sort_lower(const int* __restrict__ cnt, int32_t* __restrict__ lower, int64_t nv) {
-    for (int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; u < nv; u += (int64_t)gridDim.x * blockDim.x) {
+__device__ __forceinline__ void ico_sort_lower(const int* __restrict__ cnt, int32_t* __restrict__ lower, int64_t nv,
+                                               int64_t first, int64_t stride) {
+    for (int64_t u = first; u < nv; u += stride) {
         int m = cnt[u];
         int32_t* l = lower + 6 * u;
         for (int i = 1; i < m; ++i) {
@@ -56,9 +59,10 @@ __global__ void k_ico_sort_lower(const int* __restrict__ cnt, int32_t* __restric
     }
 }
 
-__global__ void k_ico_midpoints(const int* __restrict__ cnt, const int32_t* __restrict__ lower,
-                                const int64_t* __restrict__ base, int64_t nv, double* __restrict__ vert) {
-    for (int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; u < nv; u += (int64_t)gridDim.x * blockDim.x) {
+__device__ __forceinline__ void ico_midpoints(const int* __restrict__ cnt, const int32_t* __restrict__ lower,
+                                              const int64_t* __restrict__ base, int64_t nv, double* __restrict__ vert,
+                                              int64_t first, int64_t stride) {
+    for (int64_t u = first; u < nv; u += stride) {
         int m = cnt[u];
         for (int s = 0; s < m; ++s) {
             int64_t v = lower[6 * u + s];
@@ -79,10 +83,10 @@ __device__ __forceinline__ int ico_mid(int a, int b, const int* cnt, const int32
     return (int)(nv + base[u] + pos);
 }
 
-__global__ void k_ico_faces(const int32_t* __restrict__ faces, int64_t nf, const int* __restrict__ cnt,
-                            const int32_t* __restrict__ lower, const int64_t* __restrict__ base, int64_t nv,
-                            int32_t* __restrict__ out) {
-    for (int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; f < nf; f += (int64_t)gridDim.x * blockDim.x) {
+__device__ __forceinline__ void ico_faces(const int32_t* __restrict__ faces, int64_t nf, const int* __restrict__ cnt,
+                                          const int32_t* __restrict__ lower, const int64_t* __restrict__ base, int64_t nv,
+                                          int32_t* __restrict__ out, int64_t first, int64_t stride) {
+    for (int64_t f = first; f < nf; f += stride) {
         int a = faces[3 * f], b = faces[3 * f + 1], c = faces[3 * f + 2];
         int m0 = ico_mid(a, b, cnt, lower, base, nv), m1 = ico_mid(b, c, cnt, lower, base, nv),
             m2 = ico_mid(c, a, cnt, lower, base, nv);
@@ -95,14 +99,108 @@ __global__ void k_ico_faces(const int32_t* __restrict__ faces, int64_t nf, const
 }
 
 // icosphere's refine_spherical: scalar = sqrt(dot(v**2, [1,1,1])); v += (v / scalar) * (radius - scalar)
-__global__ void k_ico_refine(double* __restrict__ vert, int64_t nv) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (int64_t)gridDim.x * blockDim.x) {
+__device__ __forceinline__ void ico_refine(double* __restrict__ vert, int64_t nv, int64_t first, int64_t stride) {
+    for (int64_t i = first; i < nv; i += stride) {
         double x = vert[3 * i], y = vert[3 * i + 1], z = vert[3 * i + 2];
         double scalar = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z)));
         double off = __dsub_rn(1.0, scalar);
         vert[3 * i] = __dadd_rn(x, __dmul_rn(__ddiv_rn(x, scalar), off));
         vert[3 * i + 1] = __dadd_rn(y, __dmul_rn(__ddiv_rn(y, scalar), off));
         vert[3 * i + 2] = __dadd_rn(z, __dmul_rn(__ddiv_rn(z, scalar), off));
+    }
+}
+
+#define GRID_RANGE (int64_t)blockIdx.x * blockDim.x + threadIdx.x, (int64_t)gridDim.x * blockDim.x
+
+__global__ void k_ico_lower_neighbours(const int32_t* __restrict__ faces, int64_t nf, int* __restrict__ cnt,
+                                       int32_t* __restrict__ lower) {
+    ico_lower_neighbours(faces, nf, cnt, lower, GRID_RANGE);
+}
+__global__ void k_ico_sort_lower(const int* __restrict__ cnt, int32_t* __restrict__ lower, int64_t nv) {
+    ico_sort_lower(cnt, lower, nv, GRID_RANGE);
+}
+__global__ void k_ico_midpoints(const int* __restrict__ cnt, const int32_t* __restrict__ lower,
+                                const int64_t* __restrict__ base, int64_t nv, double* __restrict__ vert) {
+    ico_midpoints(cnt, lower, base, nv, vert, GRID_RANGE);
+}
+__global__ void k_ico_faces(const int32_t* __restrict__ faces, int64_t nf, const int* __restrict__ cnt,
+                            const int32_t* __restrict__ lower, const int64_t* __restrict__ base, int64_t nv,
+                            int32_t* __restrict__ out) {
+    ico_faces(faces, nf, cnt, lower, base, nv, out, GRID_RANGE);
+}
+__global__ void k_ico_refine(double* __restrict__ vert, int64_t nv) { ico_refine(vert, nv, GRID_RANGE); }
+
+// Levels 0 .. n_steps of the subdivision in ONE CTA (the small levels are pure launch latency otherwise: nine
+// launches of a few microseconds per level).  Phases are separated by __syncthreads(), which also orders the
+// CTA's global-memory writes.  Step l reads level l and writes level l + 1; n_steps <= ICO_FUSED_STEPS.
+#define ICO_FUSED_THREADS 1024
+#define ICO_FUSED_STEPS 5  // up to level 5: 2 562 -> 10 242 vertices in the last fused step
+#define ICO_FUSED_ITEMS 3  // ceil(2562 / 1024) items of the per-vertex scan per thread
+
+struct IcoBase {
+    double v[36];
+    int32_t f[60];
+};
+
+__global__ void __launch_bounds__(ICO_FUSED_THREADS) k_ico_small_levels(IcoBase b, int n_steps, double* __restrict__ vert,
+                                                                        int32_t* __restrict__ faces_all, int* __restrict__ cnt,
+                                                                        int32_t* __restrict__ lower, int64_t* __restrict__ base) {
+    __shared__ int warp_sums[ICO_FUSED_THREADS / 32];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    if (t < 36) vert[t] = b.v[t];
+    if (t < 60) faces_all[t] = b.f[t];
+    __syncthreads();
+    int64_t nv = 12, nf = 20, face_off = 0;
+    for (int level = 0; level < n_steps; ++level) {
+        const int32_t* faces = faces_all + 3 * face_off;
+        int32_t* faces_next = faces_all + 3 * (face_off + nf);
+        for (int64_t i = t; i < nv; i += ICO_FUSED_THREADS) cnt[i] = 0;
+        __syncthreads();
+        ico_lower_neighbours(faces, nf, cnt, lower, t, ICO_FUSED_THREADS);
+        __syncthreads();
+        ico_sort_lower(cnt, lower, nv, t, ICO_FUSED_THREADS);
+        // exclusive scan of cnt[0 .. nv) -> base[0 .. nv]: thread t owns items [3t, 3t + 3)
+        int c[ICO_FUSED_ITEMS], mine = 0;
+#pragma unroll
+        for (int k = 0; k < ICO_FUSED_ITEMS; ++k) {
+            int64_t i = (int64_t)t * ICO_FUSED_ITEMS + k;
+            c[k] = i < nv ? cnt[i] : 0;
+            mine += c[k];
+        }
+        int incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        if (lane == 31) warp_sums[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            int w = warp_sums[lane], wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int v = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += v;
+            }
+            warp_sums[lane] = wi - w;
+        }
+        __syncthreads();
+        int64_t ex = warp_sums[warp] + incl - mine;
+#pragma unroll
+        for (int k = 0; k < ICO_FUSED_ITEMS; ++k) {
+            int64_t i = (int64_t)t * ICO_FUSED_ITEMS + k;
+            if (i <= nv) base[i] = ex;  // base[nv] = total (c[] is 0 beyond nv)
+            ex += c[k];
+        }
+        __syncthreads();
+        ico_midpoints(cnt, lower, base, nv, vert, t, ICO_FUSED_THREADS);
+        ico_faces(faces, nf, cnt, lower, base, nv, faces_next, t, ICO_FUSED_THREADS);
+        __syncthreads();
+        face_off += nf;
+        nv = 4 * nv - 6;  // 10 * 4^(l+1) + 2
+        nf *= 4;
+        ico_refine(vert, nv, t, ICO_FUSED_THREADS);
+        __syncthreads();
     }
 }
 
@@ -113,17 +211,6 @@ __global__ void k_ico_latlon(const double* __restrict__ vert, int64_t nv, float2
         double n2 = __dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z));
         latlon[i] = make_float2((float)asin(__ddiv_rn(z, n2)), (float)atan2(y, x));
     }
-}
-
-struct IcoBase {
-    double v[36];
-    int32_t f[60];
-};
-
-__global__ void k_ico_base(IcoBase b, double* __restrict__ vert, int32_t* __restrict__ faces) {
-    int t = threadIdx.x;
-    if (t < 36) vert[t] = b.v[t];
-    if (t < 60) faces[t] = b.f[t];
 }
 
 extern "C" int agx_icosphere(int max_level, double* vertices, int32_t* faces_all, float* latlon, void* stream_) {
@@ -142,21 +229,21 @@ extern "C" int agx_icosphere(int max_level, double* vertices, int32_t* faces_all
         for (int i = 0; i < 36; ++i) base0.v[i] = raw[i] / s;
         for (int i = 0; i < 60; ++i) base0.f[i] = f0[i];
     }
-    k_ico_base<<<1, 64, 0, stream>>>(base0, vertices, faces_all);
-    agx_note_launch(1);
-
     int64_t nv_max = ico_nv(max_level);
     agx_pool_keep_warm();
     int* cnt = nullptr;
     int32_t* lower = nullptr;
     int64_t* base = nullptr;
-    if (max_level > 0) {
-        int64_t nv_prev = ico_nv(max_level - 1);
+    {   // scratch sized for the coarser of every pair of levels (and at least level 0 for the fused kernel's init)
+        int64_t nv_prev = ico_nv(max_level > 0 ? max_level - 1 : 0);
         AGX_CUDA_OK(cudaMallocAsync(&cnt, nv_prev * sizeof(int), stream));
         AGX_CUDA_OK(cudaMallocAsync(&lower, 6 * nv_prev * sizeof(int32_t), stream));
         AGX_CUDA_OK(cudaMallocAsync(&base, (nv_prev + 1) * sizeof(int64_t), stream));
     }
-    for (int level = 0; level < max_level; ++level) {
+    const int fused_steps = max_level < ICO_FUSED_STEPS ? max_level : ICO_FUSED_STEPS;
+    k_ico_small_levels<<<1, ICO_FUSED_THREADS, 0, stream>>>(base0, fused_steps, vertices, faces_all, cnt, lower, base);
+    agx_note_launch(1);
+    for (int level = fused_steps; level < max_level; ++level) {
         int64_t nv = ico_nv(level), nf = ico_nf(level);
         const int32_t* faces = faces_all + 3 * ico_face_offset(level);
         int32_t* faces_next = faces_all + 3 * ico_face_offset(level + 1);
@@ -176,11 +263,9 @@ extern "C" int agx_icosphere(int max_level, double* vertices, int32_t* faces_all
         agx_note_launch(1);
     }
     AGX_LAUNCH_OK();
-    if (max_level > 0) {
-        AGX_CUDA_OK(cudaFreeAsync(cnt, stream));
-        AGX_CUDA_OK(cudaFreeAsync(lower, stream));
-        AGX_CUDA_OK(cudaFreeAsync(base, stream));
-    }
+    AGX_CUDA_OK(cudaFreeAsync(cnt, stream));
+    AGX_CUDA_OK(cudaFreeAsync(lower, stream));
+    AGX_CUDA_OK(cudaFreeAsync(base, stream));
     return AGX_OK;
 }
 

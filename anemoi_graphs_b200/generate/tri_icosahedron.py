@@ -14,21 +14,20 @@ import torch
 
 from .. import device as _device
 from .. import ops
-from .utils import get_coordinates_ordering
 
 
 class DeviceMesh:
     """What the hidden ``_nx_graph`` attribute holds here: the icosphere of a node set on the device."""
 
-    def __init__(self, icosphere: ops.Icosphere, node_ordering: np.ndarray) -> None:
+    def __init__(self, icosphere: ops.Icosphere, order_dev: torch.Tensor) -> None:
         self.icosphere = icosphere
-        self.node_ordering = node_ordering
+        self.order_dev = order_dev  # CUDA int64: icosphere vertex (or candidate row) at every graph position
 
     def number_of_nodes(self) -> int:
-        return int(len(self.node_ordering))
+        return int(self.order_dev.shape[0])
 
     def __getstate__(self):  # never pickled with device memory (``clean`` removes it anyway)
-        return {"icosphere": None, "node_ordering": self.node_ordering}
+        return {"icosphere": None, "order_dev": None}
 
 
 def get_icosphere(resolution: int) -> ops.Icosphere:
@@ -41,22 +40,31 @@ def get_latlon_coords_icosphere(resolution: int) -> np.ndarray:
     return get_icosphere(resolution).latlon.cpu().numpy()
 
 
-def _ordering_of(latlon_dev: torch.Tensor) -> np.ndarray:
-    """Host node ordering of device coordinates: one (2, N) column-major copy, two numpy argsorts."""
-    soa = latlon_dev.t().contiguous().cpu().numpy()
-    return get_coordinates_ordering(lat=soa[0], lon=soa[1])
+def _ordering_of(latlon_dev: torch.Tensor) -> torch.Tensor:
+    """Node ordering of device coordinates (generate/utils.py:15-33) as a CUDA int64 tensor.
+
+    The two argsorts are numpy's, on the host - they DEFINE the order (unstable sorts over tens of thousands of
+    tied keys, ``generate.utils.get_coordinates_ordering``).  The gathers around them (``lat[index]`` between the
+    sorts, ``index_latitude[index_longitude]`` after) run on the device, so the host only ever touches one
+    contiguous float32 column per sort."""
+    lat_dev = latlon_dev[:, 0].contiguous()
+    lon = latlon_dev[:, 1].contiguous().cpu().numpy()
+    index_latitude = torch.from_numpy(np.argsort(lon)).to(latlon_dev.device)
+    lat_sorted = lat_dev[index_latitude].cpu().numpy()
+    index_longitude = torch.from_numpy(np.argsort(lat_sorted)).to(latlon_dev.device)
+    return index_latitude[index_longitude.flip(0)]
 
 
 def create_tri_nodes(resolution: int, area_mask_builder=None):
     """Global (or area-limited) mesh nodes from a refined icosahedron (tri_icosahedron.py:24-58).
 
     Returns ``(mesh, coords_rad, node_ordering)``: the device mesh, the float32 vertex coordinates (CUDA tensor,
-    not ordered) and the order that sorts them by latitude and longitude (numpy, host)."""
+    not ordered) and the order that sorts them by latitude and longitude (CUDA int64)."""
     ico = get_icosphere(resolution)
     node_ordering = _ordering_of(ico.latlon)
 
     if area_mask_builder is not None:
-        area_mask = area_mask_builder.get_mask_device(ico.latlon).cpu().numpy()
+        area_mask = area_mask_builder.get_mask_device(ico.latlon)
         node_ordering = node_ordering[area_mask[node_ordering]]
 
     return DeviceMesh(ico, node_ordering), ico.latlon, node_ordering
@@ -97,7 +105,10 @@ def multiscale_edges(nodes, resolutions, x_hops: int = 1, area_mask_builder=None
     n_nodes = int(st.x.shape[0])
     node_type = nodes["node_type"]
     if node_type == "TriNodes" and area_mask_builder is None and n_nodes == ops.ico_num_vertices(ico.max_level):
-        order = torch.as_tensor(np.asarray(nodes["_node_ordering"]), dtype=torch.int32)
+        if isinstance(mesh, DeviceMesh) and mesh.order_dev is not None:
+            order = mesh.order_dev
+        else:
+            order = torch.as_tensor(np.asarray(nodes["_node_ordering"]))
         return ops.multiscale_tri_edges(ico, resolutions, x_hops, order)
     # limited-area / stretched: valid vertices by the area mask, vertex -> node by 1-NN
     nv = ops.ico_num_vertices(max(resolutions))

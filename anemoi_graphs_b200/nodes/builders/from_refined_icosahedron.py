@@ -55,9 +55,11 @@ class IcosahedralNodes(BaseNodeBuilder, ABC):
 
     def get_coordinates(self) -> torch.Tensor:
         """float32 (num_nodes, 2) coordinates in radians, in graph order."""
-        self.nx_graph, coords_rad, self.node_ordering = self.create_nodes()
-        order = torch.from_numpy(np.ascontiguousarray(self.node_ordering)).to(coords_rad.device, non_blocking=True)
+        self.nx_graph, coords_rad, order = self.create_nodes()
         self._x_device = coords_rad[order]  # == coords_rad[node_ordering], gathered on the device
+        # the hidden ``_node_ordering`` attribute is a host array in the reference: a pinned copy, complete when the
+        # enclosing deferred scope (or this builder's register_nodes) flushes
+        self.node_ordering = _device.to_host(order).numpy()
         return self._x_device if _device.is_resident() else _device.to_host(self._x_device)
 
     def register_nodes(self, graph):
@@ -69,7 +71,7 @@ class IcosahedralNodes(BaseNodeBuilder, ABC):
         return graph
 
     @abstractmethod
-    def create_nodes(self) -> tuple[object, np.ndarray, np.ndarray]: ...
+    def create_nodes(self) -> tuple[object, torch.Tensor, torch.Tensor]: ...
 
 
 class LimitedAreaIcosahedralNodes(IcosahedralNodes):
