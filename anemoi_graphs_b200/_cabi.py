@@ -51,7 +51,7 @@ SIGNATURES = {
     "agx_edge_attrs_apply": (
         c_int,
         [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p,
-         c_int64, c_int, c_void_p, c_void_p],
+         c_int, c_int64, c_int, c_void_p, c_void_p],
     ),  # fmt: skip
     "agx_icosphere": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "agx_multiscale_tri_count": (

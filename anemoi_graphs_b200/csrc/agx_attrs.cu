@@ -389,9 +389,19 @@ __global__ void __launch_bounds__(256) k_attr_fold(const double* __restrict__ ws
 
 // Global statistics -> normalisation parameters (normalise.py:33-52).
 // ws[0..1] = length (shift, div); ws[2..5] = direction (shift, 1/div, shift, div).
-__global__ void k_attr_params(double* __restrict__ ws, const double* __restrict__ stats, int64_t n_edges, int len_norm,
-                              int dir_norm) {
+__global__ void k_attr_params(double* __restrict__ ws, const double* __restrict__ stats_sets, int n_sets, int64_t n_edges,
+                              int len_norm, int dir_norm) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    // fold the per-shard statistics in order (one set on a single GPU): the same association on every rank
+    double stats[8] = {0.0, 0.0, 1e300, -1e300, 0.0, 0.0, 1e300, -1e300};
+    for (int r = 0; r < n_sets; ++r)
+        for (int b = 0; b < 8; b += 4) {
+            const double* p = stats_sets + 8 * r + b;
+            stats[b] += p[0];
+            stats[b + 1] += p[1];
+            stats[b + 2] = fmin(stats[b + 2], p[2]);
+            stats[b + 3] = fmax(stats[b + 3], p[3]);
+        }
     for (int which = 0; which < 2; ++which) {
         int norm = which ? dir_norm : len_norm;
         double shift = 0.0, div = 1.0;
@@ -497,12 +507,13 @@ static int attrs_raw(const int32_t* edge_src, const int32_t* edge_dst, int64_t n
 
 // pass B: statistics -> parameters, in-place scaling of the raw values
 static int attrs_scale(int64_t n_edges, int len_norm, int len_invert, float* out_len, int dir_norm, int dir_rotated,
-                       float* out_dir, const double* stats, int64_t n_edges_global, double* workspace,
+                       float* out_dir, const double* stats, int n_stat_sets, int64_t n_edges_global, double* workspace,
                        cudaStream_t stream) {
     int want_len = len_norm >= 0, want_dir = dir_norm >= 0;
     bool len_scale = want_len && len_norm > 0, dir_scale = want_dir && dir_norm > 0;
     if (n_edges == 0 || !(len_scale || dir_scale || (want_len && len_invert))) return AGX_OK;
-    k_attr_params<<<1, 32, 0, stream>>>(workspace, stats, n_edges_global, want_len ? len_norm : 0, want_dir ? dir_norm : 0);
+    k_attr_params<<<1, 32, 0, stream>>>(workspace, stats, n_stat_sets, n_edges_global, want_len ? len_norm : 0,
+                                        want_dir ? dir_norm : 0);
     int64_t work = (n_edges * (want_dir ? 2 : 1) + 3) / 4;
     k_attr_scale<<<agx_grid(work, 256, 8), 256, 0, stream>>>(want_len ? out_len : nullptr, n_edges, len_scale, len_invert,
                                                            want_dir ? out_dir : nullptr, 2 * n_edges, dir_scale,
@@ -531,7 +542,8 @@ extern "C" int agx_edge_attrs_stats(const int32_t* edge_src, const int32_t* edge
 extern "C" int agx_edge_attrs_apply(const int32_t* edge_src, const int32_t* edge_dst, int64_t n_edges,
                                     const float* src_rec, const double* dst_rec, int len_norm, int len_invert,
                                     float* out_len, int dir_norm, int dir_rotated, float* out_dir, const double* stats,
-                                    int64_t n_edges_global, int raw_present, double* workspace, void* stream_) {
+                                    int n_stat_sets, int64_t n_edges_global, int raw_present, double* workspace,
+                                    void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     int want_len = len_norm >= 0, want_dir = dir_norm >= 0;
     AGX_REQUIRE(len_norm <= AGX_NORM_UNIT_STD && dir_norm <= AGX_NORM_UNIT_STD, AGX_ERR_ARG, "agx_edge_attrs: unknown norm code");
@@ -541,15 +553,16 @@ extern "C" int agx_edge_attrs_apply(const int32_t* edge_src, const int32_t* edge
     AGX_REQUIRE(!want_len || out_len, AGX_ERR_ARG, "agx_edge_attrs: out_len is NULL");
     AGX_REQUIRE(!want_dir || out_dir, AGX_ERR_ARG, "agx_edge_attrs: out_dir is NULL");
     bool need_stats = (want_len && len_norm > 0) || (want_dir && dir_norm > 0);
-    AGX_REQUIRE(!need_stats || stats, AGX_ERR_ARG, "agx_edge_attrs_apply: this normalisation needs the global statistics");
+    AGX_REQUIRE(!need_stats || (stats && n_stat_sets >= 1), AGX_ERR_ARG,
+                "agx_edge_attrs_apply: this normalisation needs the statistics of every shard");
     AGX_REQUIRE(n_edges_global >= n_edges, AGX_ERR_ARG, "agx_edge_attrs_apply: n_edges_global < n_edges");
     if (!raw_present) {
         rc = attrs_raw(edge_src, edge_dst, n_edges, src_rec, dst_rec, want_len, 0, out_len, want_dir, dir_rotated, out_dir,
                        true, nullptr, workspace, stream);
         if (rc) return rc;
     }
-    return attrs_scale(n_edges, len_norm, len_invert, out_len, dir_norm, dir_rotated, out_dir, stats, n_edges_global,
-                       workspace, stream);
+    return attrs_scale(n_edges, len_norm, len_invert, out_len, dir_norm, dir_rotated, out_dir, stats, n_stat_sets,
+                       n_edges_global, workspace, stream);
 }
 
 extern "C" int agx_edge_attrs(const int32_t* edge_src, const int32_t* edge_dst, int64_t n_edges, const float* src_rec,
@@ -569,6 +582,6 @@ extern "C" int agx_edge_attrs(const int32_t* edge_src, const int32_t* edge_dst, 
     rc = attrs_raw(edge_src, edge_dst, n_edges, src_rec, dst_rec, want_len, need_stats ? 0 : len_invert, out_len, want_dir,
                    dir_rotated, out_dir, true, stats, workspace, stream);
     if (rc || !need_stats) return rc;
-    return attrs_scale(n_edges, len_norm, len_invert, out_len, dir_norm, dir_rotated, out_dir, stats, n_edges, workspace,
+    return attrs_scale(n_edges, len_norm, len_invert, out_len, dir_norm, dir_rotated, out_dir, stats, 1, n_edges, workspace,
                        stream);
 }

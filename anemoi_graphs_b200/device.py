@@ -33,6 +33,7 @@ from . import _cabi
 
 _defer_depth = 0
 _pending: list[torch.cuda.Event] = []
+_works: dict[int, list] = {}  # storage pointer -> outstanding asynchronous collectives writing into that storage
 _resident = False
 
 
@@ -79,9 +80,25 @@ def deferred():
 
 
 def flush() -> None:
-    """Wait for every outstanding device->host copy issued by ``to_host``."""
+    """Wait for every outstanding collective (``all_gather_v(async_op=True)``) and device->host copy
+    (``to_host``)."""
+    for key in list(_works):
+        for work in _works.pop(key):
+            work.wait()  # NCCL: orders the current stream behind the collective; gloo: blocks the host
     while _pending:
         _pending.pop().synchronize()
+
+
+def _storage_key(t: torch.Tensor) -> int:
+    return t.untyped_storage().data_ptr()
+
+
+def wait_for(t: torch.Tensor | None) -> None:
+    """Order the current stream behind the asynchronous collectives still filling ``t``'s storage."""
+    if t is None or not _works:
+        return
+    for work in _works.pop(_storage_key(t), []):
+        work.wait()
 
 
 def maybe_flush() -> None:
@@ -106,6 +123,7 @@ def to_host(t: torch.Tensor) -> torch.Tensor:
     of one edge set overlaps the kernels of the next."""
     if not t.is_cuda:
         return t
+    wait_for(t)
     out = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
     if t.numel() == 0:
         return out
@@ -165,7 +183,7 @@ def seed_node_state(nodes, x_dev: torch.Tensor) -> NodeState:
     return st
 
 
-def node_tables(nodes, with_rotation: bool):
+def node_tables(nodes, with_rotation: bool = True):
     from . import ops
 
     st = node_state(nodes)
@@ -221,12 +239,15 @@ def all_gather_counts(count: int, device: torch.device) -> list[int]:
     return [int(v) for v in out.tolist()]
 
 
-def all_gather_v(full: torch.Tensor, counts: list[int], dim: int) -> torch.Tensor:
+def all_gather_v(full: torch.Tensor, counts: list[int], dim: int, async_op: bool = False) -> torch.Tensor:
     """In-place variable-length all-gather along ``dim``.
 
     ``full`` is the complete output buffer; this rank has already written its own block (the slice at
     offset ``sum(counts[:rank])`` of length ``counts[rank]``) - the kernels write straight into it, so
     there is no staging copy.  NCCL moves every rank's block into every other rank's buffer.
+
+    ``async_op=True`` only enqueues the transfers: the other ranks' blocks are complete after ``wait_for(full)``
+    (issued automatically by ``to_host`` and ``flush``), so the exchange overlaps the kernels of the next edge set.
     """
     import torch.distributed as dist
 
@@ -243,19 +264,35 @@ def all_gather_v(full: torch.Tensor, counts: list[int], dim: int) -> torch.Tenso
         dim = 0
     backend = dist.get_backend()
     equal = len(set(counts)) == 1 and counts[0] > 0
+    works = []
     for row in rows:
         views = [row.narrow(dim, offs[r], counts[r]) for r in range(w)]
         if equal and row.is_contiguous():
             # equal blocks: NCCL's in-place all-gather (send buffer = this rank's slot of the receive buffer)
-            dist.all_gather_into_tensor(row, views[rank])
+            works.append(dist.all_gather_into_tensor(row, views[rank], async_op=async_op))
         elif backend == "nccl":
             # unequal sizes: ProcessGroupNCCL falls back to one grouped ncclBroadcast per rank, still in place
-            dist.all_gather(views, views[rank])
+            works.append(dist.all_gather(views, views[rank], async_op=async_op))
         else:  # gloo (CPU tests): broadcasts
             for r in range(w):
                 if counts[r]:
-                    dist.broadcast(views[r], src=r)
+                    works.append(dist.broadcast(views[r], src=r, async_op=async_op))
+    if async_op:
+        _works.setdefault(_storage_key(full), []).extend(wk for wk in works if wk is not None)
     return full
+
+
+def all_gather_stats_raw(stats: torch.Tensor) -> torch.Tensor:
+    """Per-rank attribute statistics stacked in rank order: (W, 8) float64.  The attribute kernel folds them in
+    that order (``agx_edge_attrs_apply(n_stat_sets=W)``), so every rank applies bit-identical constants."""
+    import torch.distributed as dist
+
+    _, w = world()
+    if w == 1:
+        return stats.reshape(1, 8)
+    allst = torch.empty((w, 8), dtype=stats.dtype, device=stats.device)
+    dist.all_gather_into_tensor(allst, stats.reshape(1, 8))
+    return allst
 
 
 def all_gather_stats(stats: torch.Tensor) -> torch.Tensor:

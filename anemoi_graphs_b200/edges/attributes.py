@@ -122,16 +122,16 @@ def compute_attributes(graph, edges_name: tuple[str, str, str], attrs: dict) -> 
     store = graph[tuple(edges_name)]
     edge_index = _device.device_edge_index(store)
     host_side = not store["edge_index"].is_cuda
-    want_rot = any(isinstance(a, EdgeDirection) and a.luse_rotated_features for a in ours.values())
-    src = _device.node_tables(graph[source_name], with_rotation=False)
-    dst = _device.node_tables(graph[target_name], with_rotation=want_rot)
+    src = _device.node_tables(graph[source_name])
+    dst = _device.node_tables(graph[target_name])
     lengths = [(k, a) for k, a in ours.items() if isinstance(a, EdgeLength)]
     dirs = [(k, a) for k, a in ours.items() if isinstance(a, EdgeDirection)]
     _, w = _device.world()
+    local = getattr(edge_index, "_agx_local", None)  # set by a sharded builder: this rank's own columns
     while lengths or dirs:
         kl = lengths.pop(0) if lengths else None
         kd = dirs.pop(0) if dirs else None
-        args = dict(length=False, direction=False, sharded=w > 1)
+        args = dict(length=False, direction=False, sharded=w > 1, local=local)
         if kl:
             args.update(kl[1]._kernel_args())
         if kd:

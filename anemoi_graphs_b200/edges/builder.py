@@ -165,8 +165,16 @@ class NodeMaskingMixin:
         return torch.stack([src, dst])
 
 
-def _gather_blocks(full: torch.Tensor, counts: list[int]) -> torch.Tensor:
-    return _device.all_gather_v(full, counts, dim=1)
+def _gather_blocks(full: torch.Tensor, counts: list[int], rank: int, masked: bool) -> torch.Tensor:
+    """All-gather the per-rank column blocks of ``full`` (2, E).  Without node masks the exchange is asynchronous
+    and ``full`` remembers which columns this rank produced itself (``_agx_local``), so the attribute kernel can
+    start on them while the other ranks' blocks are still in flight."""
+    if masked:
+        return _device.all_gather_v(full, counts, dim=1)  # undo_masking reads every column next
+    _device.all_gather_v(full, counts, dim=1, async_op=True)
+    lo = sum(counts[:rank])
+    full._agx_local = (lo, lo + counts[rank], list(counts))
+    return full
 
 
 class KNNEdges(BaseEdgeBuilder, NodeMaskingMixin):
@@ -218,7 +226,7 @@ class KNNEdges(BaseEdgeBuilder, NodeMaskingMixin):
             index.knn(dst[lo:hi], k, dst_base=lo, stats=self.stats, out=out, out_offset=lo * k)
         if w > 1:
             counts = [(b - a) * k for a, b in (_device.shard_range(nq, r, w) for r in range(w))]
-            out = _gather_blocks(out, counts)
+            out = _gather_blocks(out, counts, rank, src_sel is not None or dst_sel is not None)
         return self.undo_masking(out, src_sel, dst_sel)
 
 
@@ -284,7 +292,7 @@ class CutOffEdges(BaseEdgeBuilder, NodeMaskingMixin):
             out = torch.empty((2, sum(counts)), dtype=torch.int32, device=dst.device)
             index.radius_fill(q, self.radius, offsets, total, out, sum(counts[:rank]), dst_base=lo, stats=self.stats)
         if w > 1:
-            out = _gather_blocks(out, counts)
+            out = _gather_blocks(out, counts, rank, src_sel is not None or dst_sel is not None)
         return self.undo_masking(out, src_sel, dst_sel)
 
 

@@ -290,6 +290,11 @@ def _attr_workspace(device) -> torch.Tensor:
     return _workspace[key]
 
 
+# below this many edges a multi-GPU build evaluates the attributes on every rank instead of sharding them: the
+# statistics exchange and the two gathers cost more than the kernel (1.3 M multi-scale edges: 0.13 ms replicated)
+ATTR_SHARD_MIN_EDGES = 4_000_000
+
+
 def edge_attributes(
     edge_index: torch.Tensor,
     src: NodeTables,
@@ -301,12 +306,16 @@ def edge_attributes(
     direction_norm: str | None = None,
     direction_rotated: bool = True,
     sharded: bool = False,
+    local: tuple[int, int, list[int]] | None = None,
 ):
     """Fused EdgeLength / EdgeDirection: returns ``(len (E, 1) float32 | None, dir (E, 2) float32 | None)``.
 
-    ``sharded=True`` (multi-GPU): this rank evaluates only its contiguous range of the edges, the
-    normalisation statistics are combined across ranks and the attribute blocks all-gathered, so every
-    rank returns the complete arrays."""
+    ``sharded=True`` (multi-GPU): this rank evaluates only a contiguous range of the edges, the per-rank
+    normalisation statistics are exchanged (and folded in rank order inside the kernel) and the attribute blocks
+    all-gathered asynchronously, so every rank ends with the complete arrays (complete once ``device.wait_for`` /
+    ``device.flush`` has run).  ``local = (lo, hi, counts)`` names the range this rank's own builder produced
+    (its columns of ``edge_index`` are valid before the edge all-gather has finished) and every rank's block
+    size; without it the edges are split evenly."""
     from . import device as _device
 
     for norm in (length_norm, direction_norm):
@@ -315,7 +324,7 @@ def edge_attributes(
                 f"Attribute normalisation \"{norm}\" is not valid. Options are: 'l1', 'l2', 'unit-max' or 'unit-std'."
             )
     assert edge_index.is_cuda and edge_index.dtype == torch.int32 and edge_index.dim() == 2 and edge_index.shape[0] == 2
-    edge_index = edge_index.contiguous()
+    assert edge_index.is_contiguous(), "edge_index must be a contiguous (2, E) int32 tensor"
     n_edges = int(edge_index.shape[1])
     dev = edge_index.device
     out_len = torch.empty((n_edges, 1), dtype=torch.float32, device=dev) if length else None
@@ -327,9 +336,12 @@ def edge_attributes(
     len_code = NORM_CODES[length_norm] if length else -1
     dir_code = NORM_CODES[direction_norm] if direction else -1
     rank, w = _device.world() if sharded else (0, 1)
+    if w > 1 and local is None and n_edges < ATTR_SHARD_MIN_EDGES:
+        w = 1  # small edge set: every rank evaluates all of it (identical results, no exchange)
     ws = _attr_workspace(dev)
     stream = current_stream()
     if w == 1:
+        _device.wait_for(edge_index)
         with _span("edge_attrs", n_edges):
             check(
                 lib.agx_edge_attrs(
@@ -339,7 +351,13 @@ def edge_attributes(
                 )
             )  # fmt: skip
         return out_len, out_dir
-    lo, hi = _device.shard_range(n_edges, rank, w)
+    if local is not None:
+        lo, hi, counts = local
+        assert sum(counts) == n_edges and hi - lo == counts[rank]
+    else:
+        _device.wait_for(edge_index)
+        lo, hi = _device.shard_range(n_edges, rank, w)
+        counts = [b - a for a, b in (_device.shard_range(n_edges, r, w) for r in range(w))]
     m = hi - lo
     e_src, e_dst = edge_index[0].data_ptr() + 4 * lo, edge_index[1].data_ptr() + 4 * lo
     o_len = out_len.data_ptr() + 4 * lo if length else None
@@ -356,21 +374,20 @@ def edge_attributes(
                     int(bool(direction_rotated)), o_len, o_dir, ptr(stats), ptr(ws), stream,
                 )
             )  # fmt: skip
-        stats = _device.all_gather_stats(stats)
+        stats = _device.all_gather_stats_raw(stats)
         raw_present = 1
     with _span("edge_attrs_apply", m):
         check(
             lib.agx_edge_attrs_apply(
                 e_src, e_dst, m, ptr(src_rec), ptr(dst_rec), len_code, int(bool(length_invert)), o_len, dir_code,
-                int(bool(direction_rotated)), o_dir, ptr(stats), n_edges, raw_present, ptr(ws), stream,
+                int(bool(direction_rotated)), o_dir, ptr(stats), w if stats is not None else 0, n_edges, raw_present,
+                ptr(ws), stream,
             )
         )  # fmt: skip
-    counts = [_device.shard_range(n_edges, r, w) for r in range(w)]
-    counts = [b - a for a, b in counts]
     if length:
-        _device.all_gather_v(out_len, counts, 0)
+        _device.all_gather_v(out_len, counts, 0, async_op=True)
     if direction:
-        _device.all_gather_v(out_dir, counts, 0)
+        _device.all_gather_v(out_dir, counts, 0, async_op=True)
     return out_len, out_dir
 
 

@@ -24,6 +24,8 @@ def concat_edges_device(e1: torch.Tensor, e2: torch.Tensor) -> torch.Tensor:
 
     Column-wise unique of a 2-row int32 array is a sort-unique of the packed 64-bit key ``src << 32 | dst``
     (indices are non-negative), done with the device sort (plumbing)."""
+    _device.wait_for(e1)  # a sharded builder's all-gather may still be filling its result
+    _device.wait_for(e2)
     cat = torch.cat([e1, e2], dim=1).to(torch.int64)
     key = torch.unique((cat[0] << 32) | cat[1], sorted=True)
     return torch.stack([key >> 32, key & 0xFFFFFFFF]).to(torch.int32)

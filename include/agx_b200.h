@@ -121,17 +121,18 @@ int64_t agx_edge_attrs_workspace(void);
  * multi-GPU build).  _stats evaluates the raw values of the local edges ONCE: it writes them (float32, not yet
  * normalised) to out_len / out_dir when those are given, and reduces them to
  * stats[8] = {len sum, sum of squares, min, max, dir sum, sum of squares, min, max} (float64; an empty shard
- * gives {0, 0, +1e300, -1e300}).  The caller combines the shards' statistics (sum / min / max) and passes the
- * global ones, with the global edge count, to _apply, which normalises the local block in place
- * (raw_present = 1) or evaluates the raw values first (raw_present = 0).  normalise.py:20-55.              */
+ * gives {0, 0, +1e300, -1e300}).  The caller gathers the shards' statistics and passes all n_stat_sets of them
+ * (8 doubles each, in rank order; they are folded in that order, so every rank derives bit-identical constants),
+ * with the global edge count, to _apply, which normalises the local block in place (raw_present = 1) or
+ * evaluates the raw values first (raw_present = 0).  normalise.py:20-55.                                  */
 int agx_edge_attrs_stats(const int32_t* edge_src, const int32_t* edge_dst, int64_t n_edges, const float* src_rec,
                          const double* dst_rec, int want_len, int want_dir, int dir_rotated,
                          float* out_len /*DEV E or NULL*/, float* out_dir /*DEV E*2 or NULL*/,
                          double* stats /*DEV 8*/, double* workspace, void* stream);
 int agx_edge_attrs_apply(const int32_t* edge_src, const int32_t* edge_dst, int64_t n_edges, const float* src_rec,
                          const double* dst_rec, int len_norm, int len_invert, float* out_len, int dir_norm,
-                         int dir_rotated, float* out_dir, const double* stats /*DEV 8 or NULL if no norm*/,
-                         int64_t n_edges_global, int raw_present, double* workspace, void* stream);
+                         int dir_rotated, float* out_dir, const double* stats /*DEV n_stat_sets*8 or NULL if no norm*/,
+                         int n_stat_sets, int64_t n_edges_global, int raw_present, double* workspace, void* stream);
 
 /* ---- icosphere + multi-scale edges -------------------------------------------------------------------
  * agx_icosphere: replaces trimesh.creation.icosphere (generate/tri_icosahedron.py:121,173):

@@ -50,6 +50,17 @@ def _worker(rank: int, world: int, port: int, out_dir: str) -> None:
         full[:, off : off + mine] = rank + 1
         agx_device.all_gather_v(full, counts, dim=1)
         assert full[0].tolist() == [1] * 5 + [2] * 2 and full[1].tolist() == [1] * 5 + [2] * 2
+        # --- asynchronous exchange: the other rank's block is complete after wait_for / flush -----------
+        full = torch.zeros((2, sum(counts)), dtype=torch.int32)
+        full[:, off : off + mine] = rank + 1
+        agx_device.all_gather_v(full, counts, dim=1, async_op=True)
+        side = torch.zeros((sum(counts), 1), dtype=torch.float32)
+        side[off : off + mine] = float(rank + 1)
+        agx_device.all_gather_v(side, counts, dim=0, async_op=True)
+        agx_device.wait_for(full)
+        assert full[0].tolist() == [1] * 5 + [2] * 2 and full[1].tolist() == [1] * 5 + [2] * 2
+        agx_device.flush()  # waits for `side`
+        assert side[:, 0].tolist() == [1.0] * 5 + [2.0] * 2
         # --- an empty rank block --------------------------------------------------------------------
         counts = agx_device.all_gather_counts(0 if rank == 1 else 4, torch.device("cpu"))
         full = torch.zeros((sum(counts), 2), dtype=torch.float32)
@@ -67,6 +78,9 @@ def _worker(rank: int, world: int, port: int, out_dir: str) -> None:
         np.testing.assert_allclose(tot[0].item(), v.sum(), rtol=1e-14)
         np.testing.assert_allclose(tot[5].item(), (v**2).sum(), rtol=1e-14)
         assert tot[2].item() == v.min() and tot[7].item() == v.max()
+        raw = agx_device.all_gather_stats_raw(st)  # what the kernel folds, in rank order
+        assert raw.shape == (world, 8) and torch.equal(raw[rank], st)
+        np.testing.assert_allclose(raw[:, 0].sum().item(), v.sum(), rtol=1e-14)
         torch.save(tot, os.path.join(out_dir, f"stats{rank}.pt"))
         dist.barrier()
     finally:

@@ -7,6 +7,13 @@ from anemoi_graphs_b200 import device as agx_device
 from anemoi_graphs_b200.config import DotDict, instantiate
 from anemoi_graphs_b200.graph import HeteroData
 
+import os
+if int(os.environ.get("WORLD_SIZE", "1")) > 1:  # under torchrun: sharded build, rank 0 reports
+    import torch.distributed as dist
+    torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+    dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["LOCAL_RANK"])))
+    if int(os.environ["RANK"]) != 0:
+        sys.stdout = open(os.devnull, "w")
 workload = sys.argv[1] if len(sys.argv) > 1 else "o1280_res7"
 grid, res = bench.WORKLOADS[workload]
 x_host = bench.data_coordinates(grid).pin_memory()
