@@ -304,7 +304,33 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn(KnnArgs a) {
         int n_rows = 0;      // rows of the union window over all faces (uniform across the warp)
         int my_row = -1, my_j0 = 0, my_j1 = 0;
         bool fits = !cap.everything;
+        // fast path: the whole tile lives on ONE cube face and every lane's cap ends at least a cell inside it
+        bool fast = false;
         if (fits) {
+            const int face = agx_major_face(qv.x, qv.y, qv.z);
+            if (__all_sync(0xffffffffu, face == __shfl_sync(0xffffffffu, face, 0))) {
+                float fa, fb, fc;
+                agx_face_frame(face, qv.x, qv.y, qv.z, fa, fb, fc);
+                int i0, i1, j0, j1;
+                bool ok = agx_axis_window_major(fa, fc, cap, a.cells, i0, i1);
+                ok = agx_axis_window_major(fb, fc, cap, a.cells, j0, j1) && ok;
+                if (__all_sync(0xffffffffu, ok)) {
+                    fast = true;
+                    i0 = __reduce_min_sync(0xffffffffu, i0);
+                    j0 = __reduce_min_sync(0xffffffffu, j0);
+                    i1 = __reduce_max_sync(0xffffffffu, i1);
+                    j1 = __reduce_max_sync(0xffffffffu, j1);
+                    n_rows = i1 - i0 + 1;
+                    if (lane < n_rows) {
+                        my_row = (face * a.cells + i0 + lane) * a.cells;
+                        my_j0 = j0;
+                        my_j1 = j1;
+                    }
+                    fits = n_rows <= KNN_MAX_ROWS;
+                }
+            }
+        }
+        if (fits && !fast) {
             for (int face = 0; face < 6; ++face) {
                 int i0, i1, j0, j1;
                 bool ok = agx_face_window(face, qv, cap, a.cells, i0, i1, j0, j1);

@@ -29,9 +29,20 @@ __global__ void __launch_bounds__(256) k_radius(const float4* __restrict__ pts, 
         int64_t out_pos = FILL ? offsets[q] : 0;
         const int32_t dst = (int32_t)(dst_base + q);
         int found = 0;
-        for (int face = 0; face < 6; ++face) {
-            int i0, i1, j0, j1;
-            if (!agx_face_window(face, qv, cap, cells, i0, i1, j0, j1)) continue;
+        // single-face fast path (the cap ends at least a cell inside the query's major face), else all six faces
+        const int mface = agx_major_face(qv.x, qv.y, qv.z);
+        int fi0, fi1, fj0, fj1;
+        bool fast;
+        {
+            float fa, fb, fc;
+            agx_face_frame(mface, qv.x, qv.y, qv.z, fa, fb, fc);
+            fast = !cap.everything && agx_axis_window_major(fa, fc, cap, cells, fi0, fi1);
+            fast = fast && agx_axis_window_major(fb, fc, cap, cells, fj0, fj1);
+        }
+        const int face_end = fast ? mface + 1 : 6;
+        for (int face = fast ? mface : 0; face < face_end; ++face) {
+            int i0 = fi0, i1 = fi1, j0 = fj0, j1 = fj1;
+            if (!fast && !agx_face_window(face, qv, cap, cells, i0, i1, j0, j1)) continue;
             for (int i = i0; i <= i1; ++i) {
                 int row = (face * cells + i) * cells;
                 int s = __ldg(cell_start + row + j0), e = __ldg(cell_start + row + j1 + 1);
