@@ -120,6 +120,35 @@ def test_knn_random_sphere_all_k(ops, k):
     np.testing.assert_allclose(rd.cpu().numpy().reshape(-1), rd_want, rtol=1e-13, atol=0)
 
 
+@pytest.mark.parametrize("k", [3, 16])
+def test_knn_incoherent_query_order_is_binned(ops, k, monkeypatch):
+    """A shuffled point cloud: large inputs are sampled, found incoherent and searched in spatially binned order.
+    The result must not depend on the processing order (forced on / off) and must match the oracle on a subsample."""
+    lat, lon = grids.uniform_sphere(40000, seed=11)
+    ref = grids.latlon_deg_to_x(lat, lon).numpy()
+    lat, lon = grids.uniform_sphere(300000, seed=12)
+    q = grids.latlon_deg_to_x(lat, lon).numpy()
+    outs = {}
+    for mode in ("auto", "0", "1"):
+        if mode == "auto":
+            monkeypatch.delenv("AGX_KNN_BIN", raising=False)
+        else:
+            monkeypatch.setenv("AGX_KNN_BIN", mode)
+        st = ops.new_stats("cuda")
+        with ops.NeighbourIndex(dev(ref), hint_k=k) as ix:
+            outs[mode] = (ix.knn(dev(q), k, stats=st).cpu().numpy(), st.cpu().tolist())
+    # the same edge SET whatever the processing order (within a query, sources closer than 2^-14 relative may swap:
+    # the staged scan orders them by truncated FP32 chord, the per-thread search by exact FP32 chord)
+    np.testing.assert_array_equal(canon(outs["0"][0]), canon(outs["1"][0]))
+    np.testing.assert_array_equal(outs["auto"][0], outs["1"][0])  # auto = binned here, bit for bit reproducible
+    assert outs["0"][1][3] == 0 and outs["auto"][1][3] > 0  # unbinned: no tile could be staged; auto: staged
+    sub = np.arange(0, q.shape[0], 37)
+    want, info = R.knn_edges_canonical(ref, q[sub], k)
+    got = outs["auto"][0].reshape(2, -1, k)[:, sub, :]
+    got[1] = np.arange(sub.size)[:, None]
+    np.testing.assert_array_equal(canon(got.reshape(2, -1)), want)
+
+
 def test_knn_sparse_clustered_and_polar(ops):
     """Queries far from every reference point (cap growth), references clustered in one cell, both poles."""
     rng = np.random.default_rng(3)
