@@ -75,6 +75,10 @@ struct agx_index {
     float4* pts;          // (n) cell-sorted (x, y, z, __int_as_float(original index)); in-cell order = index
     int* cell_start;      // (6*C*C + 1) offsets into pts
     float chord2_typ;     // typical squared chord between neighbouring points (4*pi/n), for initial radii
+    // processing order chosen by agx_radius_count for a query set, kept for the agx_radius_fill that follows
+    const void* order_q;  // the query array it belongs to (NULL: none cached)
+    int64_t order_nq;
+    int32_t* order_perm;  // NULL: as given
 };
 
 #define AGX_PI_F 3.14159265358979323846f

@@ -122,6 +122,9 @@ extern "C" int agx_index_build(const float* latlon, int64_t n, int cells_per_fac
     ix->pts = nullptr;
     ix->cell_start = nullptr;
     ix->chord2_typ = (float)(12.566370614359172 / (double)n);
+    ix->order_q = nullptr;
+    ix->order_nq = 0;
+    ix->order_perm = nullptr;
 
     float4 *rec = nullptr, *scat = nullptr;
     int *cell_of = nullptr, *hist = nullptr;
@@ -173,6 +176,7 @@ extern "C" int agx_index_free(agx_index_t* ix, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     cudaFreeAsync(ix->pts, stream);
     cudaFreeAsync(ix->cell_start, stream);
+    if (ix->order_perm) cudaFreeAsync(ix->order_perm, stream);
     delete ix;
     return AGX_OK;
 }

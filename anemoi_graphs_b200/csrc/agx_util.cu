@@ -220,3 +220,55 @@ extern "C" int agx_max_positive(const double* values, int64_t n, double* out_val
     *out_index = host.i;
     return AGX_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// node pruning (RemoveUnconnectedNodes, /root/reference/src/anemoi/graphs/processors/post_process.py:45-60,
+// 133-149): mark the endpoints that occur in an edge row; relabel a row through new_index = exclusive scan of
+// the keep flags.  Replaces a python dict + Tensor.apply_ over every edge.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_mark_nodes(const int32_t* __restrict__ row, int64_t n, int64_t n_nodes,
+                                                     int32_t* __restrict__ flags, int* __restrict__ bad) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        int v = row[i];
+        if (v < 0 || v >= n_nodes)
+            *bad = 1;
+        else
+            flags[v] = 1;  // benign race: every writer stores the same value
+    }
+}
+
+__global__ void __launch_bounds__(256) k_relabel_nodes(int32_t* __restrict__ row, int64_t n, const int64_t* __restrict__ new_index) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        row[i] = (int32_t)new_index[row[i]];
+}
+
+extern "C" int agx_mark_nodes(const int32_t* row, int64_t n, int64_t n_nodes, int32_t* flags, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    AGX_REQUIRE(n >= 0 && n_nodes >= 0, AGX_ERR_ARG, "agx_mark_nodes: negative size");
+    if (n == 0) return AGX_OK;
+    AGX_REQUIRE(row && flags, AGX_ERR_ARG, "agx_mark_nodes: NULL buffer");
+    int* bad = nullptr;
+    agx_pool_keep_warm();
+    AGX_CUDA_OK(cudaMallocAsync(&bad, sizeof(int), stream));
+    AGX_CUDA_OK(cudaMemsetAsync(bad, 0, sizeof(int), stream));
+    k_mark_nodes<<<agx_grid(n, 256, 8), 256, 0, stream>>>(row, n, n_nodes, flags, bad);
+    AGX_LAUNCH_OK();
+    agx_note_launch(1);
+    int host = 0;
+    AGX_CUDA_OK(cudaMemcpyAsync(&host, bad, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    AGX_CUDA_OK(cudaFreeAsync(bad, stream));
+    AGX_CUDA_OK(cudaStreamSynchronize(stream));
+    AGX_REQUIRE(host == 0, AGX_ERR_ARG, "agx_mark_nodes: an edge endpoint is outside [0, %lld)", (long long)n_nodes);
+    return AGX_OK;
+}
+
+extern "C" int agx_relabel_nodes(int32_t* row, int64_t n, const int64_t* new_index, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    AGX_REQUIRE(n >= 0, AGX_ERR_ARG, "agx_relabel_nodes: n < 0");
+    if (n == 0) return AGX_OK;
+    AGX_REQUIRE(row && new_index, AGX_ERR_ARG, "agx_relabel_nodes: NULL buffer");
+    k_relabel_nodes<<<agx_grid(n, 256, 8), 256, 0, stream>>>(row, n, new_index);
+    AGX_LAUNCH_OK();
+    agx_note_launch(1);
+    return AGX_OK;
+}

@@ -109,7 +109,7 @@ class ClockSampler:
     def start(self) -> None:
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "20",
                  "-i", str(self.gpu_index)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
             )  # fmt: skip

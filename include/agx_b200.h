@@ -97,6 +97,14 @@ int agx_radius_fill(const agx_index_t* index, const float* q_latlon /*DEV*/, int
 int agx_max_positive(const double* values /*DEV n*/, int64_t n, double* out_value /*HOST*/,
                      int64_t* out_index /*HOST*/, void* stream);
 
+/* ---- node pruning -------------------------------------------------------------------------------------
+ * RemoveUnconnectedNodes (processors/post_process.py:45-60 update_edge_indices, :133-149 compute_mask):
+ * agx_mark_nodes sets flags[v] = 1 for every endpoint v in an edge row (flags pre-zeroed / pre-seeded by the caller,
+ * AGX_ERR_ARG if an endpoint is outside [0, n_nodes)); after agx_exclusive_scan(flags) -> new_index,
+ * agx_relabel_nodes rewrites a row in place as new_index[v] - the reference's python dict + Tensor.apply_.       */
+int agx_mark_nodes(const int32_t* row /*DEV n*/, int64_t n, int64_t n_nodes, int32_t* flags /*DEV n_nodes*/, void* stream);
+int agx_relabel_nodes(int32_t* row /*DEV n, in place*/, int64_t n, const int64_t* new_index /*DEV n_nodes+1*/, void* stream);
+
 /* ---- edge attributes ------------------------------------------------------------------------------
  * agx_node_tables: everything the attribute kernel needs from ONE node, as one 32-byte record per role:
  *   src_rec  float[8]  = (x, y, z, cos lat, lat, lon, 0, 0) - float32 unit vector and cos(lat) with numpy's

@@ -294,3 +294,83 @@ def test_stretched_tri_nodes_and_edges(golden, hops):
     CutOffEdges("data", "str", 0.6).update_graph(graph)
     np.testing.assert_array_equal(canon(graph[("str", "to", "data")].edge_index), canon(g["str_knn4_edge_index"]))
     np.testing.assert_array_equal(canon(graph[("data", "to", "str")].edge_index), canon(g["str_cutoff_edge_index"]))
+
+
+# ------------------------------------------------------------------------------------------------
+# post-processor: RemoveUnconnectedNodes (reference tests/processors/test_post_process.py + a randomised check
+# against the reference's own dict-based algorithm)
+# ------------------------------------------------------------------------------------------------
+def _graph_with_isolated_nodes():
+    from anemoi_graphs_b200.graph import HeteroData
+
+    graph = HeteroData()
+    graph["test_nodes"].x = torch.tensor([[1], [2], [3], [4], [5], [6]])
+    graph["test_nodes"]["mask_attr"] = torch.tensor([[1], [1], [1], [0], [0], [0]], dtype=torch.bool)
+    graph["test_nodes", "to", "test_nodes"].edge_index = torch.tensor([[2, 3, 4], [1, 2, 3]])
+    return graph
+
+
+def test_remove_unconnected_nodes_reference_cases():
+    from anemoi_graphs_b200.processors import RemoveUnconnectedNodes
+
+    graph = RemoveUnconnectedNodes(nodes_name="test_nodes", ignore=None, save_mask_indices_to_attr=None).update_graph(
+        _graph_with_isolated_nodes()
+    )
+    assert graph["test_nodes"].num_nodes == 4
+    assert torch.equal(graph["test_nodes"].x, torch.tensor([[2], [3], [4], [5]]))
+    assert "original_indices" not in graph["test_nodes"]
+
+    graph = RemoveUnconnectedNodes(
+        nodes_name="test_nodes", ignore=None, save_mask_indices_to_attr="original_indices"
+    ).update_graph(_graph_with_isolated_nodes())
+    assert graph["test_nodes"].num_nodes == 4
+    assert torch.equal(graph["test_nodes", "to", "test_nodes"].edge_index, torch.tensor([[1, 2, 3], [0, 1, 2]]))
+    assert torch.equal(graph["test_nodes"].original_indices, torch.tensor([[1], [2], [3], [4]]))
+
+    graph = RemoveUnconnectedNodes(nodes_name="test_nodes", ignore="mask_attr", save_mask_indices_to_attr=None).update_graph(
+        _graph_with_isolated_nodes()
+    )
+    assert graph["test_nodes"].num_nodes == 5
+    assert torch.equal(graph["test_nodes"].x, torch.tensor([[1], [2], [3], [4], [5]]))
+    assert torch.equal(graph["test_nodes", "to", "test_nodes"].edge_index, torch.tensor([[2, 3, 4], [1, 2, 3]]))
+
+
+@pytest.mark.parametrize("resident", [False, True])
+def test_remove_unconnected_nodes_random_graph_matches_reference_algorithm(resident):
+    from anemoi_graphs_b200.graph import HeteroData
+    from anemoi_graphs_b200.processors import RemoveUnconnectedNodes
+
+    rng = np.random.default_rng(7)
+    n_a, n_b = 5000, 300
+    used = rng.choice(n_a, size=1800, replace=False)
+    e_ab = np.stack([rng.choice(used, size=20000), rng.integers(0, n_b, size=20000)]).astype(np.int32)
+    e_ba = np.stack([rng.integers(0, n_b, size=9000), rng.choice(used[:900], size=9000)]).astype(np.int32)
+    e_aa = np.stack([rng.choice(used, size=4000), rng.choice(used, size=4000)]).astype(np.int32)
+    keep_anyway = np.zeros((n_a, 1), dtype=bool)
+    keep_anyway[rng.choice(n_a, size=50, replace=False)] = True
+    where = (lambda t: t.cuda()) if resident else (lambda t: t)
+    graph = HeteroData()
+    graph["a"].x = where(torch.from_numpy(rng.random((n_a, 2)).astype(np.float32)))
+    graph["a"]["w"] = where(torch.arange(n_a, dtype=torch.float32).reshape(-1, 1))
+    graph["a"]["keep"] = where(torch.from_numpy(keep_anyway))
+    graph["b"].x = where(torch.from_numpy(rng.random((n_b, 2)).astype(np.float32)))
+    for key, e in ((("a", "to", "b"), e_ab), (("b", "to", "a"), e_ba), (("a", "to", "a"), e_aa)):
+        graph[key].edge_index = where(torch.from_numpy(e.copy()))
+    # the reference's algorithm (post_process.py:45-60,133-149), restated with numpy
+    mask = keep_anyway[:, 0].copy()
+    mask[e_ab[0]] = True
+    mask[e_ba[1]] = True
+    mask[e_aa[0]] = True
+    mask[e_aa[1]] = True
+    mapping = dict(zip(np.where(mask)[0].tolist(), range(int(mask.sum()))))
+    remap = np.vectorize(mapping.get)
+    graph = RemoveUnconnectedNodes("a", save_mask_indices_to_attr="orig", ignore="keep").update_graph(graph)
+    assert graph["a"].num_nodes == int(mask.sum())
+    assert graph["a"].x.is_cuda == resident and graph["a", "to", "b"].edge_index.is_cuda == resident
+    np.testing.assert_array_equal(graph["a"]["w"].cpu().numpy()[:, 0], np.where(mask)[0].astype(np.float32))
+    np.testing.assert_array_equal(graph["a"]["orig"].cpu().numpy()[:, 0], np.where(mask)[0])
+    np.testing.assert_array_equal(graph["a", "to", "b"].edge_index.cpu().numpy(), np.stack([remap(e_ab[0]), e_ab[1]]))
+    np.testing.assert_array_equal(graph["b", "to", "a"].edge_index.cpu().numpy(), np.stack([e_ba[0], remap(e_ba[1])]))
+    np.testing.assert_array_equal(graph["a", "to", "a"].edge_index.cpu().numpy(), np.stack([remap(e_aa[0]), remap(e_aa[1])]))
+    assert graph["a", "to", "b"].edge_index.dtype == torch.int32
+    assert graph["b"].num_nodes == n_b

@@ -220,6 +220,34 @@ def test_cutoff_random_radii(ops, radius):
     np.testing.assert_array_equal(canon(ei), canon(want))
 
 
+@pytest.mark.parametrize("degree", [6, 40])
+def test_cutoff_tile_and_warp_forms_agree_bit_for_bit(ops, degree, monkeypatch):
+    """The low-degree tile kernel and the warp-per-query kernel emit the same pairs in the same order, for coherent
+    and for shuffled (binned) query orders; checked against the oracle on a subsample."""
+    n_ref = 200000
+    ref = grids.latlon_deg_to_x(*grids.uniform_sphere(n_ref, seed=21)).numpy()
+    q = grids.latlon_deg_to_x(*grids.uniform_sphere(300000, seed=22)).numpy()
+    radius = float(np.arccos(1.0 - 2.0 * degree / n_ref))
+    outs = {}
+    for tile, binned in (("0", "0"), ("1", "0"), ("1", "1"), ("1", None)):
+        monkeypatch.setenv("AGX_RADIUS_TILE", tile)
+        if binned is None:
+            monkeypatch.delenv("AGX_RADIUS_BIN", raising=False)
+        else:
+            monkeypatch.setenv("AGX_RADIUS_BIN", binned)
+        with ops.NeighbourIndex(dev(ref), hint_radius=radius) as ix:
+            outs[(tile, binned)] = ix.radius(dev(q), radius).cpu().numpy()
+    for key, val in outs.items():
+        np.testing.assert_array_equal(val, outs[("0", "0")], err_msg=str(key))
+    sub = np.arange(0, q.shape[0], 61)
+    want = R.canonical_sort(R.cutoff_edges(ref, q[sub], 1.0, radius=radius))
+    got = outs[("1", None)]
+    pick = np.isin(got[1], sub)
+    got = got[:, pick]
+    got[1] = np.searchsorted(sub, got[1])
+    np.testing.assert_array_equal(canon(got), want)
+
+
 def test_cutoff_radius_beyond_pi_connects_everything(ops):
     """For r >= pi every point is within reach.  (sklearn itself is not monotone there: its leaf test uses
     sin^2(r/2), which DEcreases past pi, while whole-node acceptance uses r - the result depends on the tree
