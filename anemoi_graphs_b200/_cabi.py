@@ -31,7 +31,10 @@ SIGNATURES = {
     "agx_index_free": (c_int, [c_void_p, c_void_p]),
     "agx_index_info": (c_int, [c_void_p, POINTER(c_int64), POINTER(c_int)]),
     "agx_search_vectors": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
-    "agx_knn": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "agx_knn": (
+        c_int,
+        [c_void_p, c_void_p, c_int64, c_int, c_double, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p],
+    ),
     "agx_radius_count": (c_int, [c_void_p, c_void_p, c_int64, c_double, c_void_p, c_void_p]),
     "agx_exclusive_scan": (c_int, [c_void_p, c_int64, c_void_p, POINTER(c_int64), c_void_p]),
     "agx_radius_fill": (c_int, [c_void_p, c_void_p, c_int64, c_double, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),

@@ -166,6 +166,7 @@ struct KnnArgs {
     const float2* ref_latlon;
     int cells;
     float chord2_init;
+    float chord2_limit;  // search limit (max_radius, inflated by the margins), +inf when there is none
     const float2* q_latlon;
     const int32_t* qperm;  // optional processing order of the queries (spatially binned), or NULL
     int64_t nq;
@@ -189,9 +190,11 @@ __device__ __forceinline__ bool knn_cap_sufficient(float dk, float t2, float& ne
     return dk < __int_as_float(0x7f800000) && need <= t2;
 }
 
-// Per-thread search straight from global memory: grow the cap until it provably holds the k-th neighbour.
+// Per-thread search straight from global memory: grow the cap until it provably holds the k-th neighbour - or until
+// it reaches the caller's search limit (returns true: the list holds what lies inside the limit and nothing is
+// proven about the rest).
 template <int CAP>
-__device__ __forceinline__ void knn_thread_search(const KnnArgs& a, float3 qv, float t2, TopF<CAP>& top, AgxCap& cap) {
+__device__ __forceinline__ bool knn_thread_search(const KnnArgs& a, float3 qv, float t2, TopF<CAP>& top, AgxCap& cap) {
     while (true) {
         top.reset();
         cap = agx_make_cap(t2);
@@ -207,12 +210,13 @@ __device__ __forceinline__ void knn_thread_search(const KnnArgs& a, float3 qv, f
                 }
             }
         }
-        if (cap.everything) break;
+        if (cap.everything) return false;
         float need;
         float dk = top.d_at(a.k - 1);
-        if (knn_cap_sufficient(dk, t2, need)) break;
+        if (knn_cap_sufficient(dk, t2, need)) return false;
+        if (t2 >= a.chord2_limit) return true;
         bool have_k = dk < __int_as_float(0x7f800000);
-        t2 = have_k ? fmaxf(need * 1.0001f, t2 * 1.5f) : t2 * 4.0f;
+        t2 = fminf(have_k ? fmaxf(need * 1.0001f, t2 * 1.5f) : t2 * 4.0f, a.chord2_limit);
     }
 }
 
@@ -293,6 +297,7 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn(KnnArgs a) {
         // ---- scan ------------------------------------------------------------------------------------
         TopF<CAP> top;
         bool staged = fits;
+        bool limited = false;
         float t2_thread = t2;
         float dk = __int_as_float(0x7f800000);       // largest FP32 chord^2 among the k chosen candidates
         float rest_lb = __int_as_float(0x7f800000);  // lower bound of the FP32 chord^2 of every other candidate
@@ -327,21 +332,45 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn(KnnArgs a) {
             }
             float need;
             if (!knn_cap_sufficient(dk, t2, need)) {
-                // this lane needs a wider cap than the tile staged: finish it on its own
-                t2_thread = dk < __int_as_float(0x7f800000) ? fmaxf(need * 1.0001f, t2 * 1.5f) : t2 * 4.0f;
-                staged = false;
-                if (a.stats && active) atomicAdd(a.stats + 2, 1ull);
+                if (t2 >= a.chord2_limit) {
+                    limited = true;  // the tile's cap already is the search limit
+                } else {
+                    // this lane needs a wider cap than the tile staged: finish it on its own
+                    t2_thread = dk < __int_as_float(0x7f800000) ? fmaxf(need * 1.0001f, t2 * 1.5f) : t2 * 4.0f;
+                    t2_thread = fminf(t2_thread, a.chord2_limit);
+                    staged = false;
+                    if (a.stats && active) atomicAdd(a.stats + 2, 1ull);
+                }
             }
         }
         if (!staged) {
-            knn_thread_search<CAP>(a, qv, t2_thread, top, cap);
+            limited = knn_thread_search<CAP>(a, qv, t2_thread, top, cap);
             dk = top.d_at(k - 1);
             rest_lb = top.d_at(k);  // +inf when there is no (k+1)-th candidate
+        }
+        if (limited) {
+            // fewer than k provable neighbours inside the search limit: report what was found there (-1 / +inf for
+            // the missing ones); anything reported is farther than max_radius or exact (see agx_b200.h)
+            if (active) {
+                int32_t* os = a.out_src + q * k;
+#pragma unroll
+                for (int s = 0; s < CAP - 1; ++s)
+                    if (s < k) {
+                        bool have = top.id[s] != 0x7fffffff;
+                        os[s] = have ? top.id[s] : -1;
+                        if (a.out_rdist)
+                            a.out_rdist[q * k + s] = have ? agx_rdist64(ql, a.ref_latlon[top.id[s]]) : __longlong_as_double(0x7ff0000000000000ll);
+                    }
+                if (a.out_dst) {
+                    int32_t* od = a.out_dst + q * k;
+                    for (int s = 0; s < k; ++s) od[s] = (int32_t)(a.dst_base + q);
+                }
+            }
         }
         // ---- decide the set --------------------------------------------------------------------------
         float amb = dk + 2.5f * agx_chord2_margin(dk);  // d_k + 2 margins
         bool ambiguous = (CAP > 1) && (rest_lb <= amb);
-        if (active) {
+        if (active && !limited) {
             int32_t* os = a.out_src + q * k;
             if (!ambiguous) {
                 if (a.out_rdist == nullptr) {
@@ -399,12 +428,13 @@ static void launch_knn(const KnnArgs& a, cudaStream_t stream) {
     k_knn<CAP><<<grid, KNN_WARPS * 32, 0, stream>>>(a);
 }
 
-extern "C" int agx_knn(const agx_index_t* ix, const float* q_latlon, int64_t nq, int k, int32_t* out_src,
+extern "C" int agx_knn(const agx_index_t* ix, const float* q_latlon, int64_t nq, int k, double max_radius, int32_t* out_src,
                        int32_t* out_dst, int64_t dst_base, double* out_rdist, int64_t* stats, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     AGX_REQUIRE(ix != nullptr, AGX_ERR_ARG, "agx_knn: NULL index");
     AGX_REQUIRE(nq >= 0, AGX_ERR_ARG, "agx_knn: nq < 0");
     AGX_REQUIRE(k > 0, AGX_ERR_ARG, "agx_knn: k must be positive (got %d)", k);
+    AGX_REQUIRE(max_radius >= 0.0, AGX_ERR_ARG, "agx_knn: max_radius must be >= 0 (0 = unlimited)");
     // sklearn raises "Expected n_neighbors <= n_samples_fit" (neighbors/_base.py kneighbors)
     AGX_REQUIRE((int64_t)k <= ix->n, AGX_ERR_ARG, "Expected n_neighbors <= n_samples_fit, but n_neighbors = %d, n_samples_fit = %lld",
                 k, (long long)ix->n);
@@ -423,6 +453,15 @@ extern "C" int agx_knn(const agx_index_t* ix, const float* q_latlon, int64_t nq,
     a.cell_start = ix->cell_start;
     a.ref_latlon = ix->latlon;
     a.cells = ix->cells;
+    // search limit: chord^2 of max_radius plus the four margins the sufficiency test needs, so that every query whose
+    // k-th neighbour lies within max_radius is still answered exactly
+    a.chord2_limit = __builtin_inff();
+    if (max_radius > 0.0 && max_radius < 3.141592653589793) {
+        double sh = sin(0.5 * max_radius), c2 = 4.0 * sh * sh;
+        double lim = c2 + 5.0 * (4.2e-7 * sqrt(c2) + 1.0e-6 * c2 + 1.0e-13);
+        a.chord2_limit = (float)(lim * 1.000001);
+        if (t2 > lim) t2 = lim;
+    }
     a.chord2_init = (float)t2;
     a.q_latlon = (const float2*)q_latlon;
     a.qperm = nullptr;

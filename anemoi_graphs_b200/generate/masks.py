@@ -85,8 +85,11 @@ class KNNAreaMaskBuilder:
         """CUDA bool mask: nearest reference node within ``margin_radius_km``."""
         assert self._reference is not None, f"{self.__class__.__name__} must be fitted first."
         q = _device.to_device(coords_rad, torch.float32)
+        # only "is the nearest reference node within the margin?" is asked, so the search stops a little beyond it -
+        # a query on the far side of the globe from a limited-area patch must not walk every cell on the way
+        limit = 1.01 * self.margin_radius_km / EARTH_RADIUS + 1e-6
         with ops.NeighbourIndex(self._reference, hint_k=1) as index:
-            _, rdist = index.knn(q, 1, return_rdist=True, tag="knn_mask")
+            _, rdist = index.knn(q, 1, return_rdist=True, tag="knn_mask", max_radius=limit)
         dist = 2.0 * torch.asin(torch.sqrt(rdist[:, 0]))  # HaversineDistance64._rdist_to_dist
         return dist * EARTH_RADIUS <= self.margin_radius_km
 

@@ -120,10 +120,13 @@ class NeighbourIndex:
         out: torch.Tensor | None = None,
         out_offset: int = 0,
         tag: str = "knn",
+        max_radius: float = 0.0,
     ):
         """``edge_index`` (2, nq*k) int32 - row 0 the k nearest reference points of each query, row 1
         ``dst_base + query`` - and optionally the float64 ``rdist`` (nq, k).  With ``out`` (a larger
-        contiguous (2, E) int32 buffer) the block is written at column ``out_offset`` instead."""
+        contiguous (2, E) int32 buffer) the block is written at column ``out_offset`` instead.  ``max_radius``
+        (radians, 0 = unlimited) bounds the search: exact for queries whose k-th neighbour is within it, otherwise
+        -1 / +inf or points beyond it (``agx_b200.h``)."""
         q = _dev_x(q)
         nq = int(q.shape[0])
         if out is None:
@@ -136,7 +139,7 @@ class NeighbourIndex:
         with _span(tag, nq * k):
             check(
                 self.lib.agx_knn(
-                    self.handle, ptr(q), nq, int(k), out.data_ptr() + 4 * out_offset,
+                    self.handle, ptr(q), nq, int(k), float(max_radius), out.data_ptr() + 4 * out_offset,
                     out.data_ptr() + row + 4 * out_offset, int(dst_base), ptr(rdist), ptr(stats), current_stream(),
                 )
             )  # fmt: skip

@@ -72,8 +72,13 @@ int agx_search_vectors(const float* latlon /*DEV n*2*/, int64_t n, float* xyz /*
  * (sklearn _dist_metrics.pyx.tp:2639-2648); ties within 2^-40 relative go to the lower index.
  * out_rdist (optional, nq*k) receives the float64 rdist of every neighbour.
  * stats (optional, DEV int64[4]) += {queries refined in float64, queries with a tie at the k-th
- * boundary, queries needing a wider search, candidate records staged in shared memory (x32 = FP32 pairs)}. */
-int agx_knn(const agx_index_t* index, const float* q_latlon /*DEV nq*2*/, int64_t nq, int k,
+ * boundary, queries needing a wider search, candidate records staged in shared memory (x32 = FP32 pairs)}.
+ * max_radius (radians; 0 = unlimited) bounds the search, for callers that only ask "is anything within r?"
+ * (KNNAreaMaskBuilder.get_mask compares the distance with a margin, generate/masks.py:94-99 - without the bound a
+ * query far from a clustered reference set walks the whole sphere): a query whose k-th neighbour lies within
+ * max_radius is answered exactly; otherwise the slots hold reference points found inside the bound, each of them
+ * farther than max_radius, or -1 with rdist = +inf.                                                          */
+int agx_knn(const agx_index_t* index, const float* q_latlon /*DEV nq*2*/, int64_t nq, int k, double max_radius,
             int32_t* out_src /*DEV*/, int32_t* out_dst /*DEV or NULL*/, int64_t dst_base,
             double* out_rdist /*DEV or NULL*/, int64_t* stats /*DEV or NULL*/, void* stream);
 

@@ -165,6 +165,30 @@ def test_knn_sparse_clustered_and_polar(ops):
             np.testing.assert_array_equal(canon(ei), want)
 
 
+def test_knn_search_limit_on_clustered_references(ops):
+    """max_radius: exact for queries whose nearest reference point lies within it, -1 / +inf (or a point beyond it)
+    for the others - the contract KNNAreaMaskBuilder relies on for limited-area patches."""
+    ref = grids.latlon_deg_to_x(*grids.lam_patch(150, 150, 10.0)).numpy()  # 22 500 points in a 1500 km patch
+    q = grids.latlon_deg_to_x(*grids.uniform_sphere(60000, seed=8)).numpy()
+    q = np.concatenate([q, ref[::50] + np.float32(1e-3)])  # and some queries inside the patch
+    limit = 300.0 / 6371.0
+    with ops.NeighbourIndex(dev(ref), hint_k=1) as ix:
+        full, rd_full = ix.knn(dev(q), 1, return_rdist=True)
+        lim, rd_lim = ix.knn(dev(q), 1, return_rdist=True, max_radius=limit)
+    full, lim = full.cpu().numpy()[0], lim.cpu().numpy()[0]
+    d_full = 2.0 * np.arcsin(np.sqrt(rd_full.cpu().numpy()[:, 0]))
+    d_lim = 2.0 * np.arcsin(np.sqrt(np.minimum(rd_lim.cpu().numpy()[:, 0], 1.0)))
+    near = d_full <= limit
+    assert near.sum() > 500 and (~near).sum() > 10000
+    np.testing.assert_array_equal(lim[near], full[near])
+    np.testing.assert_array_equal(rd_lim.cpu().numpy()[near, 0], rd_full.cpu().numpy()[near, 0])
+    assert ((lim[~near] == -1) | (d_lim[~near] > limit)).all()
+    assert np.isinf(rd_lim.cpu().numpy()[~near, 0][lim[~near] == -1]).all()
+    # the mask the reference computes (generate/masks.py:94-99) from a bounded search
+    want = R.knn_area_mask(ref, q, 250.0)
+    np.testing.assert_array_equal(d_lim * 6371.0 <= 250.0, want)
+
+
 def test_knn_argument_errors(ops):
     ref = np.zeros((3, 2), dtype=np.float32)
     with ops.NeighbourIndex(dev(ref)) as ix:
