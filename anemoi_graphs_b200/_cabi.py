@@ -69,6 +69,14 @@ SIGNATURES = {
         [c_int, c_void_p, POINTER(c_int32), c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     ),
     "agx_multiscale_tri_fill": (c_int, [c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "agx_hex_num_cells": (c_int64, [c_int]),
+    "agx_hex_cells": (c_int, [c_int, c_void_p, c_void_p, c_void_p]),
+    "agx_hex_adjacency": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "agx_multiscale_adj_count": (
+        c_int,
+        [c_int, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), c_int, c_int, c_int64,
+         c_void_p, c_void_p, c_void_p],
+    ),  # fmt: skip
 }
 
 _lib = None

@@ -296,7 +296,10 @@ __global__ void k_ms_adjacency(const int32_t* __restrict__ faces, int64_t nf, in
 }
 
 // scratch element i of node t lives at scratch[i * n_nodes + t] (coalesced across threads)
-__global__ void __launch_bounds__(128) k_ms_expand(MsLevels lv, int x_hops, int64_t n_nodes, int hop_cap,
+// walk_all = 0: the frontier only crosses valid vertices (tri meshes, tri_icosahedron.py:214-215);
+// walk_all = 1: the whole disk is walked and invalid cells are dropped afterwards (h3.k_ring(idx, k) & nodes,
+// hex_icosahedron.py:147).
+__global__ void __launch_bounds__(128) k_ms_expand(MsLevels lv, int x_hops, int walk_all, int64_t n_nodes, int hop_cap,
                                                     int32_t* __restrict__ counts, int32_t* __restrict__ scratch) {
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_nodes; t += (int64_t)gridDim.x * blockDim.x) {
         int32_t* uni = scratch + t;                                      // union list (graph positions), stride n_nodes
@@ -317,7 +320,7 @@ __global__ void __launch_bounds__(128) k_ms_expand(MsLevels lv, int x_hops, int6
                     int d = deg[w];
                     for (int s = 0; s < d; ++s) {
                         int x = nb[6 * (int64_t)w + s];
-                        if (vmap[x] < 0) continue;  // mesh edges need both endpoints valid (tri_icosahedron.py:214-215)
+                        if (!walk_all && vmap[x] < 0) continue;  // mesh edges need both endpoints valid
                         bool seen = false;
                         for (int j = 0; j < n_que; ++j) seen |= (que[(int64_t)j * n_nodes] == x);
                         if (!seen) que[(int64_t)(n_que++) * n_nodes] = x;
@@ -327,6 +330,7 @@ __global__ void __launch_bounds__(128) k_ms_expand(MsLevels lv, int x_hops, int6
             }
             for (int i = 1; i < n_que; ++i) {  // i = 0 is the centre (center=False)
                 int r = vmap[que[(int64_t)i * n_nodes]];
+                if (r < 0) continue;
                 bool seen = (r == (int)t);  // two vertices of one level never share a node; guard self loops anyway
                 for (int j = 0; j < n_uni; ++j) seen |= (uni[(int64_t)j * n_nodes] == r);
                 if (!seen) uni[(int64_t)(n_uni++) * n_nodes] = r;
@@ -398,7 +402,7 @@ static int ms_run(int max_level, const int32_t* faces_all, const int32_t* levels
         off += nv;
     }
     (void)max_level;
-    k_ms_expand<<<agx_grid(n_nodes, 128, 16), 128, 0, stream>>>(lv, x_hops, n_nodes, ms_hop_cap(x_hops), counts, scratch);
+    k_ms_expand<<<agx_grid(n_nodes, 128, 16), 128, 0, stream>>>(lv, x_hops, 0, n_nodes, ms_hop_cap(x_hops), counts, scratch);
     AGX_LAUNCH_OK();
     agx_note_launch(n_levels + 1);
     AGX_CUDA_OK(cudaFreeAsync(deg_all, stream));
@@ -458,6 +462,33 @@ extern "C" int agx_multiscale_tri_count_mapped(int max_level, const int32_t* fac
         inv[l] = node_vertex + (int64_t)l * n_nodes;
     }
     return ms_run(max_level, faces_all, levels, n_levels, x_hops, n_nodes, vmap, inv, counts, scratch, stream);
+}
+
+extern "C" int agx_multiscale_adj_count(int n_levels, const int32_t* const* nb, const int32_t* const* deg,
+                                        const int32_t* const* cell_node, const int32_t* const* node_cell, int x_hops,
+                                        int walk_all, int64_t n_nodes, int32_t* counts, int32_t* scratch, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    AGX_REQUIRE(n_levels > 0 && n_levels <= MS_MAX_LEVELS, AGX_ERR_ARG, "agx_multiscale_adj_count: 1..%d levels supported",
+                MS_MAX_LEVELS);
+    AGX_REQUIRE(x_hops > 0, AGX_ERR_ARG, "x_hops == 0, graph would have no edges ...");
+    AGX_REQUIRE(x_hops <= 8, AGX_ERR_UNSUPPORTED, "agx_multiscale_adj_count: x_hops = %d > 8 is not built yet", x_hops);
+    AGX_REQUIRE(n_nodes >= 0, AGX_ERR_ARG, "agx_multiscale_adj_count: n_nodes < 0");
+    if (n_nodes == 0) return AGX_OK;
+    AGX_REQUIRE(nb && deg && cell_node && node_cell && counts && scratch, AGX_ERR_ARG, "agx_multiscale_adj_count: NULL buffer");
+    MsLevels lv;
+    lv.n = n_levels;
+    for (int l = 0; l < n_levels; ++l) {
+        AGX_REQUIRE(nb[l] && deg[l] && cell_node[l] && node_cell[l], AGX_ERR_ARG, "agx_multiscale_adj_count: NULL table at level %d", l);
+        lv.nb[l] = nb[l];
+        lv.deg[l] = deg[l];
+        lv.vmap[l] = cell_node[l];
+        lv.inv[l] = node_cell[l];
+    }
+    k_ms_expand<<<agx_grid(n_nodes, 128, 16), 128, 0, stream>>>(lv, x_hops, walk_all ? 1 : 0, n_nodes, ms_hop_cap(x_hops),
+                                                                counts, scratch);
+    AGX_LAUNCH_OK();
+    agx_note_launch(1);
+    return AGX_OK;
 }
 
 extern "C" int agx_multiscale_tri_fill(int64_t n_nodes, const int32_t* counts, const int64_t* offsets,

@@ -343,10 +343,10 @@ class MultiScaleEdges(BaseEdgeBuilder):
                 area_mask_builder=all_points_mask_builder,
             )
         if node_type in ("HexNodes", "LimitedAreaHexNodes"):
-            raise NotImplementedError(
-                "MultiScaleEdges on hexagonal (H3) nodes is not built: the h3 library the reference relies on "
-                "(generate/hex_icosahedron.py) is neither in /root/reference nor in this image, so there is "
-                "nothing to check a restatement against (DESIGN.md, out of scope)."
+            from ..generate import hex_icosahedron
+
+            return hex_icosahedron.multiscale_edges(
+                source_nodes, resolutions=source_nodes["_resolutions"], x_hops=self.x_hops
             )
         raise ValueError(f"Invalid node type {node_type}")
 

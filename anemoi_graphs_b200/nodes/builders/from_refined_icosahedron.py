@@ -16,6 +16,7 @@ import numpy as np
 import torch
 
 from ... import device as _device
+from ...generate.hex_icosahedron import create_hex_nodes
 from ...generate.masks import KNNAreaMaskBuilder
 from ...generate.tri_icosahedron import create_stretched_tri_nodes
 from ...generate.tri_icosahedron import create_tri_nodes
@@ -23,11 +24,6 @@ from .base import BaseNodeBuilder
 
 LOGGER = logging.getLogger(__name__)
 
-_H3_MESSAGE = (
-    "hexagonal (H3) nodes are not built: the reference takes cell ids, centres and neighbourhoods from the h3 C "
-    "library (generate/hex_icosahedron.py:47,79,99,147), which is neither under /root/reference nor installed "
-    "here, so a restatement could not be checked against anything (DESIGN.md, out of scope)."
-)
 
 
 class IcosahedralNodes(BaseNodeBuilder, ABC):
@@ -56,7 +52,9 @@ class IcosahedralNodes(BaseNodeBuilder, ABC):
     def get_coordinates(self) -> torch.Tensor:
         """float32 (num_nodes, 2) coordinates in radians, in graph order."""
         self.nx_graph, coords_rad, order = self.create_nodes()
-        self._x_device = coords_rad[order]  # == coords_rad[node_ordering], gathered on the device
+        # == torch.tensor(coords_rad[node_ordering], dtype=torch.float32), gathered (and, for the float64 hexagonal
+        # centres, rounded) on the device
+        self._x_device = coords_rad[order].to(torch.float32)
         # the hidden ``_node_ordering`` attribute is a host array in the reference: a pinned copy, complete when the
         # enclosing deferred scope (or this builder's register_nodes) flushes
         self.node_ordering = _device.to_host(order).numpy()
@@ -102,10 +100,12 @@ class TriNodes(IcosahedralNodes):
 
 
 class HexNodes(IcosahedralNodes):
-    """Nodes based on H3 hexagonal refinements - not built (no h3, no oracle)."""
+    """Nodes based on iterative refinements of an icosahedron (H3 hexagonal cells).
+
+    The reference depends on the h3 Python library; here the cells come from ``agx_hex_cells``."""
 
     def create_nodes(self):
-        raise NotImplementedError(_H3_MESSAGE)
+        return create_hex_nodes(resolution=max(self.resolutions))
 
 
 class LimitedAreaTriNodes(LimitedAreaIcosahedralNodes):
@@ -116,10 +116,10 @@ class LimitedAreaTriNodes(LimitedAreaIcosahedralNodes):
 
 
 class LimitedAreaHexNodes(LimitedAreaIcosahedralNodes):
-    """H3 nodes within an area of interest - not built (no h3, no oracle)."""
+    """H3 hexagonal-cell nodes within an area of interest."""
 
     def create_nodes(self):
-        raise NotImplementedError(_H3_MESSAGE)
+        return create_hex_nodes(resolution=max(self.resolutions), area_mask_builder=self.area_mask_builder)
 
 
 class StretchedIcosahedronNodes(IcosahedralNodes):

@@ -512,8 +512,97 @@ def multiscale_tri_edges_mapped(
     return out
 
 
+# ----------------------------------------------------------------------------------------------
+# hexagonal (H3) mesh
+# ----------------------------------------------------------------------------------------------
+def hex_num_cells(res: int) -> int:
+    """H3's ``numHexagons(res)`` = 2 + 120 * 7**res."""
+    n = int(load_library().agx_hex_num_cells(int(res)))
+    if n < 0:
+        raise ValueError(f"H3 resolutions are 0..15, got {res}")
+    return n
+
+
+class HexCells:
+    """All cells of one H3 resolution on the device: ``latlon`` float64 (n, 2) radians - the values the reference
+    obtains as ``np.deg2rad(h3.h3_to_geo(idx))`` (generate/hex_icosahedron.py:47) - in (face, i, j) order, and the
+    ``pentagon`` flags.  ``neighbours()`` gives the edge-adjacency table (one ring of ``h3.k_ring``)."""
+
+    def __init__(self, res: int, device=None) -> None:
+        _cabi.require_cuda()
+        device = torch.device("cuda") if device is None else device
+        self.res = int(res)
+        self.n = hex_num_cells(self.res)
+        self.latlon = torch.empty((self.n, 2), dtype=torch.float64, device=device)
+        self.pentagon = torch.empty(self.n, dtype=torch.uint8, device=device)
+        with _span("hex_cells", self.n):
+            check(load_library().agx_hex_cells(self.res, ptr(self.latlon), ptr(self.pentagon), current_stream()))
+        self._latlon32 = None
+        self._nb = None
+
+    @property
+    def latlon32(self) -> torch.Tensor:
+        if self._latlon32 is None:
+            self._latlon32 = self.latlon.to(torch.float32)
+        return self._latlon32
+
+    def neighbours(self) -> tuple[torch.Tensor, torch.Tensor]:
+        """``(nb (n, 6) int32, -1 padded; deg (n,) int32)``: the cells sharing an edge with each cell."""
+        if self._nb is None:
+            x = self.latlon32
+            with NeighbourIndex(x, hint_k=7) as index:
+                knn7 = index.knn(x, 7, tag="knn_hex_adjacency")[0]
+            nb = torch.empty((self.n, 6), dtype=torch.int32, device=x.device)
+            deg = torch.empty(self.n, dtype=torch.int32, device=x.device)
+            check(load_library().agx_hex_adjacency(knn7.data_ptr(), ptr(self.pentagon), self.n, ptr(nb), ptr(deg), current_stream()))
+            self._nb = (nb, deg)
+        return self._nb
+
+
+def multiscale_adj_edges(levels: list[tuple], x_hops: int, walk_all: bool, n_nodes: int) -> torch.Tensor:
+    """Multi-scale edges over explicit adjacency tables: (2, E) int32 sorted by (dst, src).
+
+    ``levels`` lists, per mesh level, ``(nb (n, 6) int32, deg (n,) int32, cell_node (n,) int32, node_cell
+    (n_nodes,) int32)`` - see ``agx_multiscale_adj_count``."""
+    lib = load_library()
+    if x_hops > 8:
+        raise NotImplementedError(f"x_hops = {x_hops} > 8 is not built yet")
+    dev = levels[0][0].device
+    n_levels = len(levels)
+    tables = [[t.contiguous() for t in lv] for lv in levels]
+    for nb, deg, cell_node, node_cell in tables:
+        assert nb.dtype == deg.dtype == cell_node.dtype == node_cell.dtype == torch.int32
+        assert nb.shape == (deg.shape[0], 6) and cell_node.shape == deg.shape and node_cell.shape == (n_nodes,)
+    arrays = [(c_void_p * n_levels)(*[lv[i].data_ptr() for lv in tables]) for i in range(4)]
+    per_node = int(lib.agx_multiscale_scratch_per_node(n_levels, int(x_hops)))
+    scratch = torch.empty(per_node * max(n_nodes, 1), dtype=torch.int32, device=dev)
+    counts = torch.zeros(n_nodes, dtype=torch.int32, device=dev)
+    offsets = torch.empty(n_nodes + 1, dtype=torch.int64, device=dev)
+    stream = current_stream()
+    with _span("multiscale_count", n_nodes):
+        check(
+            lib.agx_multiscale_adj_count(
+                n_levels, arrays[0], arrays[1], arrays[2], arrays[3], int(x_hops), int(bool(walk_all)), n_nodes,
+                ptr(counts), ptr(scratch), stream,
+            )
+        )  # fmt: skip
+    total = c_int64()
+    check(lib.agx_exclusive_scan(ptr(counts), n_nodes, ptr(offsets), byref(total), stream))
+    out = torch.empty((2, total.value), dtype=torch.int32, device=dev)
+    if total.value:
+        check(
+            lib.agx_multiscale_tri_fill(
+                n_nodes, ptr(counts), ptr(offsets), ptr(scratch), per_node, out[0].data_ptr(), out[1].data_ptr(), stream
+            )
+        )
+    return out
+
+
 __all__ = [
     "multiscale_tri_edges_mapped",
+    "HexCells",
+    "hex_num_cells",
+    "multiscale_adj_edges",
     "NeighbourIndex",
     "NodeTables",
     "Icosphere",

@@ -177,6 +177,33 @@ int agx_multiscale_tri_fill(int64_t n_nodes, const int32_t* counts, const int64_
                             const int32_t* scratch, int64_t scratch_per_node, int32_t* out_src,
                             int32_t* out_dst, void* stream);
 
+/* ---- hexagonal (H3) hidden mesh ------------------------------------------------------------------------
+ * agx_hex_cells: replaces `h3.uncompact(h3.get_res0_indexes(), res)` + `np.deg2rad(h3.h3_to_geo(idx))`
+ * (generate/hex_icosahedron.py:47,99): the float64 (lat, lon) radians of all agx_hex_num_cells(res) =
+ * 2 + 120*7^res cell centres of an H3 resolution, in (icosahedron face, lattice i, lattice j) order - H3's own
+ * order is a Python set's, the reference re-orders by get_coordinates_ordering anyway - and the pentagon flags.
+ * The H3 library itself is not available to this build: the geometry is restated from its published
+ * definition (faceijk.c _hex2dToGeo, coordijk.c _downAp7/_downAp7r, geoCoord.c _geoAzDistanceRads) and
+ * checked against the two cell centres H3's documentation prints (oracle/h3_restated.py).
+ * agx_hex_adjacency: the cells sharing an edge with each cell, nb[6*u + s] (-1 padded), deg[u] = 6 (5 for the 12
+ * pentagons), from row 0 of an `agx_knn(k = 7)` self query of the centres: on an aperture-7 grid the 6 nearest
+ * centres ARE the edge neighbours (second ring sqrt(3) x farther, gnomonic distortion <= 1.26).  One BFS step
+ * over this table = one ring of `h3.k_ring` (generate/hex_icosahedron.py:147).
+ * agx_multiscale_adj_count: the multi-scale expansion of agx_multiscale_tri_count over caller-supplied
+ * adjacency tables (HOST arrays of n_levels DEV pointers): nb / deg as above; cell_node[l][c] = graph position
+ * of the node that level-l cell c stands for (`h3_to_center_child`, hex_icosahedron.py:149-150) or -1;
+ * node_cell[l][t] = the inverse or -1.  walk_all = 1 walks the full disk and drops invalid cells afterwards
+ * (`k_ring(idx, k) & nodes`), 0 never crosses an invalid cell (the tri rule).  Fill with
+ * agx_multiscale_tri_fill; scratch as agx_multiscale_scratch_per_node.                                   */
+int64_t agx_hex_num_cells(int res);
+int agx_hex_cells(int res, double* latlon /*DEV n*2*/, uint8_t* pentagon /*DEV n or NULL*/, void* stream);
+int agx_hex_adjacency(const int32_t* knn7 /*DEV n*7*/, const uint8_t* pentagon /*DEV n*/, int64_t n,
+                      int32_t* nb /*DEV n*6*/, int32_t* deg /*DEV n*/, void* stream);
+int agx_multiscale_adj_count(int n_levels, const int32_t* const* nb /*HOST[n_levels] of DEV*/,
+                             const int32_t* const* deg, const int32_t* const* cell_node,
+                             const int32_t* const* node_cell, int x_hops, int walk_all, int64_t n_nodes,
+                             int32_t* counts /*DEV n_nodes*/, int32_t* scratch /*DEV*/, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -68,8 +68,10 @@ def test_node_builders_host_side():
         LatLonNodes([0.0], [1.0, 2.0], name="n")
     assert TriNodes(3, "h").resolutions == [0, 1, 2, 3]
     assert TriNodes([1, 3], "h").resolutions == [1, 3]
-    with pytest.raises(NotImplementedError, match="h3"):
-        HexNodes(1, "h").create_nodes()
+    assert HexNodes(2, "h").resolutions == [0, 1, 2]
+    if not torch.cuda.is_available():  # no CPU fallback: generating cells without a device must fail loudly
+        with pytest.raises(RuntimeError, match="CUDA"):
+            HexNodes(1, "h").create_nodes()
 
 
 def test_attribute_ctor_and_norm_validation():
