@@ -209,17 +209,17 @@ static int agx_sample_coherence(const agx_index_t* ix, const float2* q_latlon, i
     int n_samples = (int)(n_tiles < AGX_SAMPLE_TILES ? n_tiles : AGX_SAMPLE_TILES);
     int64_t stride = n_tiles / n_samples;
     int* n_fit = nullptr;
-    AGX_CUDA_OK(cudaMallocAsync(&n_fit, sizeof(int), stream));
-    AGX_CUDA_OK(cudaMemsetAsync(n_fit, 0, sizeof(int), stream));
+    AGX_CUDA_OK(cudaMallocAsync(&n_fit, 2 * sizeof(int), stream));
+    AGX_CUDA_OK(cudaMemsetAsync(n_fit, 0, 2 * sizeof(int), stream));
     k_tile_sample<<<(n_samples * 32 + 127) / 128, 128, 0, stream>>>(ix->cell_start, ix->cells, q_latlon, nq, chord2_cap, stride,
                                                                        n_samples, n_fit);
     AGX_LAUNCH_OK();
     agx_note_launch(1);
-    int host = 0;
-    AGX_CUDA_OK(cudaMemcpyAsync(&host, n_fit, sizeof(int), cudaMemcpyDeviceToHost, stream));
-    AGX_CUDA_OK(cudaFreeAsync(n_fit, stream));
-    AGX_CUDA_OK(cudaStreamSynchronize(stream));
-    *frac = (double)host / (double)n_samples;
+    int host[2] = {0, 0};
+    int rc = agx_readback(host, n_fit, 1, stream);  // not through the copy engine: bulk D2H copies may be queued there
+    cudaFreeAsync(n_fit, stream);
+    if (rc) return rc;
+    *frac = (double)host[0] / (double)n_samples;
     return AGX_OK;
 }
 

@@ -6,6 +6,8 @@
 
 #include "agx_common.cuh"
 
+#include <math.h>
+
 static thread_local char g_err[512] = "";
 static std::atomic<int64_t> g_launches{0};
 
@@ -33,6 +35,29 @@ void agx_pool_keep_warm(void) {
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
     }
     done_mask.fetch_or(bit, std::memory_order_relaxed);
+}
+
+// Small device -> host read-backs (a scan total, a reduction result) must not queue behind the bulk device -> host
+// copies of the previous edge set on the copy engine (3.7 ms for the 208 MB of the O1280 cut-off edges): a
+// one-thread kernel stores the words straight into mapped pinned memory over PCIe, and the host waits for the
+// stream only.
+__global__ void k_store_to_host(const unsigned long long* __restrict__ src, volatile unsigned long long* dst, int words) {
+    for (int i = threadIdx.x; i < words; i += blockDim.x) dst[i] = src[i];
+    __threadfence_system();
+}
+
+int agx_readback(void* host_dst, const void* dev_src, int words, cudaStream_t stream) {
+    static thread_local unsigned long long* slot = nullptr;  // 32 words of mapped pinned memory per host thread
+    AGX_REQUIRE(words > 0 && words <= 32, AGX_ERR_ARG, "agx_readback: 1..32 words");
+    if (!slot) AGX_CUDA_OK(cudaHostAlloc((void**)&slot, 32 * sizeof(unsigned long long), cudaHostAllocMapped | cudaHostAllocPortable));
+    unsigned long long* dev_view = nullptr;
+    AGX_CUDA_OK(cudaHostGetDevicePointer((void**)&dev_view, slot, 0));
+    k_store_to_host<<<1, 32, 0, stream>>>((const unsigned long long*)dev_src, dev_view, words);
+    AGX_LAUNCH_OK();
+    agx_note_launch(1);
+    AGX_CUDA_OK(cudaStreamSynchronize(stream));
+    memcpy(host_dst, slot, words * sizeof(unsigned long long));
+    return AGX_OK;
 }
 
 extern "C" const char* agx_last_error(void) { return g_err; }
@@ -149,9 +174,9 @@ extern "C" int agx_exclusive_scan(const int32_t* counts, int64_t n, int64_t* off
     AGX_LAUNCH_OK();
     agx_note_launch(3);
     if (total) {
-        AGX_CUDA_OK(cudaMemcpyAsync(total, tmp + n_tiles, sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
-        AGX_CUDA_OK(cudaFreeAsync(tmp, stream));
-        AGX_CUDA_OK(cudaStreamSynchronize(stream));
+        int rc = agx_readback(total, tmp + n_tiles, 1, stream);
+        cudaFreeAsync(tmp, stream);
+        if (rc) return rc;
     } else {
         AGX_CUDA_OK(cudaFreeAsync(tmp, stream));
     }
@@ -213,11 +238,47 @@ extern "C" int agx_max_positive(const double* values, int64_t n, double* out_val
     AGX_LAUNCH_OK();
     agx_note_launch(2);
     MaxPos host;
-    AGX_CUDA_OK(cudaMemcpyAsync(&host, part + blocks, sizeof(MaxPos), cudaMemcpyDeviceToHost, stream));
-    AGX_CUDA_OK(cudaFreeAsync(part, stream));
-    AGX_CUDA_OK(cudaStreamSynchronize(stream));
+    int rc = agx_readback(&host, part + blocks, 2, stream);
+    cudaFreeAsync(part, stream);
+    if (rc) return rc;
     *out_value = host.v;
     *out_index = host.i;
+    return AGX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// The host half of the grid reference distance (utils.py:62-63): sklearn's compiled HaversineDistance64 calls the
+// C library's sin / cos (sklearn/metrics/_dist_metrics.pyx.tp:2639-2648), so the handful of candidate nodes the
+// GPU search nominates are re-evaluated HERE with the same libm calls and the reference's exact-compare
+// semantics: per node the smallest distance to its neighbours (column 1 of the k = 2 self query), over nodes the
+// largest strictly positive one.  Plain host code (no CUDA): the value carries glibc's bits, not the GPU's.
+// ------------------------------------------------------------------------------------------------
+static double host_rdist64(float lat1f, float lon1f, float lat2f, float lon2f) {
+    volatile double lat1 = lat1f, lon1 = lon1f, lat2 = lat2f, lon2 = lon2f;
+    volatile double sin_0 = sin(0.5 * (lat1 - lat2));
+    volatile double sin_1 = sin(0.5 * (lon1 - lon2));
+    volatile double a = sin_0 * sin_0;  // volatile: no contraction into FMAs whatever the host flags are
+    volatile double cc = cos(lat1) * cos(lat2);
+    volatile double b = cc * sin_1;
+    volatile double c = b * sin_1;
+    return a + c;
+}
+
+extern "C" int agx_host_reference_rdist(const float* q_latlon, const float* nb_latlon, int64_t n_cand, int n_nb,
+                                        double* out_rdist) {
+    AGX_REQUIRE(n_cand >= 0 && n_nb > 0 && out_rdist, AGX_ERR_ARG, "agx_host_reference_rdist: bad arguments");
+    AGX_REQUIRE(n_cand == 0 || (q_latlon && nb_latlon), AGX_ERR_ARG, "agx_host_reference_rdist: NULL buffer");
+    double best = 0.0;
+    for (int64_t c = 0; c < n_cand; ++c) {
+        double nearest = 1.0e300;
+        for (int j = 0; j < n_nb; ++j) {
+            const float* p = nb_latlon + 2 * (c * n_nb + j);
+            double r = host_rdist64(q_latlon[2 * c], q_latlon[2 * c + 1], p[0], p[1]);
+            if (r < nearest) nearest = r;
+        }
+        if (nearest > best && nearest < 1.0e300) best = nearest;
+    }
+    *out_rdist = best;
     return AGX_OK;
 }
 
@@ -249,15 +310,16 @@ extern "C" int agx_mark_nodes(const int32_t* row, int64_t n, int64_t n_nodes, in
     AGX_REQUIRE(row && flags, AGX_ERR_ARG, "agx_mark_nodes: NULL buffer");
     int* bad = nullptr;
     agx_pool_keep_warm();
-    AGX_CUDA_OK(cudaMallocAsync(&bad, sizeof(int), stream));
-    AGX_CUDA_OK(cudaMemsetAsync(bad, 0, sizeof(int), stream));
+    AGX_CUDA_OK(cudaMallocAsync(&bad, 2 * sizeof(int), stream));
+    AGX_CUDA_OK(cudaMemsetAsync(bad, 0, 2 * sizeof(int), stream));
     k_mark_nodes<<<agx_grid(n, 256, 8), 256, 0, stream>>>(row, n, n_nodes, flags, bad);
     AGX_LAUNCH_OK();
     agx_note_launch(1);
-    int host = 0;
-    AGX_CUDA_OK(cudaMemcpyAsync(&host, bad, sizeof(int), cudaMemcpyDeviceToHost, stream));
-    AGX_CUDA_OK(cudaFreeAsync(bad, stream));
-    AGX_CUDA_OK(cudaStreamSynchronize(stream));
+    int host2[2] = {0, 0};
+    int rc = agx_readback(host2, bad, 1, stream);
+    cudaFreeAsync(bad, stream);
+    if (rc) return rc;
+    const int host = host2[0];
     AGX_REQUIRE(host == 0, AGX_ERR_ARG, "agx_mark_nodes: an edge endpoint is outside [0, %lld)", (long long)n_nodes);
     return AGX_OK;
 }

@@ -79,9 +79,21 @@ def deferred():
             flush()
 
 
+def deferring() -> bool:
+    """Inside a ``deferred()`` scope (results are only complete when the scope exits)?"""
+    return _defer_depth > 0
+
+
 def flush() -> None:
-    """Wait for every outstanding collective (``all_gather_v(async_op=True)``) and device->host copy
-    (``to_host``)."""
+    """Give every provisionally numbered node set its final order, then wait for every outstanding collective
+    (``all_gather_v(async_op=True)``) and device->host copy (``to_host``)."""
+    for prov in list(_provisionals):
+        prov.resolve()
+    wait_copies()
+
+
+def wait_copies() -> None:
+    """Wait for the outstanding collectives and device->host copies only (provisional node sets stay provisional)."""
     for key in list(_works):
         for work in _works.pop(key):
             work.wait()  # NCCL: orders the current stream behind the collective; gloo: blocks the host
@@ -140,6 +152,24 @@ def to_host(t: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def to_host_into(t: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    """``to_host`` into an existing pinned host tensor (or a view of one)."""
+    wait_for(t)
+    if t.numel() == 0:
+        return out
+    ready = torch.cuda.Event()
+    ready.record()
+    side = _copy_stream(t.device)
+    with torch.cuda.stream(side):
+        side.wait_event(ready)
+        out.copy_(t, non_blocking=True)
+        done = torch.cuda.Event()
+        done.record(side)
+    t.record_stream(side)
+    _pending.append(done)
+    return out
+
+
 def like_input(result: torch.Tensor, reference_input: torch.Tensor) -> torch.Tensor:
     """Return ``result`` (CUDA) on the device the caller's input lives on."""
     return result if reference_input.is_cuda else to_host(result)
@@ -158,19 +188,28 @@ class NodeState:
     x: torch.Tensor  # CUDA float32 (n, 2)
     tables: object | None = None  # ops.NodeTables
     extras: dict = field(default_factory=dict)
+    prov: object | None = None  # Provisional: ``x`` is in provisional numbering until it resolves
 
 
 STATE_ATTR = "_agx_state"
 EDGE_ATTR = "_agx_edge_index"
 
 
-def node_state(nodes) -> NodeState:
-    """Device copy of ``nodes.x`` (uploaded once per node set; re-uploaded if ``x`` was replaced or modified)."""
+def node_state(nodes, provisional_ok: bool = False) -> NodeState:
+    """Device copy of ``nodes.x`` (uploaded once per node set; re-uploaded if ``x`` was replaced or modified).
+
+    A node set whose final order is still being computed (``Provisional``) is given that order first, unless the
+    caller states that it works in the provisional numbering and tags what it produces (``provisional_ok``)."""
     x = nodes["x"]
     st = nodes.get(STATE_ATTR, None) if hasattr(nodes, "get") else None
+    if isinstance(st, NodeState) and st.prov is not None:
+        if provisional_ok:
+            return st
+        st.prov.resolve()
+        st = nodes[STATE_ATTR]
     if isinstance(st, NodeState) and st.key == _key(x):
         return st
-    flush()  # x may be a pinned tensor one of our own copies is still filling
+    wait_copies()  # x may be a pinned tensor one of our own copies is still filling
     st = NodeState(key=_key(x), x=to_device(x, torch.float32))
     nodes[STATE_ATTR] = st
     return st
@@ -183,13 +222,190 @@ def seed_node_state(nodes, x_dev: torch.Tensor) -> NodeState:
     return st
 
 
-def node_tables(nodes, with_rotation: bool = True):
+def node_tables(nodes, with_rotation: bool = True, provisional_ok: bool = False):
     from . import ops
 
-    st = node_state(nodes)
+    st = node_state(nodes, provisional_ok)
     if st.tables is None:
         st.tables = ops.NodeTables(st.x)
     return st.tables
+
+
+# --------------------------------------------------------------------------------------------------
+# provisional numbering: edge construction that overlaps the host-side node ordering
+# --------------------------------------------------------------------------------------------------
+_provisionals: list = []
+_order_pool = None
+last_trace: dict = {}  # host timestamps of the most recent provisional node set (tools/step_timeline.py)
+# AGX_LAZY_ORDER=0 restores the serial "sort, then build" order of operations (A/B measurements)
+LAZY_NODE_ORDER = __import__("os").environ.get("AGX_LAZY_ORDER", "1") != "0"
+
+
+def _pool():
+    global _order_pool
+    if _order_pool is None:
+        from concurrent.futures import ThreadPoolExecutor
+
+        _order_pool = ThreadPoolExecutor(max_workers=1, thread_name_prefix="agx-node-order")
+    return _order_pool
+
+
+class Provisional:
+    """A node set whose FINAL order is still being computed on a host thread.
+
+    The order of icosahedral nodes is defined by two unstable numpy argsorts on the host
+    (``generate.utils.get_coordinates_ordering``, DESIGN.md H4: 4.4 ms for 164 k nodes, more than all the GPU
+    work of the O1280 graph).  Edge sets whose content does not depend on how the nodes are numbered - cut-off
+    and multi-scale edges, every attribute - are therefore built right away in the generator's own numbering
+    (``x_prov``), while a worker thread sorts; each index row they produce is registered here (``add_row``) and
+    rewritten ``v -> rank[v]`` (``agx_relabel_nodes``) once the order is known, before it is copied to the host.
+    Anything that does depend on the numbering (KNN's lower-index tie rule on the source side, masks, merged
+    builders, a caller reading ``x``) asks for the final order first: ``node_state(nodes)`` / ``flush()``.
+
+    Only a permutation is supported (same node count before and after)."""
+
+    def __init__(self, x_prov: torch.Tensor, sorter, combine) -> None:
+        """``sorter(lat, lon)`` runs on the worker thread on contiguous host float32 columns and returns one or more
+        int64 index arrays; ``combine(*device_copies)`` turns them into the order (CUDA int64: generator index at
+        every graph position) on the device."""
+        import time
+
+        self.x_prov = x_prov.contiguous()
+        n = int(x_prov.shape[0])
+        self.n = n
+        dev = x_prov.device
+        self.combine = combine
+        self.x_final = torch.empty((n, 2), dtype=torch.float32, device=dev)
+        self.x_host = None  # pinned (n, 2) float32 when the graph lives on the host
+        self.order_host = torch.empty(n, dtype=torch.int64, pin_memory=True)  # ``_node_ordering``
+        self.order_dev = None
+        self.rows: list = []
+        self.nodes = None
+        self.state = None
+        self.on_resolved = None
+        self.done = False
+        # the worker needs the coordinates on the host, as two contiguous columns: one async copy behind the
+        # kernel that produced them
+        columns = self.x_prov.t().contiguous()
+        staged = torch.empty((2, n), dtype=torch.float32, pin_memory=True)
+        ready = torch.cuda.Event()
+        ready.record()
+        side = _copy_stream(dev)
+        with torch.cuda.stream(side):
+            side.wait_event(ready)
+            staged.copy_(columns, non_blocking=True)
+            copied = torch.cuda.Event()
+            copied.record(side)
+        columns.record_stream(side)
+        self.trace = {"created": time.perf_counter()}
+
+        def work():
+            self.trace["worker_start"] = time.perf_counter()
+            copied.synchronize()
+            self.trace["coords_on_host"] = time.perf_counter()
+            cols = staged.numpy()
+            out = sorter(cols[0], cols[1])
+            self.trace["sorted"] = time.perf_counter()
+            return out
+
+        self.future = _pool().submit(work)
+        _provisionals.append(self)
+
+    def attach(self, nodes, state: NodeState) -> None:
+        self.nodes, self.state = nodes, state
+        state.prov = self
+        state.x = self.x_prov
+
+    def add_row(self, tensor: torch.Tensor, row: int, host: torch.Tensor | None) -> None:
+        """``tensor[row]`` (CUDA int32 (2, E)) holds provisional indices of this node set; ``host`` is the pinned
+        (2, E) tensor whose row receives the final ones (None: the graph is device-resident)."""
+        self.rows.append((tensor, row, host))
+
+    def resolve(self) -> None:
+        if self.done:
+            return
+        self.done = True
+        if self in _provisionals:
+            _provisionals.remove(self)
+        from ._cabi import check, current_stream, load_library
+
+        import time
+
+        self.trace["resolve_enter"] = time.perf_counter()
+        parts = self.future.result()  # numpy int64 index arrays
+        self.trace["resolve_got_order"] = time.perf_counter()
+        dev = self.x_prov.device
+        parts = parts if isinstance(parts, tuple) else (parts,)
+        staged = torch.empty((len(parts), self.n), dtype=torch.int64, pin_memory=True)
+        for i, part in enumerate(parts):
+            staged[i].numpy()[:] = part
+        parts_dev = staged.to(dev, non_blocking=True)
+        order_dev = self.combine(*[parts_dev[i] for i in range(len(parts))]).contiguous()
+        to_host_into(order_dev, self.order_host)  # ``_node_ordering``: complete at flush like every host copy
+        rank = torch.empty(self.n + 1, dtype=torch.int64, device=dev)
+        rank[order_dev] = torch.arange(self.n, dtype=torch.int64, device=dev)
+        torch.index_select(self.x_prov, 0, order_dev, out=self.x_final)
+        self.order_dev = order_dev
+        lib = load_library()
+        for tensor, row, host in self.rows:
+            wait_for(tensor)  # a sharded builder's all-gather may still be filling it
+            check(lib.agx_relabel_nodes(tensor[row].data_ptr(), int(tensor.shape[1]), rank.data_ptr(), current_stream()))
+            if host is not None:
+                to_host_into(tensor[row], host[row])
+        self.rows = []
+        if self.x_host is not None:
+            to_host_into(self.x_final, self.x_host)
+        if self.state is not None:
+            st = self.state
+            st.prov = None
+            st.x = self.x_final
+            st.tables = None  # built from the provisional coordinates
+            st.extras = {}
+            if self.nodes is not None:
+                st.key = _key(self.nodes["x"])
+        if self.on_resolved is not None:
+            self.on_resolved(self)
+        self.trace["resolve_done"] = time.perf_counter()
+        global last_trace
+        last_trace = self.trace
+
+
+def active_provisional(nodes):
+    """The unresolved ``Provisional`` of a node set, or None."""
+    st = nodes.get(STATE_ATTR, None) if hasattr(nodes, "get") else None
+    return st.prov if isinstance(st, NodeState) else None
+
+
+def tag_rows(edge_index: torch.Tensor, src_prov, dst_prov) -> torch.Tensor:
+    """Mark which rows of a freshly built CUDA (2, E) edge_index are in provisional numbering."""
+    if src_prov is not None or dst_prov is not None:
+        edge_index._agx_prov = (src_prov, dst_prov)
+    return edge_index
+
+
+def row_tags(edge_index: torch.Tensor) -> tuple:
+    tags = getattr(edge_index, "_agx_prov", (None, None))
+    return tuple(p if (p is not None and not p.done) else None for p in tags)
+
+
+def edge_index_like_input(edge_dev: torch.Tensor, reference_input: torch.Tensor) -> torch.Tensor:
+    """``like_input`` for an edge_index that may carry provisional rows: final rows are copied (or returned) now,
+    provisional rows are registered with their node set and complete when it resolves."""
+    tags = row_tags(edge_dev)
+    if tags == (None, None):
+        return like_input(edge_dev, reference_input)
+    if reference_input.is_cuda:
+        for row, prov in enumerate(tags):
+            if prov is not None:
+                prov.add_row(edge_dev, row, None)
+        return edge_dev
+    out = torch.empty(edge_dev.shape, dtype=edge_dev.dtype, pin_memory=True)
+    for row, prov in enumerate(tags):
+        if prov is None:
+            to_host_into(edge_dev[row], out[row])
+        else:
+            prov.add_row(edge_dev, row, out)
+    return out
 
 
 def remember_edge_index(store, host_or_dev: torch.Tensor, dev: torch.Tensor) -> None:

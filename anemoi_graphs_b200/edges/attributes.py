@@ -122,8 +122,20 @@ def compute_attributes(graph, edges_name: tuple[str, str, str], attrs: dict) -> 
     store = graph[tuple(edges_name)]
     edge_index = _device.device_edge_index(store)
     host_side = not store["edge_index"].is_cuda
-    src = _device.node_tables(graph[source_name])
-    dst = _device.node_tables(graph[target_name])
+    # A row of the edge list may still be in the provisional numbering of its node set (device.Provisional): the
+    # attributes depend on coordinates only, so they are evaluated right away against the matching (provisional)
+    # node records.  Anything else - final rows against a provisional node set - needs the final order first.
+    tags = _device.row_tags(edge_index)
+    for row, name in ((0, source_name), (1, target_name)):
+        prov = _device.active_provisional(graph[name])
+        if prov is not None and tags[row] is not prov:
+            prov.resolve()
+    if source_name == target_name and tags[0] is not tags[1]:
+        for prov in tags:
+            if prov is not None:
+                prov.resolve()
+    src = _device.node_tables(graph[source_name], provisional_ok=True)
+    dst = _device.node_tables(graph[target_name], provisional_ok=True)
     lengths = [(k, a) for k, a in ours.items() if isinstance(a, EdgeLength)]
     dirs = [(k, a) for k, a in ours.items() if isinstance(a, EdgeDirection)]
     _, w = _device.world()

@@ -72,12 +72,20 @@ class BaseEdgeBuilder(ABC):
         """Prepare node information and get source and target nodes."""
         return graph[self.source_name], graph[self.target_name]
 
+    # May this builder run on a node set that is still in provisional numbering (``device.Provisional``)?  Only if
+    # its result does not depend on how the nodes are numbered; ``_provisional_ok`` is raised per call by
+    # ``register_edges`` when nothing else (masks, a merge with existing edges) needs final indices.
+    provisional_source_ok = True
+    provisional_target_ok = True
+    _provisional_ok = False
+
     def get_edge_index_device(self, graph) -> torch.Tensor:
         source_nodes, target_nodes = self.prepare_node_data(graph)
         return self.compute_edge_index(source_nodes, target_nodes)
 
     def get_edge_index(self, graph) -> torch.Tensor:
         """Edge indices (2, num_edges) int32 of source and target nodes (edges/builder.py:69-87)."""
+        self._provisional_ok = False
         dev = self.get_edge_index_device(graph)
         out = _device.like_input(dev, graph[self.target_name]["x"])
         _device.maybe_flush()
@@ -85,9 +93,13 @@ class BaseEdgeBuilder(ABC):
 
     def register_edges(self, graph):
         """Register edges in the graph (edges/builder.py:89-115)."""
-        edge_dev = self.get_edge_index_device(graph)
-        edge_type = type(self).__name__
         store = graph[self.name]
+        self._provisional_ok = "edge_index" not in store  # a merge sorts by index: final numbering only
+        try:
+            edge_dev = self.get_edge_index_device(graph)
+        finally:
+            self._provisional_ok = False
+        edge_type = type(self).__name__
         x = graph[self.target_name]["x"]
 
         if "edge_index" in store:
@@ -98,7 +110,7 @@ class BaseEdgeBuilder(ABC):
         else:
             store["edge_type"] = edge_type
 
-        out = _device.like_input(edge_dev, x)
+        out = _device.edge_index_like_input(edge_dev, x)
         store["edge_index"] = out
         _device.remember_edge_index(store, out, edge_dev)
         _device.maybe_flush()
@@ -146,8 +158,12 @@ class NodeMaskingMixin:
 
     def get_node_coordinates(self, source_nodes, target_nodes):
         """Device coordinates of the (masked) source and target nodes and the row selections."""
-        src = _device.node_state(source_nodes).x
-        dst = _device.node_state(target_nodes).x
+        masked = self.source_mask_attr_name is not None or self.target_mask_attr_name is not None
+        ok = self._provisional_ok and not masked
+        src_st = _device.node_state(source_nodes, provisional_ok=ok and self.provisional_source_ok)
+        dst_st = _device.node_state(target_nodes, provisional_ok=ok and self.provisional_target_ok)
+        self._row_provs = (src_st.prov, dst_st.prov)  # rows of the result that will be in provisional numbering
+        src, dst = src_st.x, dst_st.x
         src_sel = self._selection(source_nodes, self.source_mask_attr_name, src.device)
         dst_sel = self._selection(target_nodes, self.target_mask_attr_name, dst.device)
         if src_sel is not None:
@@ -208,6 +224,9 @@ class KNNEdges(BaseEdgeBuilder, NodeMaskingMixin):
         self.num_nearest_neighbours = num_nearest_neighbours
         self.stats = None  # optional CUDA int64[4]: {float64-refined, tied at the k-th boundary, widened, 0}
 
+    # ties at the k-th boundary go to the lower SOURCE index: the sources need their final numbering
+    provisional_source_ok = False
+
     def compute_edge_index(self, source_nodes, target_nodes) -> torch.Tensor:
         src, dst, src_sel, dst_sel = self.get_node_coordinates(source_nodes, target_nodes)
         assert self.num_nearest_neighbours is not None, "number of neighbors required for knn encoder"
@@ -227,7 +246,7 @@ class KNNEdges(BaseEdgeBuilder, NodeMaskingMixin):
         if w > 1:
             counts = [(b - a) * k for a, b in (_device.shard_range(nq, r, w) for r in range(w))]
             out = _gather_blocks(out, counts, rank, src_sel is not None or dst_sel is not None)
-        return self.undo_masking(out, src_sel, dst_sel)
+        return _device.tag_rows(self.undo_masking(out, src_sel, dst_sel), *self._row_provs)
 
 
 class CutOffEdges(BaseEdgeBuilder, NodeMaskingMixin):
@@ -265,7 +284,10 @@ class CutOffEdges(BaseEdgeBuilder, NodeMaskingMixin):
         """Cut-off radius = reference distance of the TARGET nodes x cut-off factor (edges/builder.py:312-334)."""
         target_nodes = graph[self.target_name]
         mask = target_nodes[mask_attr] if mask_attr is not None else None
-        target_grid_reference_distance = get_grid_reference_distance(_device.node_state(target_nodes).x, mask)
+        # the reference distance does not depend on the numbering of the nodes
+        target_grid_reference_distance = get_grid_reference_distance(
+            _device.node_state(target_nodes, provisional_ok=True).x, mask
+        )
         radius = target_grid_reference_distance * self.cutoff_factor
         return radius
 
@@ -293,7 +315,7 @@ class CutOffEdges(BaseEdgeBuilder, NodeMaskingMixin):
             index.radius_fill(q, self.radius, offsets, total, out, sum(counts[:rank]), dst_base=lo, stats=self.stats)
         if w > 1:
             out = _gather_blocks(out, counts, rank, src_sel is not None or dst_sel is not None)
-        return self.undo_masking(out, src_sel, dst_sel)
+        return _device.tag_rows(self.undo_masking(out, src_sel, dst_sel), *self._row_provs)
 
 
 class MultiScaleEdges(BaseEdgeBuilder):
@@ -329,6 +351,7 @@ class MultiScaleEdges(BaseEdgeBuilder):
                 resolutions=source_nodes["_resolutions"],
                 x_hops=self.x_hops,
                 area_mask_builder=source_nodes.get("_area_mask_builder", None),
+                allow_provisional=self._provisional_ok,
             )
         if node_type == "StretchedTriNodes":
             from ..generate.masks import KNNAreaMaskBuilder

@@ -55,6 +55,30 @@ def _ordering_of(latlon_dev: torch.Tensor) -> torch.Tensor:
     return index_latitude[index_longitude.flip(0)]
 
 
+def _sort_columns_host(lat: np.ndarray, lon: np.ndarray):
+    """The host half of ``get_coordinates_ordering`` for a provisional node set (runs on the worker thread): the
+    reference's two numpy argsorts on contiguous float32 columns and the gather between them.  Same calls on the
+    same values as ``_ordering_of`` - the permutation is numpy's."""
+    index_latitude = np.argsort(lon)
+    index_longitude = np.argsort(lat[index_latitude])
+    return index_latitude, index_longitude
+
+
+def _combine_order(index_latitude: torch.Tensor, index_longitude: torch.Tensor) -> torch.Tensor:
+    """``arange(n)[index_latitude][index_longitude[::-1]]`` on the device."""
+    return index_latitude[index_longitude.flip(0)]
+
+
+def create_tri_nodes_provisional(resolution: int):
+    """Global mesh nodes whose order is computed on a host thread WHILE the edge kernels run
+    (``device.Provisional``): returns ``(mesh, provisional)``; ``mesh.order_dev`` is set when the order resolves."""
+    ico = get_icosphere(resolution)
+    mesh = DeviceMesh(ico, None)
+    prov = _device.Provisional(ico.latlon, _sort_columns_host, _combine_order)
+    prov.on_resolved = lambda p: setattr(mesh, "order_dev", p.order_dev)
+    return mesh, prov
+
+
 def create_tri_nodes(resolution: int, area_mask_builder=None):
     """Global (or area-limited) mesh nodes from a refined icosahedron (tri_icosahedron.py:24-58).
 
@@ -88,7 +112,9 @@ def create_stretched_tri_nodes(base_resolution: int, lam_resolution: int, area_m
     return DeviceMesh(lam, node_ordering), coords_rad, node_ordering
 
 
-def multiscale_edges(nodes, resolutions, x_hops: int = 1, area_mask_builder=None) -> torch.Tensor:
+def multiscale_edges(
+    nodes, resolutions, x_hops: int = 1, area_mask_builder=None, allow_provisional: bool = False
+) -> torch.Tensor:
     """Multi-scale connections of a tri-node set: CUDA int32 (2, E) sorted by (target, source).
 
     Replaces ``add_edges_to_nx_graph`` + ``nx.to_scipy_sparse_array`` (tri_icosahedron.py:138-224,
@@ -101,15 +127,23 @@ def multiscale_edges(nodes, resolutions, x_hops: int = 1, area_mask_builder=None
     ico = mesh.icosphere if isinstance(mesh, DeviceMesh) and mesh.icosphere is not None else None
     if ico is None or ico.max_level < max(resolutions):
         ico = get_icosphere(max(resolutions))
-    st = _device.node_state(nodes)
-    n_nodes = int(st.x.shape[0])
     node_type = nodes["node_type"]
+    st = _device.node_state(nodes, provisional_ok=(allow_provisional and node_type == "TriNodes" and area_mask_builder is None))
+    n_nodes = int(st.x.shape[0])
     if node_type == "TriNodes" and area_mask_builder is None and n_nodes == ops.ico_num_vertices(ico.max_level):
+        if st.prov is not None:
+            # the final order is not known yet: edges in the icosphere's own numbering, relabelled when it is
+            identity = torch.arange(n_nodes, dtype=torch.int32, device=st.x.device)
+            edges = ops.multiscale_tri_edges(ico, resolutions, x_hops, identity)
+            return _device.tag_rows(edges, st.prov, st.prov)
+        mesh = nodes.get("_nx_graph", None)
         if isinstance(mesh, DeviceMesh) and mesh.order_dev is not None:
             order = mesh.order_dev
         else:
             order = torch.as_tensor(np.asarray(nodes["_node_ordering"]))
         return ops.multiscale_tri_edges(ico, resolutions, x_hops, order)
+    if st.prov is not None:  # not reachable for the node types that defer their order; never mix numberings
+        st = _device.node_state(nodes)
     # limited-area / stretched: valid vertices by the area mask, vertex -> node by 1-NN
     nv = ops.ico_num_vertices(max(resolutions))
     coords = ico.latlon[:nv]

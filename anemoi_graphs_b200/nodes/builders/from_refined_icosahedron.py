@@ -20,6 +20,7 @@ from ...generate.hex_icosahedron import create_hex_nodes
 from ...generate.masks import KNNAreaMaskBuilder
 from ...generate.tri_icosahedron import create_stretched_tri_nodes
 from ...generate.tri_icosahedron import create_tri_nodes
+from ...generate.tri_icosahedron import create_tri_nodes_provisional
 from .base import BaseNodeBuilder
 
 LOGGER = logging.getLogger(__name__)
@@ -51,6 +52,18 @@ class IcosahedralNodes(BaseNodeBuilder, ABC):
 
     def get_coordinates(self) -> torch.Tensor:
         """float32 (num_nodes, 2) coordinates in radians, in graph order."""
+        self._provisional = None
+        if self.provisional_order and _device.deferring() and _device.LAZY_NODE_ORDER:
+            # inside a deferred scope (GraphCreator.update_graph): the order is sorted on a host thread while the
+            # edge kernels already run in the generator's numbering; x / _node_ordering are complete at flush
+            self.nx_graph, prov = self.create_nodes_provisional()
+            self._provisional = prov
+            self._x_device = prov.x_final
+            self.node_ordering = prov.order_host.numpy()
+            if _device.is_resident():
+                return prov.x_final
+            prov.x_host = torch.empty((prov.n, 2), dtype=torch.float32, pin_memory=True)
+            return prov.x_host
         self.nx_graph, coords_rad, order = self.create_nodes()
         # == torch.tensor(coords_rad[node_ordering], dtype=torch.float32), gathered (and, for the float64 hexagonal
         # centres, rounded) on the device
@@ -64,9 +77,16 @@ class IcosahedralNodes(BaseNodeBuilder, ABC):
         graph = super().register_nodes(graph)
         nodes = graph[self.name]
         # the device copy already exists: seed the per-node-set state so no builder uploads x again
-        _device.seed_node_state(nodes, self._x_device)
+        st = _device.seed_node_state(nodes, self._x_device)
+        if self._provisional is not None:
+            self._provisional.attach(nodes, st)
         _device.maybe_flush()
         return graph
+
+    provisional_order = False  # subclasses whose order is host-sorted and that can defer it set this
+
+    def create_nodes_provisional(self):
+        raise NotImplementedError
 
     @abstractmethod
     def create_nodes(self) -> tuple[object, torch.Tensor, torch.Tensor]: ...
@@ -95,8 +115,13 @@ class LimitedAreaIcosahedralNodes(IcosahedralNodes):
 class TriNodes(IcosahedralNodes):
     """Nodes based on iterative refinements of an icosahedron (triangular mesh)."""
 
+    provisional_order = True
+
     def create_nodes(self):
         return create_tri_nodes(resolution=max(self.resolutions))
+
+    def create_nodes_provisional(self):
+        return create_tri_nodes_provisional(resolution=max(self.resolutions))
 
 
 class HexNodes(IcosahedralNodes):

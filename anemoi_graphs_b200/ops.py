@@ -206,24 +206,40 @@ def haversine_rdist_host(lat1: float, lon1: float, lat2: float, lon2: float) -> 
     return s0 * s0 + math.cos(lat1) * math.cos(lat2) * s1 * s1
 
 
+REFDIST_K = 7  # self + 6: every neighbour that can tie for "nearest" on a degree-6 mesh or a regular grid
+REFDIST_MAX_CANDIDATES = 4096
+
+
 def grid_reference_distance(x: torch.Tensor) -> float:
     """``utils.get_grid_reference_distance`` (/root/reference/src/anemoi/graphs/utils.py:44-63): the largest
-    strictly positive distance in a k=2 self query.  The search, the float64 distances and the max run on
-    the GPU; the ONE winning pair is then re-evaluated with libm so the returned float64 carries the same
-    bits sklearn produces (it becomes the cut-off radius)."""
+    strictly positive nearest-neighbour distance of a node set (column 1 of a k = 2 self query).
+
+    The search and the float64 distances run on the GPU: a k = 7 self query, per node the smallest of its six
+    neighbour distances (the value of "column 1" whichever of several equidistant neighbours sklearn's heap keeps),
+    the maximum of those.  The nodes within rounding (1e-13 relative; CUDA's sin/cos differ from glibc's by <= 2 ulp)
+    of that maximum are then re-evaluated on the host with libm and the reference's exact-compare semantics
+    (``agx_host_reference_rdist``), so the returned float64 carries the bits sklearn produces (it becomes the
+    cut-off radius).  Nothing here depends on how the nodes are numbered."""
     xd = _dev_x(x)
     lib = load_library()
-    with NeighbourIndex(xd, hint_k=2) as index:
-        ei, rdist = index.knn(xd, 2, return_rdist=True, tag="knn_refdist")
-    value, flat = c_double(), c_int64()
-    check(lib.agx_max_positive(ptr(rdist), rdist.numel(), byref(value), byref(flat), current_stream()))
-    if flat.value < 0:
+    n = int(xd.shape[0])
+    k = min(REFDIST_K, n)
+    if k < 2:
         raise ValueError("zero-size array to reduction operation maximum which has no identity")
-    pair = torch.stack([ei[0, flat.value], ei[1, flat.value]]).cpu()
-    a = xd[pair[1].item()].cpu().tolist()  # query
-    b = xd[pair[0].item()].cpu().tolist()  # its neighbour
-    rd = haversine_rdist_host(a[0], a[1], b[0], b[1])
-    return 2.0 * math.asin(math.sqrt(rd))
+    with NeighbourIndex(xd, hint_k=k) as index:
+        ei, rdist = index.knn(xd, k, return_rdist=True, tag="knn_refdist")
+    nearest = rdist[:, 1:].min(dim=1).values  # 0 where a duplicate point exists (excluded like ``dists > 0``)
+    top = nearest.max()
+    cand = torch.nonzero((nearest >= top * (1.0 - 1.0e-13)) & (nearest > 0.0), as_tuple=False).squeeze(1)
+    cand = cand[:REFDIST_MAX_CANDIDATES]
+    if cand.numel() == 0:
+        raise ValueError("zero-size array to reduction operation maximum which has no identity")
+    nb = ei[0].view(n, k)[cand, 1:].long()
+    q_host = xd[cand].cpu().contiguous()
+    nb_host = xd[nb.reshape(-1)].cpu().contiguous()
+    value = c_double()
+    check(lib.agx_host_reference_rdist(q_host.data_ptr(), nb_host.data_ptr(), int(cand.numel()), k - 1, byref(value)))
+    return 2.0 * math.asin(math.sqrt(value.value))
 
 
 class NodeTables:

@@ -101,6 +101,13 @@ int agx_radius_fill(const agx_index_t* index, const float* q_latlon /*DEV*/, int
  * (agx_knn with out_rdist): largest strictly positive value and its flat position.            */
 int agx_max_positive(const double* values /*DEV n*/, int64_t n, double* out_value /*HOST*/,
                      int64_t* out_index /*HOST*/, void* stream);
+/* Host half of the same (NO device work, all pointers HOST): the nodes the GPU search nominates (those whose
+ * nearest-neighbour distance is within rounding of the largest) are re-evaluated with the C library's sin / cos -
+ * the calls sklearn's compiled HaversineDistance64 makes (_dist_metrics.pyx.tp:2639-2648) - so that the cut-off
+ * radius carries the reference's bits: out_rdist = max over candidates c of min over its n_nb neighbours of
+ * rdist(q[c], nb[c][j]) (exact compares; a zero minimum - duplicate points - is skipped like `dists > 0`).   */
+int agx_host_reference_rdist(const float* q_latlon /*HOST n_cand*2*/, const float* nb_latlon /*HOST n_cand*n_nb*2*/,
+                             int64_t n_cand, int n_nb, double* out_rdist /*HOST*/);
 
 /* ---- node pruning -------------------------------------------------------------------------------------
  * RemoveUnconnectedNodes (processors/post_process.py:45-60 update_edge_indices, :133-149 compute_mask):

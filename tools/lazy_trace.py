@@ -1,0 +1,27 @@
+"""Host timeline of the provisional node order inside one bench step (run on the GPU box)."""
+import sys, time, pathlib
+sys.path.insert(0, str(pathlib.Path(__file__).resolve().parents[1]))
+import torch
+import bench
+from anemoi_graphs_b200 import device as agx_device
+from anemoi_graphs_b200.create import GraphCreator
+
+grid, res = bench.WORKLOADS["o1280_res7"]
+x_host = bench.data_coordinates(grid).pin_memory()
+x_dev = x_host.cuda()
+creator = GraphCreator(bench.recipe(res))
+for resident in (True, False):
+    agx_device.set_resident(resident)
+    x = x_dev if resident else x_host
+    for rep in range(6):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        g = bench.run_step(creator, x)
+        t1 = time.perf_counter()
+        torch.cuda.synchronize()
+        t2 = time.perf_counter()
+        tr = agx_device.last_trace
+        if rep >= 3:
+            print(f"resident={resident} step: returned {1e3*(t1-t0):.2f} ms, synced {1e3*(t2-t0):.2f} ms | " +
+                  "  ".join(f"{k}={1e3*(v-t0):.2f}" for k, v in tr.items()))
+        g = None
