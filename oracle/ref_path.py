@@ -14,7 +14,7 @@ Parity status: PINNED against the unmodified reference executed in the build con
 (``oracle/make_golden.py`` -> ``tests/golden/*.npz``; checked by ``tests/test_oracle_golden.py``)
 and against the reference's published counts (docs/_static/hetero_data_graph.txt:13,19,25;
 docs/graphs/edges/tri_refined_edges.csv; tests/nodes/test_tri_nodes.py:32).
-HexNodes (h3) has no oracle in this image.
+HexNodes: the h3 library is absent; ``oracle/h3_restated.py`` restates its geometry (parity with h3 itself unpinned).
 
 Citations are relative to /root/reference/src/anemoi/graphs/.
 """
