@@ -70,6 +70,10 @@ SIGNATURES = {
         [c_int, c_void_p, POINTER(c_int32), c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     ),
     "agx_multiscale_tri_fill": (c_int, [c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "agx_voronoi_areas": (
+        c_int,
+        [c_void_p, c_int64, c_void_p, c_int, c_int, c_void_p, c_int64, c_double, c_void_p, c_void_p, c_void_p],
+    ),
     "agx_hex_num_cells": (c_int64, [c_int]),
     "agx_hex_cells": (c_int, [c_int, c_void_p, c_void_p, c_void_p]),
     "agx_hex_adjacency": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),

@@ -614,8 +614,58 @@ def multiscale_adj_edges(levels: list[tuple], x_hops: int, walk_all: bool, n_nod
     return out
 
 
+# ----------------------------------------------------------------------------------------------
+# spherical Voronoi cell areas
+# ----------------------------------------------------------------------------------------------
+VORONOI_K = (17, 33, 64)  # neighbours tried in turn (self included): a regular grid's cells close within the first 16
+
+
+def voronoi_areas(x: torch.Tensor, radius: float = 1.0) -> torch.Tensor:
+    """float64 (n,) areas of the spherical Voronoi cells of a node set - ``SphericalVoronoi(points, radius)
+    .calculate_areas()`` of nodes/attributes.py:199-221 - on the device.  Generators whose cell is not closed by
+    their 16 nearest neighbours are retried with 32, then 63."""
+    xd = _dev_x(x)
+    n = int(xd.shape[0])
+    lib = load_library()
+    if n < 4:
+        raise ValueError("SphericalVoronoi needs at least 4 generators")
+    areas = torch.zeros(n, dtype=torch.float64, device=xd.device)
+    subset = None  # None = all generators
+    stream = current_stream()
+    with NeighbourIndex(xd, hint_k=VORONOI_K[0]) as index:
+        for k in VORONOI_K:
+            k = min(k, n)
+            q = xd if subset is None else xd[subset.long()]
+            m = int(q.shape[0])
+            knn = index.knn(q, k, tag="knn_voronoi")[0]
+            status = torch.empty(m, dtype=torch.int32, device=xd.device)
+            with _span("voronoi_areas", m):
+                check(
+                    lib.agx_voronoi_areas(
+                        ptr(xd), n, knn.data_ptr(), k, int(k == n), ptr(subset), m, float(radius), ptr(areas),
+                        ptr(status), stream,
+                    )
+                )
+            worst = int(status.max().item())
+            if worst == 0:
+                return areas
+            if worst == 3:
+                raise ValueError("Duplicate generators present.")  # scipy's message
+            if worst == 4:
+                raise NotImplementedError("a Voronoi cell with more than 32 edges is not built")
+            retry = torch.nonzero(status > 0, as_tuple=False).squeeze(1).to(torch.int32)
+            subset = retry if subset is None else subset[retry.long()]
+            if k == n:
+                break
+    raise NotImplementedError(
+        f"{int(subset.numel())} Voronoi cells are not closed by their {VORONOI_K[-1] - 1} nearest neighbours "
+        "(fewer than ~8 generators per hemisphere, or an extremely anisotropic point set)"
+    )
+
+
 __all__ = [
     "multiscale_tri_edges_mapped",
+    "voronoi_areas",
     "HexCells",
     "hex_num_cells",
     "multiscale_adj_edges",

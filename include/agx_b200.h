@@ -211,6 +211,19 @@ int agx_multiscale_adj_count(int n_levels, const int32_t* const* nb /*HOST[n_lev
                              const int32_t* const* node_cell, int x_hops, int walk_all, int64_t n_nodes,
                              int32_t* counts /*DEV n_nodes*/, int32_t* scratch /*DEV*/, void* stream);
 
+/* ---- node attribute: spherical Voronoi cell areas -------------------------------
+ * Replaces `SphericalVoronoi(points, radius, centre).calculate_areas()` in SphericalAreaWeights.get_raw_values
+ * (nodes/attributes.py:199-221), points = latlon_rad_to_cartesian(x) in float32 (generate/transforms.py:106-110).
+ * The region of generator p is { x : x.(q - p) <= 0 for all q } with the float32 generators as given (scipy's hull
+ * facets); knn = row 0 of an agx_knn self query of the m listed generators (`subset`, NULL = all n, in order), k
+ * entries each (self included), ascending; exhaustive = 1 states that the lists hold EVERY generator (k = n), so a cell
+ * is complete when they are used up.  areas[i] (float64, indexed by generator) is written for every generator
+ * whose cell closed; status[t] (indexed by list position) = 0 done, 1 / 2 = the k neighbours did not close the cell
+ * (retry that generator with a larger k), 3 = duplicate generators, 4 = more than 32 cell edges.              */
+int agx_voronoi_areas(const float* latlon /*DEV n*2*/, int64_t n, const int32_t* knn /*DEV m*k*/, int k, int exhaustive,
+                      const int32_t* subset /*DEV m or NULL*/, int64_t m, double radius, double* areas /*DEV n*/,
+                      int32_t* status /*DEV m*/, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -21,6 +21,8 @@ product code is on that path, only ``anemoi_graphs_b200.grids`` for the syntheti
                      LimitedAreaTriNodes / StretchedTriNodes coordinates, multi-scale edges (x_hops 1, 2),
                      masked KNN and cut-off edges.
 * ``attr_vectors.npz`` SURVEY appendix-B style edge cases for EdgeLength / EdgeDirection.
+* ``area_weights.npz`` SphericalAreaWeights of the reference (scipy SphericalVoronoi) on an O24 grid, TriNodes(3)
+                     and 3 000 random points, raw and for every norm.
 """
 
 from __future__ import annotations
@@ -298,10 +300,36 @@ def make_attr_vectors() -> None:
     print("attr_vectors.npz", rot.dtype, length.dtype)
 
 
+def make_area_weights() -> None:
+    from anemoi.graphs.nodes.attributes import SphericalAreaWeights, UniformWeights
+    from torch_geometric.data import HeteroData
+
+    rng = np.random.default_rng(7)
+    lat, lon = grids.octahedral_grid(24)
+    sets = {
+        "o24": grids.latlon_deg_to_x(lat, lon).numpy(),
+        "random": np.stack([np.arcsin(rng.uniform(-1, 1, 3000)), rng.uniform(0, 2 * np.pi, 3000)], 1).astype(np.float32),
+    }
+    g = build({"hidden": tri_nodes(3)}, [])
+    sets["tri3"] = g["hidden"].x.numpy()
+    out = {}
+    for name, x in sets.items():
+        graph = HeteroData()
+        graph["n"].x = torch.from_numpy(x)
+        graph["n"].node_type = "LatLonNodes"
+        out[f"{name}_x"] = x
+        out[f"{name}_raw64"] = SphericalAreaWeights(norm=None, dtype="float64").compute(graph, "n").numpy()
+        for norm in NORMS:
+            out[f"{name}_{norm}"] = SphericalAreaWeights(norm=norm).compute(graph, "n").numpy()
+        out[f"{name}_uniform"] = UniformWeights(norm="l1").compute(graph, "n").numpy()
+    np.savez_compressed(OUT / "area_weights.npz", **out)
+    print("area_weights.npz", {k: v.shape for k, v in out.items() if k.endswith("_raw64")})
+
+
 if __name__ == "__main__":
     OUT.mkdir(parents=True, exist_ok=True)
     only = sys.argv[1:]
     for name, fn in (("attr_vectors", make_attr_vectors), ("tri", make_tri), ("toy", make_toy), ("o96", make_o96),
-                     ("lam", make_lam)):  # fmt: skip
+                     ("lam", make_lam), ("area_weights", make_area_weights)):  # fmt: skip
         if not only or name in only:
             fn()

@@ -430,3 +430,21 @@ def edge_direction(source_x, target_x, edge_index, norm: str | None = None, rota
 def concat_edges(e1: np.ndarray, e2: np.ndarray) -> np.ndarray:
     """utils.concat_edges: ``torch.unique(cat, dim=1)`` = columns sorted lexicographically, de-duplicated."""
     return np.unique(np.concatenate([e1, e2], axis=1), axis=1)
+
+
+# ----------------------------------------------------------------------------------------
+# SphericalAreaWeights                                  nodes/attributes.py:165-221, 44-52
+# ----------------------------------------------------------------------------------------
+def spherical_area_weights(x: np.ndarray, norm: str | None = None, dtype: str = "float32") -> np.ndarray:
+    """The reference's ``SphericalAreaWeights(norm, dtype=dtype).compute``: (N, 1)."""
+    from scipy.spatial import SphericalVoronoi
+
+    latitudes, longitudes = np.asarray(x[:, 0]), np.asarray(x[:, 1])
+    points = latlon_rad_to_cartesian((latitudes, longitudes))  # float32 in, float32 out
+    sv = SphericalVoronoi(points, 1.0, np.array([0, 0, 0]))
+    mask = np.array([bool(i) for i in sv.regions])
+    sv.regions = [region for region in sv.regions if region]
+    area_weights = sv.calculate_areas()
+    result = np.ones(points.shape[0]) * 0.0
+    result[mask] = area_weights
+    return normalise(result[:, np.newaxis], norm).astype(dtype)

@@ -171,3 +171,15 @@ def test_lam_and_stretched_match_reference(golden):
     np.testing.assert_array_equal(R.knn_edges(str_x, dx, 4), g["str_knn4_edge_index"])
     np.testing.assert_array_equal(R.cutoff_edges(dx, str_x, 0.6), g["str_cutoff_edge_index"])
     assert R.grid_reference_distance(str_x) == float(g["str_reference_distance"])
+
+
+def test_oracle_area_weights_match_reference(golden):
+    """SphericalAreaWeights: the oracle's scipy call against the unmodified reference class, every norm."""
+    g = golden("area_weights")
+    for name in ("o24", "tri3", "random"):
+        x = g[f"{name}_x"]
+        np.testing.assert_array_equal(R.spherical_area_weights(x, None, "float64"), g[f"{name}_raw64"])
+        for norm in [None, "l1", "l2", "unit-max", "unit-range", "unit-std"]:
+            np.testing.assert_array_equal(R.spherical_area_weights(x, norm), g[f"{name}_{norm}"])
+        # the areas tile the sphere (up to the float32 rounding of the generators)
+        np.testing.assert_allclose(g[f"{name}_raw64"].sum(), 4 * np.pi, rtol=1e-7)
