@@ -119,11 +119,13 @@ class _EdgeStorage(_Storage):
         return int(ei.shape[1]) if ei is not None else 0
 
     def edge_attrs(self) -> list[str]:
+        """Tensor attributes with one entry per edge - ``edge_index`` included, as in torch_geometric (the reference
+        removes it by name, describe.py:92)."""
         e = self.num_edges
         return [
             k
             for k, v in self._mapping.items()
-            if isinstance(v, torch.Tensor) and k != "edge_index" and v.dim() > 0 and v.shape[0] == e
+            if isinstance(v, torch.Tensor) and v.dim() > 0 and v.shape[-1 if k == "edge_index" else 0] == e
         ]
 
 

@@ -154,3 +154,35 @@ def test_node_ordering_equals_reference_expression():
         np.testing.assert_array_equal(
             get_coordinates_ordering(lat=np.ascontiguousarray(coords[:, 0]), lon=np.ascontiguousarray(coords[:, 1])), want
         )
+
+
+def test_graph_descriptor_on_a_saved_graph(tmp_path, capsys):
+    """describe.py:20-225 - sizes, isolated-node counts and attribute statistics of a saved graph."""
+    from anemoi_graphs_b200.describe import GraphDescriptor
+    from anemoi_graphs_b200.graph import HeteroData
+
+    g = HeteroData()
+    g["a"].x = torch.tensor([[0.1, 0.2], [0.3, 6.0], [-0.5, 3.0]], dtype=torch.float32)
+    g["a"].node_type = "LatLonNodes"
+    g["a"]["w"] = torch.tensor([[1.0], [2.0], [3.0]])
+    g["b"].x = torch.tensor([[0.0, 0.0], [1.0, 1.0]], dtype=torch.float32)
+    g["b"].node_type = "LatLonNodes"
+    store = g[("a", "to", "b")]
+    store.edge_index = torch.tensor([[0, 0, 2], [1, 1, 1]], dtype=torch.int32)
+    store.edge_type = "KNNEdges"
+    store["edge_length"] = torch.tensor([[1.0], [2.0], [4.0]])
+    path = tmp_path / "graph.pt"
+    torch.save(g, path)
+    d = GraphDescriptor(path)
+    assert d.total_size == (6 + 3 + 4) * 4 + 6 * 4 + 3 * 4
+    nodes = {row[0]: row for row in d.get_node_summary()}
+    assert nodes["a"][1] == 3 and nodes["a"][2] == "w" and nodes["a"][3] == 1
+    np.testing.assert_allclose(nodes["a"][4:], np.rad2deg([-0.5, 0.3, 0.2, 6.0]), rtol=1e-6)
+    (edges,) = d.get_edge_summary()
+    assert edges[:6] == ["a", "b", 3, 1, 1, 1] and edges[6] == "edge_length(1D)"
+    table = d.get_attribute_table()
+    assert [r[:3] for r in table] == [["Node", "a", "w"], ["Edge", "a-->b", "edge_length"]]
+    np.testing.assert_allclose(table[1][4:], [1.0, 7.0 / 3.0, 4.0, np.std([1.0, 2.0, 4.0], ddof=1)], rtol=1e-6)
+    d.describe()
+    out = capsys.readouterr().out
+    assert "Nodes summary" in out and "Edges summary" in out and "Graph ready." in out
