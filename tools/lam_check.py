@@ -4,6 +4,7 @@ restricted to the patch (`source_mask_attr_name`), multi-scale processor.  Non-u
 (SURVEY.md H5): stage times are printed and samples of every edge set are checked against the oracle.
 
     python tools/lam_check.py [--patch 1000] [--global-res 5] [--lam-res 10] [--k 16]
+    python tools/lam_check.py --hidden hex --hex-res 5     # the same data nodes under a global H3 hidden mesh
 """
 import argparse
 import pathlib
@@ -18,7 +19,7 @@ from anemoi_graphs_b200 import device as agx_device
 from anemoi_graphs_b200 import grids
 from anemoi_graphs_b200.edges import CutOffEdges, KNNEdges, MultiScaleEdges
 from anemoi_graphs_b200.graph import HeteroData
-from anemoi_graphs_b200.nodes import StretchedTriNodes
+from anemoi_graphs_b200.nodes import HexNodes, StretchedTriNodes
 from oracle import ref_path as R
 
 
@@ -29,6 +30,8 @@ def main():
     ap.add_argument("--lam-res", type=int, default=10)
     ap.add_argument("--k", type=int, default=16)
     ap.add_argument("--cutoff", type=float, default=0.6)
+    ap.add_argument("--hidden", choices=["tri", "hex"], default="tri")
+    ap.add_argument("--hex-res", type=int, default=5)
     args = ap.parse_args()
     lam_lat, lam_lon = grids.lam_patch(args.patch, args.patch, 2.5)
     g_lat, g_lon = grids.octahedral_grid(96)
@@ -52,7 +55,10 @@ def main():
             marks.append((name, time.perf_counter()))
 
         mark("start")
-        graph = StretchedTriNodes(args.global_res, args.lam_res, "hidden", "data", "cutout", margin_radius_km=100.0).update_graph(graph, {})
+        if args.hidden == "hex":
+            graph = HexNodes(args.hex_res, "hidden").update_graph(graph, {})
+        else:
+            graph = StretchedTriNodes(args.global_res, args.lam_res, "hidden", "data", "cutout", margin_radius_km=100.0).update_graph(graph, {})
         mark("hidden nodes")
         MultiScaleEdges("hidden", "hidden", 1).update_graph(graph, attrs)
         mark("multiscale + attrs")
@@ -66,6 +72,12 @@ def main():
               f"{graph['hidden', 'to', 'data'].edge_index.shape[1]}/{graph['data', 'to', 'hidden'].edge_index.shape[1]}  {line}", flush=True)  # fmt: skip
     # ---- oracle samples -------------------------------------------------------------------------------------
     dx, hx = x.numpy(), graph["hidden"].x.cpu().numpy()
+    if args.hidden == "hex":
+        ms = graph["hidden", "to", "hidden"].edge_index.cpu().numpy().astype(np.int64)
+        want_n = sum(6 * (2 + 120 * 7**r) - 12 for r in range(args.hex_res + 1))
+        fwd, bwd = np.sort(ms[0] * hx.shape[0] + ms[1]), np.sort(ms[1] * hx.shape[0] + ms[0])
+        ok = ms.shape[1] == want_n and np.array_equal(fwd, bwd) and np.unique(fwd).size == fwd.size
+        print("hex multiscale:", "OK" if ok else "MISMATCH", f"({ms.shape[1]} edges, H3 levels 0..{args.hex_res}: {want_n})")
     rng = np.random.default_rng(0)
     # KNN: a sample of data queries (half from the patch, half global)
     qs = np.sort(np.concatenate([rng.choice(lam_lat.size, 4000, replace=False), lam_lat.size + rng.choice(g_lat.size, 4000, replace=False)]))
