@@ -438,6 +438,25 @@ def world() -> tuple[int, int]:
     return 0, 1
 
 
+# A multi-GPU build shards a neighbour search over its QUERY nodes only when there are at least this many of them:
+# every rank needs the complete result, so a sharded edge set is all-gathered (20 bytes per edge to every rank, a
+# handful of collective launches), which costs more than it saves while one GPU does the whole search in well under
+# a millisecond.  Below the threshold every rank computes the (identical) full edge set.  Measured on O1280 -> res 7
+# (6.6 M queries, 0.44 ms on one B200) at N = 2: searches and attributes sharded 6.4 ms/step and 22.2 ms host-to-host
+# (the device->host copies queue behind the all-gathers), everything replicated 6.3 / 14.0 ms = the single-GPU
+# numbers.  AGX_SHARD_MIN_QUERIES=0 AGX_ATTR_SHARD_MIN_EDGES=0 force sharding (tools/dist_check.py, tools/sweep.py).
+SHARD_MIN_QUERIES = int(float(__import__("os").environ.get("AGX_SHARD_MIN_QUERIES", "16e6")))
+
+
+def shard_world(n_queries: int) -> tuple[int, int]:
+    """``world()`` for a search over ``n_queries`` query nodes: (0, 1) - every rank does all of it - when the set is
+    too small for sharding to pay."""
+    rank, w = world()
+    if w > 1 and n_queries < SHARD_MIN_QUERIES:
+        return 0, 1
+    return rank, w
+
+
 def shard_range(n: int, rank: int | None = None, world_size: int | None = None) -> tuple[int, int]:
     """Contiguous range of ``n`` units owned by ``rank``: ``[rank*n//W, (rank+1)*n//W)``."""
     if rank is None or world_size is None:

@@ -238,7 +238,7 @@ class KNNEdges(BaseEdgeBuilder, NodeMaskingMixin):
         )
         k = self.num_nearest_neighbours
         nq = int(dst.shape[0])
-        rank, w = _device.world()
+        rank, w = _device.shard_world(nq)
         lo, hi = _device.shard_range(nq, rank, w)
         with ops.NeighbourIndex(src, hint_k=k) as index:
             out = torch.empty((2, nq * k), dtype=torch.int32, device=dst.device)
@@ -305,7 +305,7 @@ class CutOffEdges(BaseEdgeBuilder, NodeMaskingMixin):
             self.target_name,
         )
         nq = int(dst.shape[0])
-        rank, w = _device.world()
+        rank, w = _device.shard_world(nq)
         lo, hi = _device.shard_range(nq, rank, w)
         with ops.NeighbourIndex(src, hint_radius=self.radius) as index:
             q = dst[lo:hi]

@@ -310,8 +310,10 @@ def _attr_workspace(device) -> torch.Tensor:
 
 
 # below this many edges a multi-GPU build evaluates the attributes on every rank instead of sharding them: the
-# statistics exchange and the two gathers cost more than the kernel (1.3 M multi-scale edges: 0.13 ms replicated)
-ATTR_SHARD_MIN_EDGES = 4_000_000
+# statistics exchange and the two all-gathers (12 bytes per edge to every rank) cost more than the kernel, and the
+# device->host copies of a host-resident graph queue behind them (O1280 decoder, 19.8 M edges, N = 2: 22.2 ms
+# host-to-host sharded vs 14.0 ms replicated).  AGX_ATTR_SHARD_MIN_EDGES overrides.
+ATTR_SHARD_MIN_EDGES = int(float(__import__("os").environ.get("AGX_ATTR_SHARD_MIN_EDGES", "64e6")))
 
 
 def edge_attributes(

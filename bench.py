@@ -173,6 +173,20 @@ def output_bytes(graph) -> int:
     return n
 
 
+def sharding_note(world: int, n_queries: int) -> str:
+    from anemoi_graphs_b200 import device as agx_device
+
+    if world == 1:
+        return "single GPU"
+    if n_queries < agx_device.SHARD_MIN_QUERIES:
+        return (
+            f"{world} ranks, every rank builds the full graph: {n_queries} query nodes < AGX_SHARD_MIN_QUERIES = "
+            f"{agx_device.SHARD_MIN_QUERIES} (all-gathering a sharded build costs more than the search it saves; "
+            "DESIGN.md section 5)"
+        )
+    return f"query nodes over {world} rank(s), all-gather of edge blocks"
+
+
 def bench_b200(args) -> dict:
     import torch.distributed as dist
 
@@ -316,7 +330,7 @@ def bench_b200(args) -> dict:
             "hidden_nodes": n_hidden,
             "edges": {"cutoff": sizes[EDGE_KEYS[0]], "multiscale": sizes[EDGE_KEYS[1]], "knn": sizes[EDGE_KEYS[2]]},
             "cutoff_factor": CUTOFF_FACTOR, "knn_k": KNN_K, "x_hops": X_HOPS, "attribute_norm": NORM,
-            "sharding": f"query nodes over {world} rank(s), all-gather of edge blocks" if world > 1 else "single GPU",
+            "sharding": sharding_note(world, n_data),
             "l2": "inputs + outputs (~0.7 GB per step) exceed the 126 MB L2; no explicit flush",
         },
         "e2e": {

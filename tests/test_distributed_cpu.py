@@ -25,6 +25,9 @@ def _worker(rank: int, world: int, port: int, out_dir: str) -> None:
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         assert agx_device.world() == (rank, world)
+        # a search is sharded only from SHARD_MIN_QUERIES query nodes; below it every rank does all of it
+        assert agx_device.shard_world(agx_device.SHARD_MIN_QUERIES) == (rank, world)
+        assert agx_device.shard_world(agx_device.SHARD_MIN_QUERIES - 1) == (0, 1) or agx_device.SHARD_MIN_QUERIES == 0
         # --- KNN-like fixed-size blocks: 11 queries x k=3 --------------------------------------------
         nq, k = 11, 3
         lo, hi = agx_device.shard_range(nq)

@@ -1,6 +1,8 @@
 """Multi-GPU parity: under torchrun, every rank builds the O96 -> res 5 graph (config 1) with sharded queries /
 edges and must end with EXACTLY the single-GPU result (golden fixtures of the unmodified reference)."""
 import os, sys, pathlib
+os.environ.setdefault("AGX_SHARD_MIN_QUERIES", "0")  # force the sharded paths: this graph is far below the thresholds
+os.environ.setdefault("AGX_ATTR_SHARD_MIN_EDGES", "0")
 sys.path.insert(0, str(pathlib.Path(__file__).resolve().parents[1]))
 import numpy as np
 import torch
