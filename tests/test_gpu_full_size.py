@@ -128,3 +128,54 @@ def test_o1280_attribute_samples_and_statistics(o1280_graph):
         big = np.abs(raw_dir) > 1e-3
         scale_dir = dr[pick].astype(np.float64)[big] / raw_dir[big]
         np.testing.assert_allclose(scale_dir, np.median(scale_dir), rtol=2e-6)
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE config 2: synthetic N320 reduced Gaussian grid -> TriNodes 6, the WHOLE graph against the oracle
+# ------------------------------------------------------------------------------------------------
+def test_n320_res6_whole_graph_vs_oracle():
+    from anemoi_graphs_b200.create import GraphCreator
+    from anemoi_graphs_b200.graph import HeteroData
+
+    lat, lon = grids.reduced_gaussian_grid(320)
+    x = grids.latlon_deg_to_x(lat, lon)
+    attrs = {
+        "edge_length": {"_target_": T + "edges.attributes.EdgeLength", "norm": "unit-max"},
+        "edge_dirs": {"_target_": T + "edges.attributes.EdgeDirection", "norm": "unit-std"},
+    }
+    recipe = {
+        "nodes": {"hidden": {"node_builder": {"_target_": T + "nodes.TriNodes", "resolution": 6}}},
+        "edges": [
+            {"source_name": "data", "target_name": "hidden", "attributes": attrs,
+             "edge_builders": [{"_target_": T + "edges.CutOffEdges", "cutoff_factor": 0.6}]},
+            {"source_name": "hidden", "target_name": "hidden", "attributes": attrs,
+             "edge_builders": [{"_target_": T + "edges.MultiScaleEdges", "x_hops": 1}]},
+            {"source_name": "hidden", "target_name": "data", "attributes": attrs,
+             "edge_builders": [{"_target_": T + "edges.KNNEdges", "num_nearest_neighbours": 3}]},
+        ],
+    }  # fmt: skip
+    graph = HeteroData()
+    graph["data"].x = x
+    graph["data"].node_type = "LatLonNodes"
+    g = GraphCreator(recipe).update_graph(graph)
+    dx = x.numpy()
+    hx, order = R.tri_nodes(6)
+    assert hx.shape == (40962, 2)
+    np.testing.assert_array_equal(g["hidden"].x.numpy().view(np.int32), hx.view(np.int32))
+    canon = lambda key: R.canonical_sort(g[key].edge_index.numpy())  # noqa: E731
+    # encoder: every cut-off edge
+    np.testing.assert_array_equal(canon(("data", "to", "hidden")), R.canonical_sort(R.cutoff_edges(dx, hx, 0.6)))
+    # processor: docs/graphs/edges/tri_refined_edges.csv count and the exact set
+    ms = canon(("hidden", "to", "hidden"))
+    assert ms.shape[1] == sum(60 * 4**r for r in range(7)) == 327660
+    np.testing.assert_array_equal(ms, R.multiscale_edges_tri(range(7), 1, order))
+    # decoder: every KNN edge under the lower-index tie rule
+    want, info = R.knn_edges_canonical(hx, dx, 3)
+    assert info["untied_mismatch"].size == 0
+    np.testing.assert_array_equal(canon(("hidden", "to", "data")), want)
+    # attributes of the decoder edges, all of them
+    key = ("hidden", "to", "data")
+    ei = g[key].edge_index.numpy()
+    np.testing.assert_allclose(g[key]["edge_length"].numpy(), R.edge_length(hx, dx, ei, norm="unit-max"), rtol=1e-6, atol=0)
+    want_dir = R.edge_direction(hx, dx, ei, norm="unit-std")
+    np.testing.assert_allclose(g[key]["edge_dirs"].numpy(), want_dir, rtol=1e-6, atol=1e-6 * np.abs(want_dir).max())
