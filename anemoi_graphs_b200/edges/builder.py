@@ -242,7 +242,17 @@ class KNNEdges(BaseEdgeBuilder, NodeMaskingMixin):
         lo, hi = _device.shard_range(nq, rank, w)
         with ops.NeighbourIndex(src, hint_k=k) as index:
             out = torch.empty((2, nq * k), dtype=torch.int32, device=dst.device)
-            index.knn(dst[lo:hi], k, dst_base=lo, stats=self.stats, out=out, out_offset=lo * k)
+            if w > 1 and _device.peer_push_available():
+                # sharded: search the rank's range in chunks and push each finished chunk into every peer's buffer
+                # while the next one is searched (device.PeerPush) - no all-gather afterwards
+                push = _device.PeerPush(out)
+                for a, b in _device.query_chunks(lo, hi):
+                    index.knn(dst[a:b], k, dst_base=a, stats=self.stats, out=out, out_offset=a * k)
+                    push.push(a * k, b * k)
+                push.finish()
+                w = 1  # complete on every rank
+            else:
+                index.knn(dst[lo:hi], k, dst_base=lo, stats=self.stats, out=out, out_offset=lo * k)
         if w > 1:
             counts = [(b - a) * k for a, b in (_device.shard_range(nq, r, w) for r in range(w))]
             out = _gather_blocks(out, counts, rank, src_sel is not None or dst_sel is not None)
@@ -312,7 +322,20 @@ class CutOffEdges(BaseEdgeBuilder, NodeMaskingMixin):
             offsets, total = index.radius_count(q, self.radius)
             counts = _device.all_gather_counts(total, dst.device) if w > 1 else [total]
             out = torch.empty((2, sum(counts)), dtype=torch.int32, device=dst.device)
-            index.radius_fill(q, self.radius, offsets, total, out, sum(counts[:rank]), dst_base=lo, stats=self.stats)
+            base = sum(counts[:rank])
+            if w > 1 and _device.peer_push_available():
+                push = _device.PeerPush(out)
+                chunks = _device.query_chunks(0, hi - lo)
+                bounds = offsets[[a for a, _ in chunks] + [hi - lo]].tolist()  # pair offsets at the chunk boundaries
+                for (a, b), o0, o1 in zip(chunks, bounds[:-1], bounds[1:]):
+                    # the offsets keep their block-relative values, so the chunk lands at its final columns
+                    index.radius_fill(q[a:b], self.radius, offsets[a : b + 1], o1 - o0, out, base, dst_base=lo + a,
+                                      stats=self.stats)  # fmt: skip
+                    push.push(base + o0, base + o1)
+                push.finish()
+                w = 1  # complete on every rank
+            else:
+                index.radius_fill(q, self.radius, offsets, total, out, base, dst_base=lo, stats=self.stats)
         if w > 1:
             out = _gather_blocks(out, counts, rank, src_sel is not None or dst_sel is not None)
         return _device.tag_rows(self.undo_masking(out, src_sel, dst_sel), *self._row_provs)
