@@ -551,10 +551,13 @@ class PeerPush:
     rank's own pushes and runs one tiny stream-ordered all-reduce: when it completes every rank has finished
     pushing, so every buffer is complete.
 
-    Status (round 1): correct (``tools/dist_check.py`` with AGX_PEER_PUSH=1) but NOT yet faster - 40 M-query KNN-3 at
-    N = 2: 22.6 ms against 4.5 ms with the NCCL all-gather after the search, cut-off 69.9 against 14.4 ms.  The output
-    tensor is a fresh allocation per build, so PyTorch's IPC layer re-opens (and closes) a gigabyte mapping on every
-    peer for every edge set; a persistent peer-mapped staging heap (mapped once) is the round-2 form.  Off by default."""
+    Status (round 1): correct (``tools/dist_check.py`` with AGX_PEER_PUSH=1) but NOT faster - 40 M-query KNN-3 at
+    N = 2: 22.6 ms against 4.5 ms with the NCCL all-gather after the search, cut-off 69.9 against 14.4 ms.
+    ``tools/ipc_probe.py`` shows why: a copy into a peer's buffer mapped through PyTorch's CUDA IPC tensor sharing
+    (cudaIpcOpenMemHandle + cudaMemcpyAsync) moves 26 GB/s on these boxes - it does not take the NVLink path - while
+    NCCL's all-gather moves the same gigabyte per rank in 2.3 ms; mapping the buffers also costs ~350 ms the first
+    time.  Reaching NVLink from our own kernels / copies needs the driver VMM route NCCL uses (cuMemCreate +
+    exported shareable handles); that is the round-2 form.  Off by default."""
 
     def __init__(self, full: torch.Tensor) -> None:
         import torch.distributed as dist
