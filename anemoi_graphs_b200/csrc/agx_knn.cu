@@ -176,6 +176,8 @@ struct KnnArgs {
     int64_t dst_base;
     double* out_rdist;
     unsigned long long* stats;
+    uint8_t* tie_flags;  // optional: 1 for every query whose k-th boundary is a tie (the result depends on the index order)
+    int only_flagged;    // 1: tie_flags is an INPUT - only queries whose flag is set are searched and written
 };
 
 __device__ __forceinline__ float chord2(float3 q, float4 c) {
@@ -271,9 +273,13 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn(KnnArgs a) {
     const int64_t warps_total = (int64_t)gridDim.x * KNN_WARPS;
     for (int64_t tile = (int64_t)blockIdx.x * KNN_WARPS + warp; tile < n_tiles; tile += warps_total) {
         const int64_t slot = tile * 32 + lane;
-        const bool active = slot < a.nq;
+        bool active = slot < a.nq;
         const int64_t qs = active ? slot : a.nq - 1;
         const int64_t q = a.qperm ? (int64_t)__ldg(a.qperm + qs) : qs;  // binned order, results at the query's own place
+        if (a.only_flagged) {  // re-decision pass: whole tiles without a flagged query cost one byte per lane
+            active = active && a.tie_flags[q] != 0;
+            if (!__any_sync(0xffffffffu, active)) continue;
+        }
         const float2 ql = a.q_latlon[q];
         const float3 qv = agx_search_xyz(ql);
         const float t2 = a.chord2_init;
@@ -403,10 +409,14 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn(KnnArgs a) {
                         os[s] = fin.id[s];
                         if (a.out_rdist) a.out_rdist[q * k + s] = fin.r[s];
                     }
-                if (a.stats) {
-                    atomicAdd(a.stats + 0, 1ull);
+                if (a.stats || a.tie_flags) {
                     double rk = fin.r_at(k - 1), rn = fin.r_at(k);
-                    if (fin.id_at(k) != 0x7fffffff && fabs(rn - rk) <= AGX_TIE_TAU * fmax(rn, rk)) atomicAdd(a.stats + 1, 1ull);
+                    bool tie = fin.id_at(k) != 0x7fffffff && fabs(rn - rk) <= AGX_TIE_TAU * fmax(rn, rk);
+                    if (a.stats) {
+                        atomicAdd(a.stats + 0, 1ull);
+                        if (tie) atomicAdd(a.stats + 1, 1ull);
+                    }
+                    if (a.tie_flags && tie && !a.only_flagged) a.tie_flags[q] = 1;
                 }
             }
             if (a.out_dst) {
@@ -428,8 +438,30 @@ static void launch_knn(const KnnArgs& a, cudaStream_t stream) {
     k_knn<CAP><<<grid, KNN_WARPS * 32, 0, stream>>>(a);
 }
 
+int agx_knn_ex(const agx_index_t* ix, const float* q_latlon, int64_t nq, int k, double max_radius, int32_t* out_src,
+               int32_t* out_dst, int64_t dst_base, double* out_rdist, int64_t* stats, uint8_t* tie_flags, int only_flagged,
+               void* stream_);
+
 extern "C" int agx_knn(const agx_index_t* ix, const float* q_latlon, int64_t nq, int k, double max_radius, int32_t* out_src,
                        int32_t* out_dst, int64_t dst_base, double* out_rdist, int64_t* stats, void* stream_) {
+    return agx_knn_flagged(ix, q_latlon, nq, k, max_radius, out_src, out_dst, dst_base, out_rdist, stats, nullptr, stream_);
+}
+
+extern "C" int agx_knn_flagged(const agx_index_t* ix, const float* q_latlon, int64_t nq, int k, double max_radius,
+                               int32_t* out_src, int32_t* out_dst, int64_t dst_base, double* out_rdist, int64_t* stats,
+                               uint8_t* tie_flags, void* stream_) {
+    return agx_knn_ex(ix, q_latlon, nq, k, max_radius, out_src, out_dst, dst_base, out_rdist, stats, tie_flags, 0, stream_);
+}
+
+extern "C" int agx_knn_redecide(const agx_index_t* ix, const float* q_latlon, int64_t nq, int k, double max_radius,
+                                int32_t* out_src, const uint8_t* tie_flags, void* stream_) {
+    AGX_REQUIRE(tie_flags != nullptr, AGX_ERR_ARG, "agx_knn_redecide: tie_flags is NULL");
+    return agx_knn_ex(ix, q_latlon, nq, k, max_radius, out_src, nullptr, 0, nullptr, nullptr, (uint8_t*)tie_flags, 1, stream_);
+}
+
+int agx_knn_ex(const agx_index_t* ix, const float* q_latlon, int64_t nq, int k, double max_radius, int32_t* out_src,
+               int32_t* out_dst, int64_t dst_base, double* out_rdist, int64_t* stats, uint8_t* tie_flags, int only_flagged,
+               void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     AGX_REQUIRE(ix != nullptr, AGX_ERR_ARG, "agx_knn: NULL index");
     AGX_REQUIRE(nq >= 0, AGX_ERR_ARG, "agx_knn: nq < 0");
@@ -472,8 +504,10 @@ extern "C" int agx_knn(const agx_index_t* ix, const float* q_latlon, int64_t nq,
     a.dst_base = dst_base;
     a.out_rdist = out_rdist;
     a.stats = (unsigned long long*)stats;
+    a.tie_flags = tie_flags;
+    a.only_flagged = only_flagged;
     int32_t* perm = nullptr;
-    {
+    if (!only_flagged) {  // the re-decision pass touches a handful of queries: not worth sampling their order
         int rc = agx_query_order(ix, a.q_latlon, nq, a.chord2_init, "AGX_KNN_BIN", &perm, stream);
         if (rc != AGX_OK) return rc;
         a.qperm = perm;

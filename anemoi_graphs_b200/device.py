@@ -280,6 +280,7 @@ class Provisional:
         self.order_host = torch.empty(n, dtype=torch.int64, pin_memory=True)  # ``_node_ordering``
         self.order_dev = None
         self.rows: list = []
+        self.fixups: list = []
         self.nodes = None
         self.state = None
         self.on_resolved = None
@@ -298,6 +299,7 @@ class Provisional:
             copied.record(side)
         columns.record_stream(side)
         self.trace = {"created": time.perf_counter()}
+        parts_pinned = torch.empty((2, n), dtype=torch.int64, pin_memory=True)  # the worker's results, ready for H2D
 
         def work():
             self.trace["worker_start"] = time.perf_counter()
@@ -305,7 +307,12 @@ class Provisional:
             self.trace["coords_on_host"] = time.perf_counter()
             cols = staged.numpy()
             out = sorter(cols[0], cols[1])
+            out = out if isinstance(out, tuple) else (out,)
             self.trace["sorted"] = time.perf_counter()
+            if len(out) <= parts_pinned.shape[0]:  # hand the index arrays over in pinned memory
+                for i, part in enumerate(out):
+                    parts_pinned[i].numpy()[:] = part
+                return parts_pinned[: len(out)]
             return out
 
         self.future = _pool().submit(work)
@@ -321,6 +328,11 @@ class Provisional:
         (2, E) tensor whose row receives the final ones (None: the graph is device-resident)."""
         self.rows.append((tensor, row, host))
 
+    def add_fixup(self, fn) -> None:
+        """``fn(self)`` runs when the order resolves, after the registered rows carry final labels and before they are
+        copied to the host (KNN re-decides its index-order ties there)."""
+        self.fixups.append(fn)
+
     def resolve(self) -> None:
         if self.done:
             return
@@ -335,12 +347,14 @@ class Provisional:
         parts = self.future.result()  # numpy int64 index arrays
         self.trace["resolve_got_order"] = time.perf_counter()
         dev = self.x_prov.device
-        parts = parts if isinstance(parts, tuple) else (parts,)
-        staged = torch.empty((len(parts), self.n), dtype=torch.int64, pin_memory=True)
-        for i, part in enumerate(parts):
-            staged[i].numpy()[:] = part
+        if isinstance(parts, torch.Tensor):
+            staged = parts
+        else:
+            staged = torch.empty((len(parts), self.n), dtype=torch.int64, pin_memory=True)
+            for i, part in enumerate(parts):
+                staged[i].numpy()[:] = part
         parts_dev = staged.to(dev, non_blocking=True)
-        order_dev = self.combine(*[parts_dev[i] for i in range(len(parts))]).contiguous()
+        order_dev = self.combine(*[parts_dev[i] for i in range(int(parts_dev.shape[0]))]).contiguous()
         to_host_into(order_dev, self.order_host)  # ``_node_ordering``: complete at flush like every host copy
         rank = torch.empty(self.n + 1, dtype=torch.int64, device=dev)
         rank[order_dev] = torch.arange(self.n, dtype=torch.int64, device=dev)
@@ -350,6 +364,10 @@ class Provisional:
         for tensor, row, host in self.rows:
             wait_for(tensor)  # a sharded builder's all-gather may still be filling it
             check(lib.agx_relabel_nodes(tensor[row].data_ptr(), int(tensor.shape[1]), rank.data_ptr(), current_stream()))
+        fixups, self.fixups = self.fixups, []
+        for fn in fixups:
+            fn(self)
+        for tensor, row, host in self.rows:
             if host is not None:
                 to_host_into(tensor[row], host[row])
         self.rows = []

@@ -125,6 +125,9 @@ def compute_attributes(graph, edges_name: tuple[str, str, str], attrs: dict) -> 
     # A row of the edge list may still be in the provisional numbering of its node set (device.Provisional): the
     # attributes depend on coordinates only, so they are evaluated right away against the matching (provisional)
     # node records.  Anything else - final rows against a provisional node set - needs the final order first.
+    pending = getattr(edge_index, "_agx_fixup", None)
+    if pending is not None:  # KNN edges whose index-order ties are re-decided when the node order resolves
+        pending.resolve()
     tags = _device.row_tags(edge_index)
     for row, name in ((0, source_name), (1, target_name)):
         prov = _device.active_provisional(graph[name])

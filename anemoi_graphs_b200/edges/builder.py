@@ -224,8 +224,18 @@ class KNNEdges(BaseEdgeBuilder, NodeMaskingMixin):
         self.num_nearest_neighbours = num_nearest_neighbours
         self.stats = None  # optional CUDA int64[4]: {float64-refined, tied at the k-th boundary, widened, 0}
 
-    # ties at the k-th boundary go to the lower SOURCE index: the sources need their final numbering
-    provisional_source_ok = False
+    # Ties at the k-th boundary go to the lower SOURCE index, so the result depends on the final numbering of the
+    # sources - but only for the queries that have such a tie.  With provisionally numbered sources the search runs
+    # at once, flags those queries (agx_knn_flagged), and re-decides exactly them when the order is known
+    # (``_redecide_ties``); everything else is a relabel.
+    provisional_source_ok = True
+
+    @staticmethod
+    def _redecide_ties(prov, out: torch.Tensor, flags: torch.Tensor, queries: torch.Tensor, k: int) -> None:
+        """Runs inside ``Provisional.resolve``: row 0 of ``out`` already carries final source labels."""
+        with ops.NeighbourIndex(prov.x_final, hint_k=k) as index:
+            index.knn_redecide(queries, k, out, flags)
+        out._agx_fixup = None
 
     def compute_edge_index(self, source_nodes, target_nodes) -> torch.Tensor:
         src, dst, src_sel, dst_sel = self.get_node_coordinates(source_nodes, target_nodes)
@@ -239,6 +249,21 @@ class KNNEdges(BaseEdgeBuilder, NodeMaskingMixin):
         k = self.num_nearest_neighbours
         nq = int(dst.shape[0])
         rank, w = _device.shard_world(nq)
+        src_prov, dst_prov = self._row_provs
+        if src_prov is not None and (w > 1 or dst_prov is not None):
+            # flag-and-redecide is built for the plain case only (one rank, final target numbering): order first
+            src = _device.node_state(source_nodes).x
+            dst = _device.node_state(target_nodes).x
+            self._row_provs = (None, None)
+            src_prov = dst_prov = None
+        if src_prov is not None:
+            flags = torch.zeros(nq, dtype=torch.uint8, device=dst.device)
+            with ops.NeighbourIndex(src, hint_k=k) as index:
+                out = index.knn(dst, k, stats=self.stats, tie_flags=flags)
+            out = _device.tag_rows(out, src_prov, None)
+            out._agx_fixup = src_prov
+            src_prov.add_fixup(lambda prov, out=out, flags=flags, dst=dst, k=k: self._redecide_ties(prov, out, flags, dst, k))
+            return out
         lo, hi = _device.shard_range(nq, rank, w)
         with ops.NeighbourIndex(src, hint_k=k) as index:
             out = torch.empty((2, nq * k), dtype=torch.int32, device=dst.device)

@@ -121,12 +121,14 @@ class NeighbourIndex:
         out_offset: int = 0,
         tag: str = "knn",
         max_radius: float = 0.0,
+        tie_flags: torch.Tensor | None = None,
     ):
         """``edge_index`` (2, nq*k) int32 - row 0 the k nearest reference points of each query, row 1
         ``dst_base + query`` - and optionally the float64 ``rdist`` (nq, k).  With ``out`` (a larger
         contiguous (2, E) int32 buffer) the block is written at column ``out_offset`` instead.  ``max_radius``
         (radians, 0 = unlimited) bounds the search: exact for queries whose k-th neighbour is within it, otherwise
-        -1 / +inf or points beyond it (``agx_b200.h``)."""
+        -1 / +inf or points beyond it (``agx_b200.h``).  ``tie_flags`` (zeroed uint8 (nq,)) marks the queries whose result
+        depends on the numbering of the reference points (``agx_knn_flagged``)."""
         q = _dev_x(q)
         nq = int(q.shape[0])
         if out is None:
@@ -138,12 +140,23 @@ class NeighbourIndex:
         row = out.shape[1] * 4
         with _span(tag, nq * k):
             check(
-                self.lib.agx_knn(
+                self.lib.agx_knn_flagged(
                     self.handle, ptr(q), nq, int(k), float(max_radius), out.data_ptr() + 4 * out_offset,
-                    out.data_ptr() + row + 4 * out_offset, int(dst_base), ptr(rdist), ptr(stats), current_stream(),
+                    out.data_ptr() + row + 4 * out_offset, int(dst_base), ptr(rdist), ptr(stats), ptr(tie_flags),
+                    current_stream(),
                 )
             )  # fmt: skip
         return (out, rdist) if return_rdist else out
+
+    def knn_redecide(self, q: torch.Tensor, k: int, out: torch.Tensor, tie_flags: torch.Tensor) -> None:
+        """Search only the queries flagged in ``tie_flags`` and overwrite their sources in row 0 of ``out``
+        (``agx_knn_redecide``)."""
+        q = _dev_x(q)
+        nq = int(q.shape[0])
+        assert out.shape == (2, nq * k) and out.dtype == torch.int32 and out.is_contiguous()
+        assert tie_flags.shape == (nq,) and tie_flags.dtype == torch.uint8
+        with _span("knn_ties", nq):
+            check(self.lib.agx_knn_redecide(self.handle, ptr(q), nq, int(k), 0.0, out.data_ptr(), ptr(tie_flags), current_stream()))
 
     def radius_count(self, q: torch.Tensor, radius: float) -> tuple[torch.Tensor, int]:
         """Pass 1 of the cut-off search: ``(offsets (nq+1,) int64, total)``."""

@@ -82,6 +82,21 @@ int agx_knn(const agx_index_t* index, const float* q_latlon /*DEV nq*2*/, int64_
             int32_t* out_src /*DEV*/, int32_t* out_dst /*DEV or NULL*/, int64_t dst_base,
             double* out_rdist /*DEV or NULL*/, int64_t* stats /*DEV or NULL*/, void* stream);
 
+/* agx_knn with one more output: tie_flags[q] (DEV nq bytes, zeroed by the caller) is set to 1 for every query whose
+ * k-th and (k+1)-th candidates tie within 2^-40 relative - the only queries whose edge set depends on how the
+ * reference points are NUMBERED (lower index wins).  A caller that searches before the final numbering is known
+ * (device.Provisional: the node order is still being sorted on the host) re-runs exactly these queries afterwards. */
+int agx_knn_flagged(const agx_index_t* index, const float* q_latlon /*DEV nq*2*/, int64_t nq, int k, double max_radius,
+                    int32_t* out_src /*DEV*/, int32_t* out_dst /*DEV or NULL*/, int64_t dst_base,
+                    double* out_rdist /*DEV or NULL*/, int64_t* stats /*DEV or NULL*/, uint8_t* tie_flags /*DEV nq or NULL*/,
+                    void* stream);
+
+/* The second half: searches ONLY the queries whose tie_flags byte is set (against an index built over the finally
+ * numbered reference points) and overwrites their k slots of out_src; every other query is left untouched.  No
+ * compaction and no read-back: a tile of 32 queries without a flagged one costs 32 bytes of traffic.              */
+int agx_knn_redecide(const agx_index_t* index, const float* q_latlon /*DEV nq*2*/, int64_t nq, int k, double max_radius,
+                     int32_t* out_src /*DEV nq*k*/, const uint8_t* tie_flags /*DEV nq*/, void* stream);
+
 /* ---- cut-off (radius) search -------------------------------------------------------------------
  * Replaces `radius_neighbors_graph(target, radius)` (edges/builder.py:366): every reference point
  * with rdist <= sin^2(radius/2) (inclusive).  count -> scan -> fill; output grouped by query, in
