@@ -157,3 +157,22 @@ def test_area_weights_through_graph_creator():
     for name, norm in (("data", "unit-max"), ("hidden", "l1")):
         want = R.spherical_area_weights(graph[name].x.numpy(), norm)
         np.testing.assert_allclose(graph[name]["area_weight"].numpy(), want, rtol=ATTR_RTOL)
+
+
+def test_area_weights_too_few_generators():
+    from anemoi_graphs_b200 import ops
+
+    x = torch.tensor([[0.0, 0.0], [0.5, 1.0], [-0.5, 2.0]], dtype=torch.float32).cuda()
+    with pytest.raises(ValueError):
+        ops.voronoi_areas(x)
+
+
+def test_area_weights_random_cloud_needs_retries():
+    """A random cloud: a quarter of the cells are not closed by 16 neighbours and go through the k = 32 / 63 passes."""
+    from anemoi_graphs_b200 import ops
+
+    rng = np.random.default_rng(11)
+    x = np.stack([np.arcsin(rng.uniform(-1, 1, 20000)), rng.uniform(0, 2 * np.pi, 20000)], 1).astype(np.float32)
+    got = ops.voronoi_areas(torch.from_numpy(x).cuda()).cpu().numpy()
+    want = R.spherical_area_weights(x, None, "float64")[:, 0]
+    np.testing.assert_allclose(got, want, rtol=RAW_RTOL, atol=0)
