@@ -303,6 +303,33 @@ __global__ void __launch_bounds__(256) k_relabel_nodes(int32_t* __restrict__ row
         row[i] = (int32_t)new_index[row[i]];
 }
 
+// The device half of get_coordinates_ordering (generate/utils.py:30-33) once the host has produced its two argsorts:
+// order = arange(n)[index_latitude][index_longitude[::-1]], its inverse, and the re-ordered coordinates, in one pass.
+__global__ void __launch_bounds__(256) k_order_resolve(const int64_t* __restrict__ index_latitude,
+                                                       const int64_t* __restrict__ index_longitude, int64_t n,
+                                                       const float2* __restrict__ x_in, float2* __restrict__ x_out,
+                                                       int64_t* __restrict__ order, int64_t* __restrict__ rank) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t o = index_latitude[index_longitude[n - 1 - i]];
+        order[i] = o;
+        rank[o] = i;
+        x_out[i] = x_in[o];
+    }
+}
+
+extern "C" int agx_order_resolve(const int64_t* index_latitude, const int64_t* index_longitude, int64_t n,
+                                 const float* x_in, float* x_out, int64_t* order, int64_t* rank, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    AGX_REQUIRE(n >= 0, AGX_ERR_ARG, "agx_order_resolve: n < 0");
+    if (n == 0) return AGX_OK;
+    AGX_REQUIRE(index_latitude && index_longitude && x_in && x_out && order && rank, AGX_ERR_ARG, "agx_order_resolve: NULL buffer");
+    k_order_resolve<<<agx_grid(n, 256, 8), 256, 0, stream>>>(index_latitude, index_longitude, n, (const float2*)x_in,
+                                                             (float2*)x_out, order, rank);
+    AGX_LAUNCH_OK();
+    agx_note_launch(1);
+    return AGX_OK;
+}
+
 extern "C" int agx_mark_nodes(const int32_t* row, int64_t n, int64_t n_nodes, int32_t* flags, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     AGX_REQUIRE(n >= 0 && n_nodes >= 0, AGX_ERR_ARG, "agx_mark_nodes: negative size");

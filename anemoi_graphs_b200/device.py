@@ -354,13 +354,23 @@ class Provisional:
             for i, part in enumerate(parts):
                 staged[i].numpy()[:] = part
         parts_dev = staged.to(dev, non_blocking=True)
-        order_dev = self.combine(*[parts_dev[i] for i in range(int(parts_dev.shape[0]))]).contiguous()
-        to_host_into(order_dev, self.order_host)  # ``_node_ordering``: complete at flush like every host copy
-        rank = torch.empty(self.n + 1, dtype=torch.int64, device=dev)
-        rank[order_dev] = torch.arange(self.n, dtype=torch.int64, device=dev)
-        torch.index_select(self.x_prov, 0, order_dev, out=self.x_final)
-        self.order_dev = order_dev
         lib = load_library()
+        rank = torch.empty(self.n + 1, dtype=torch.int64, device=dev)
+        if self.combine == "latlon" and int(parts_dev.shape[0]) == 2:
+            # order, its inverse and the re-ordered coordinates in one kernel
+            order_dev = torch.empty(self.n, dtype=torch.int64, device=dev)
+            check(
+                lib.agx_order_resolve(
+                    parts_dev[0].data_ptr(), parts_dev[1].data_ptr(), self.n, self.x_prov.data_ptr(),
+                    self.x_final.data_ptr(), order_dev.data_ptr(), rank.data_ptr(), current_stream(),
+                )
+            )
+        else:
+            order_dev = self.combine(*[parts_dev[i] for i in range(int(parts_dev.shape[0]))]).contiguous()
+            rank[order_dev] = torch.arange(self.n, dtype=torch.int64, device=dev)
+            torch.index_select(self.x_prov, 0, order_dev, out=self.x_final)
+        to_host_into(order_dev, self.order_host)  # ``_node_ordering``: complete at flush like every host copy
+        self.order_dev = order_dev
         for tensor, row, host in self.rows:
             wait_for(tensor)  # a sharded builder's all-gather may still be filling it
             check(lib.agx_relabel_nodes(tensor[row].data_ptr(), int(tensor.shape[1]), rank.data_ptr(), current_stream()))

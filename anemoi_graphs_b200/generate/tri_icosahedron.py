@@ -74,7 +74,7 @@ def create_tri_nodes_provisional(resolution: int):
     (``device.Provisional``): returns ``(mesh, provisional)``; ``mesh.order_dev`` is set when the order resolves."""
     ico = get_icosphere(resolution)
     mesh = DeviceMesh(ico, None)
-    prov = _device.Provisional(ico.latlon, _sort_columns_host, _combine_order)
+    prov = _device.Provisional(ico.latlon, _sort_columns_host, "latlon")  # combined by agx_order_resolve
     prov.on_resolved = lambda p: setattr(mesh, "order_dev", p.order_dev)
     return mesh, prov
 

@@ -132,6 +132,15 @@ int agx_host_reference_rdist(const float* q_latlon /*HOST n_cand*2*/, const floa
 int agx_mark_nodes(const int32_t* row /*DEV n*/, int64_t n, int64_t n_nodes, int32_t* flags /*DEV n_nodes*/, void* stream);
 int agx_relabel_nodes(int32_t* row /*DEV n, in place*/, int64_t n, const int64_t* new_index /*DEV n_nodes+1*/, void* stream);
 
+/* ---- node ordering, device half ---------------------------------------------------------------------------
+ * get_coordinates_ordering (generate/utils.py:15-33): the two (unstable, order-defining) argsorts stay numpy's on the
+ * host; given their results this evaluates `order = arange(n)[index_latitude][index_longitude[::-1]]`, its inverse
+ * `rank` (rank[order[i]] = i: the map agx_relabel_nodes applies to provisionally numbered index rows) and
+ * `x_out = x_in[order]` (nodes/builders/from_refined_icosahedron.py:66) in one kernel.                        */
+int agx_order_resolve(const int64_t* index_latitude /*DEV n*/, const int64_t* index_longitude /*DEV n*/, int64_t n,
+                      const float* x_in /*DEV n*2*/, float* x_out /*DEV n*2*/, int64_t* order /*DEV n*/,
+                      int64_t* rank /*DEV n*/, void* stream);
+
 /* ---- edge attributes ------------------------------------------------------------------------------
  * agx_node_tables: everything the attribute kernel needs from ONE node, as one 32-byte record per role:
  *   src_rec  float[8]  = (x, y, z, cos lat, lat, lon, 0, 0) - float32 unit vector and cos(lat) with numpy's
