@@ -40,6 +40,8 @@ SIGNATURES = {
         [c_void_p, c_void_p, c_int64, c_int, c_double, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p],
     ),
     "agx_knn_redecide": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_double, c_void_p, c_void_p, c_void_p]),
+    "agx_set_query_order_mode": (None, [c_int]),
+    "agx_last_query_order": (c_int, []),
     "agx_radius_count": (c_int, [c_void_p, c_void_p, c_int64, c_double, c_void_p, c_void_p]),
     "agx_exclusive_scan": (c_int, [c_void_p, c_int64, c_void_p, POINTER(c_int64), c_void_p]),
     "agx_radius_fill": (c_int, [c_void_p, c_void_p, c_int64, c_double, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),

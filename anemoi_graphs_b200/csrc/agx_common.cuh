@@ -17,7 +17,9 @@ void agx_set_error(const char* fmt, ...);
 void agx_note_launch(int n);  // bench.py "gpu_launches" accounting
 void agx_pool_keep_warm(void);
 // copy `words` 8-byte words from device memory to host memory WITHOUT the copy engine, then sync the stream
-int agx_readback(void* host_dst, const void* dev_src, int words, cudaStream_t stream);  // raise the release threshold of the device's cudaMallocAsync pool (once)
+int agx_readback(void* host_dst, const void* dev_src, int words, cudaStream_t stream);
+int agx_order_mode(void);         // thread-local override of the query-order decision: -1 auto, 0 as given, 1 binned
+void agx_note_order(int binned);  // what the last decision was  // raise the release threshold of the device's cudaMallocAsync pool (once)
 
 #define AGX_CUDA_OK(expr)                                                                   \
     do {                                                                                    \

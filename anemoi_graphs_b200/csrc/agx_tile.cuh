@@ -231,6 +231,7 @@ static int agx_query_order(const agx_index_t* ix, const float2* q_latlon, int64_
     *perm = nullptr;
     int mode = -1;
     if (const char* env = getenv(env_name)) mode = atoi(env);
+    if (mode < 0) mode = agx_order_mode();  // pinned by a caller that searches one query set in chunks
     bool bin = mode == 1;
     if (mode < 0 && nq >= 262144) {
         double frac = 1.0;
@@ -238,6 +239,7 @@ static int agx_query_order(const agx_index_t* ix, const float2* q_latlon, int64_
         if (rc != AGX_OK) return rc;
         bin = frac < 0.75;
     }
+    agx_note_order(bin);
     if (!bin) return AGX_OK;
     agx_pool_keep_warm();
     return agx_bin_queries(q_latlon, nq, perm, stream);

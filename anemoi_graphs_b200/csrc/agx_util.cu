@@ -60,6 +60,16 @@ int agx_readback(void* host_dst, const void* dev_src, int words, cudaStream_t st
     return AGX_OK;
 }
 
+// Query-order decision of the tile kernels (agx_tile.cuh agx_query_order): a caller that searches ONE query set in
+// several chunks lets the first call decide (sampling costs a stream synchronisation) and pins that decision for the
+// remaining chunks, so that the host can run ahead of the device.
+static thread_local int g_order_mode = -1;  // -1 auto, 0 as given, 1 binned
+static thread_local int g_order_last = 0;
+int agx_order_mode(void) { return g_order_mode; }
+void agx_note_order(int binned) { g_order_last = binned ? 1 : 0; }
+extern "C" void agx_set_query_order_mode(int mode) { g_order_mode = mode < 0 ? -1 : (mode ? 1 : 0); }
+extern "C" int agx_last_query_order(void) { return g_order_last; }
+
 extern "C" const char* agx_last_error(void) { return g_err; }
 extern "C" int agx_abi_version(void) { return AGX_ABI_VERSION; }
 extern "C" int64_t agx_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }

@@ -561,81 +561,113 @@ def all_gather_v(full: torch.Tensor, counts: list[int], dim: int, async_op: bool
 
 
 # --------------------------------------------------------------------------------------------------
-# peer push: the exchange of per-rank edge blocks overlapped with the search that produces them
+# chunked exchange: the all-gather of per-rank edge blocks overlapped with the search that produces them
 # --------------------------------------------------------------------------------------------------
-# OFF by default: measured slower than the NCCL all-gather in this form (see PeerPush) - opt in with AGX_PEER_PUSH=1
-PEER_PUSH = __import__("os").environ.get("AGX_PEER_PUSH", "0") == "1"
-PEER_PUSH_CHUNK_QUERIES = 4_000_000  # a rank's query range is searched in chunks of about this many queries
+GATHER_CHUNK_QUERIES = int(float(__import__("os").environ.get("AGX_GATHER_CHUNK_QUERIES", "4e6")))
 
 
-class PeerPush:
-    """Replaces the all-gather that FOLLOWS a sharded search by copies that run DURING it.
+def query_chunks(lo: int, hi: int, n_chunks: int) -> list[tuple[int, int]]:
+    """The query range [lo, hi) cut into ``n_chunks`` nearly equal pieces (some may be empty)."""
+    n = hi - lo
+    return [(lo + (i * n) // n_chunks, lo + ((i + 1) * n) // n_chunks) for i in range(n_chunks)]
 
-    Every rank of the box maps every other rank's output buffer (CUDA IPC through PyTorch's own tensor sharing:
-    the (2, E) ``full`` tensors have the same shape on all ranks).  The search runs over the rank's query range in
-    chunks; as soon as a chunk's kernels have written their columns, a side stream pushes those columns into the
-    same place of every peer's buffer - device-to-device DMA over NVLink, no SM time, no NCCL on the data path -
-    while the main stream is already searching the next chunk.  ``finish`` orders the main stream behind the
-    rank's own pushes and runs one tiny stream-ordered all-reduce: when it completes every rank has finished
-    pushing, so every buffer is complete.
 
-    Status (round 1): correct (``tools/dist_check.py`` with AGX_PEER_PUSH=1) but NOT faster - 40 M-query KNN-3 at
-    N = 2: 22.6 ms against 4.5 ms with the NCCL all-gather after the search, cut-off 69.9 against 14.4 ms.
-    ``tools/ipc_probe.py`` shows why: a copy into a peer's buffer mapped through PyTorch's CUDA IPC tensor sharing
-    (cudaIpcOpenMemHandle + cudaMemcpyAsync) moves 26 GB/s on these boxes - it does not take the NVLink path - while
-    NCCL's all-gather moves the same gigabyte per rank in 2.3 ms; mapping the buffers also costs ~350 ms the first
-    time.  Reaching NVLink from our own kernels / copies needs the driver VMM route NCCL uses (cuMemCreate +
-    exported shareable handles); that is the round-2 form.  Off by default."""
+def n_query_chunks(nq: int, world_size: int) -> int:
+    """How many chunks every rank cuts its query range into (the same number on all ranks)."""
+    per_rank = (nq + world_size - 1) // world_size
+    return max(1, min(16, (per_rank + GATHER_CHUNK_QUERIES - 1) // GATHER_CHUNK_QUERIES))
 
-    def __init__(self, full: torch.Tensor) -> None:
-        import torch.distributed as dist
-        from torch.multiprocessing.reductions import reduce_tensor
 
+_gather_pg = None
+
+
+def _gather_group():
+    """A process group of all ranks whose NCCL kernels run on a HIGH-PRIORITY stream: the exchange of a finished
+    chunk must get its few CTAs while the (persistent, SM-filling) search kernel of the next chunk is running."""
+    global _gather_pg
+    import torch.distributed as dist
+
+    if _gather_pg is None:
+        opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+        _gather_pg = dist.new_group(backend="nccl", pg_options=opts)
+    return _gather_pg
+
+
+class ChunkedGather:
+    """All-gather of a sharded (2, E) edge list that runs WHILE the search fills it.
+
+    Every rank searches its query range in the same number of chunks.  When a chunk's kernels have written their
+    columns (main stream), a second stream packs them into the rank's slot of a padded (W, 2, max) buffer, runs
+    NCCL's equal-block in-place all-gather on it (640 GB/s per rank over NVLink, against ~260 GB/s for an uneven
+    exchange) and unpacks the other ranks' slots into their final columns of ``full`` - while the main stream is
+    already searching the next chunk.  ``finish`` orders the main stream behind the last unpack.  The collectives
+    are issued in chunk order on every rank; empty chunks are skipped consistently (the count matrix is global).
+
+    ``counts[r][c]`` = number of columns rank ``r`` produces in its chunk ``c``; rank ``r``'s block starts at column
+    ``sum(counts[:r])`` and its chunks follow each other inside it."""
+
+    def __init__(self, full: torch.Tensor, counts: list[list[int]]) -> None:
         self.rank, self.w = world()
         self.full = full
-        rebuild, args = reduce_tensor(full)
-        gathered = [None] * self.w
-        dist.all_gather_object(gathered, args)
-        self.peers = [None if r == self.rank else rebuild(*gathered[r]) for r in range(self.w)]
-        self.side = torch.cuda.Stream(device=full.device)
-        self._token = torch.zeros(1, dtype=torch.int32, device=full.device)
+        self.counts = counts
+        self.offsets = []
+        col = 0
+        for r in range(self.w):
+            row = []
+            for c in counts[r]:
+                row.append(col)
+                col += c
+            self.offsets.append(row)
+        assert col == full.shape[1], (col, tuple(full.shape))
+        self.side = torch.cuda.Stream(device=full.device, priority=-1)
+        self.group = _gather_group()
 
-    def push(self, col_lo: int, col_hi: int) -> None:
-        """Columns [col_lo, col_hi) of ``full`` have just been written on the current stream: send them to the peers."""
-        if col_hi <= col_lo:
-            return
+    def mark(self) -> torch.cuda.Event:
+        """Event after the kernels of the chunk just enqueued on the current stream."""
         ready = torch.cuda.Event()
         ready.record()
-        with torch.cuda.stream(self.side):
-            self.side.wait_event(ready)
-            for step in range(1, self.w):  # start with a different peer on every rank: all links busy at once
-                peer = self.peers[(self.rank + step) % self.w]
-                for row in range(self.full.shape[0]):
-                    peer[row, col_lo:col_hi].copy_(self.full[row, col_lo:col_hi], non_blocking=True)
+        return ready
 
-    def finish(self) -> None:
+    def chunk_done(self, c: int, ready: torch.cuda.Event | None = None) -> None:
+        """Exchange chunk ``c`` once ``ready`` (default: everything enqueued so far) has completed.  Call it AFTER
+        enqueuing the search of chunk c + 1, so that the main stream never waits for this host work."""
         import torch.distributed as dist
 
+        widest = max(self.counts[r][c] for r in range(self.w))
+        if widest == 0:
+            return
+        full, rank = self.full, self.rank
+        if ready is None:
+            ready = self.mark()
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(ready)
+            slots = torch.empty((self.w, 2, widest), dtype=full.dtype, device=full.device)
+            mine, o = self.counts[rank][c], self.offsets[rank][c]
+            if mine:
+                slots[rank, :, :mine].copy_(full[:, o : o + mine])
+            dist.all_gather_into_tensor(slots.view(-1), slots[rank].reshape(-1), group=self.group)
+            for r in range(self.w):
+                n, o = self.counts[r][c], self.offsets[r][c]
+                if r != rank and n:
+                    full[:, o : o + n].copy_(slots[r, :, :n])
+            slots.record_stream(self.side)
+
+    def finish(self) -> None:
         done = torch.cuda.Event()
         done.record(self.side)
         torch.cuda.current_stream().wait_event(done)
-        dist.all_reduce(self._token)  # stream-ordered: completes once every rank's pushes are done
         self.full.record_stream(self.side)
-        self.peers = None
 
 
-def peer_push_available() -> bool:
+def all_gather_count_rows(mine: list[int], device: torch.device) -> list[list[int]]:
+    """Every rank's list of per-chunk counts: (W x C) nested list."""
     import torch.distributed as dist
 
     _, w = world()
-    return PEER_PUSH and w > 1 and dist.get_backend() == "nccl" and w <= torch.cuda.device_count()
-
-
-def query_chunks(lo: int, hi: int) -> list[tuple[int, int]]:
-    """The rank's query range [lo, hi) cut into about PEER_PUSH_CHUNK_QUERIES-sized pieces."""
-    n = hi - lo
-    pieces = max(1, min(16, (n + PEER_PUSH_CHUNK_QUERIES - 1) // PEER_PUSH_CHUNK_QUERIES))
-    return [(lo + (i * n) // pieces, lo + ((i + 1) * n) // pieces) for i in range(pieces)]
+    t = torch.tensor(mine, dtype=torch.int64, device=device)
+    out = torch.empty((w, len(mine)), dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(out, t)
+    return [[int(v) for v in row] for row in out.tolist()]
 
 
 def all_gather_stats_raw(stats: torch.Tensor) -> torch.Tensor:

@@ -267,17 +267,10 @@ class KNNEdges(BaseEdgeBuilder, NodeMaskingMixin):
         lo, hi = _device.shard_range(nq, rank, w)
         with ops.NeighbourIndex(src, hint_k=k) as index:
             out = torch.empty((2, nq * k), dtype=torch.int32, device=dst.device)
-            if w > 1 and _device.peer_push_available():
-                # sharded: search the rank's range in chunks and push each finished chunk into every peer's buffer
-                # while the next one is searched (device.PeerPush) - no all-gather afterwards
-                push = _device.PeerPush(out)
-                for a, b in _device.query_chunks(lo, hi):
-                    index.knn(dst[a:b], k, dst_base=a, stats=self.stats, out=out, out_offset=a * k)
-                    push.push(a * k, b * k)
-                push.finish()
-                w = 1  # complete on every rank
-            else:
-                index.knn(dst[lo:hi], k, dst_base=lo, stats=self.stats, out=out, out_offset=lo * k)
+            # equal blocks: one in-place NCCL all-gather after the search (640 GB/s per rank; chunking the search to
+            # overlap the exchange was measured and does not pay: the persistent search kernel leaves no room for
+            # the collective's CTAs until it ends - 40 M queries, N = 2: 4.8 ms chunked against 4.5 ms)
+            index.knn(dst[lo:hi], k, dst_base=lo, stats=self.stats, out=out, out_offset=lo * k)
         if w > 1:
             counts = [(b - a) * k for a, b in (_device.shard_range(nq, r, w) for r in range(w))]
             out = _gather_blocks(out, counts, rank, src_sel is not None or dst_sel is not None)
@@ -345,21 +338,40 @@ class CutOffEdges(BaseEdgeBuilder, NodeMaskingMixin):
         with ops.NeighbourIndex(src, hint_radius=self.radius) as index:
             q = dst[lo:hi]
             offsets, total = index.radius_count(q, self.radius)
-            counts = _device.all_gather_counts(total, dst.device) if w > 1 else [total]
-            out = torch.empty((2, sum(counts)), dtype=torch.int32, device=dst.device)
-            base = sum(counts[:rank])
-            if w > 1 and _device.peer_push_available():
-                push = _device.PeerPush(out)
-                chunks = _device.query_chunks(0, hi - lo)
+            masked = src_sel is not None or dst_sel is not None
+            if w > 1 and not masked and torch.distributed.get_backend() == "nccl":
+                # uneven blocks: padded equal-block all-gathers, chunk by chunk (device.ChunkedGather); per-chunk pair
+                # counts from the count pass
+                n_chunks = _device.n_query_chunks(nq, w)
+                chunks = _device.query_chunks(0, hi - lo, n_chunks)
                 bounds = offsets[[a for a, _ in chunks] + [hi - lo]].tolist()  # pair offsets at the chunk boundaries
-                for (a, b), o0, o1 in zip(chunks, bounds[:-1], bounds[1:]):
-                    # the offsets keep their block-relative values, so the chunk lands at its final columns
-                    index.radius_fill(q[a:b], self.radius, offsets[a : b + 1], o1 - o0, out, base, dst_base=lo + a,
-                                      stats=self.stats)  # fmt: skip
-                    push.push(base + o0, base + o1)
-                push.finish()
+                mine = [o1 - o0 for o0, o1 in zip(bounds[:-1], bounds[1:])]
+                rows = _device.all_gather_count_rows(mine, dst.device)
+                counts = [sum(r) for r in rows]
+                out = torch.empty((2, sum(counts)), dtype=torch.int32, device=dst.device)
+                base = sum(counts[:rank])
+                gather = _device.ChunkedGather(out, rows)
+                lib, marks = ops.load_library(), []
+                lib.agx_set_query_order_mode(lib.agx_last_query_order())  # as the count pass decided: no more syncs
+                try:
+                    for c, (a, b) in enumerate(chunks):
+                        if mine[c]:
+                            # the offsets keep their block-relative values, so the chunk lands at its final columns
+                            index.radius_fill(q[a:b], self.radius, offsets[a : b + 1], mine[c], out, base,
+                                              dst_base=lo + a, stats=self.stats)  # fmt: skip
+                        marks.append(gather.mark())
+                        if c > 0:
+                            gather.chunk_done(c - 1, marks[c - 1])
+                    gather.chunk_done(n_chunks - 1, marks[-1])
+                finally:
+                    lib.agx_set_query_order_mode(-1)
+                gather.finish()
+                out._agx_local = (base, base + counts[rank], list(counts))
                 w = 1  # complete on every rank
             else:
+                counts = _device.all_gather_counts(total, dst.device) if w > 1 else [total]
+                out = torch.empty((2, sum(counts)), dtype=torch.int32, device=dst.device)
+                base = sum(counts[:rank])
                 index.radius_fill(q, self.radius, offsets, total, out, base, dst_base=lo, stats=self.stats)
         if w > 1:
             out = _gather_blocks(out, counts, rank, src_sel is not None or dst_sel is not None)

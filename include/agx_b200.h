@@ -97,6 +97,14 @@ int agx_knn_flagged(const agx_index_t* index, const float* q_latlon /*DEV nq*2*/
 int agx_knn_redecide(const agx_index_t* index, const float* q_latlon /*DEV nq*2*/, int64_t nq, int k, double max_radius,
                      int32_t* out_src /*DEV nq*k*/, const uint8_t* tie_flags /*DEV nq*/, void* stream);
 
+/* Query order of the tile kernels.  agx_knn / agx_radius_* decide per call whether to walk the queries as given or in
+ * a spatially binned order; for >= 262 144 queries the decision samples tile plans and synchronises the stream.
+ * A caller that searches ONE query set in several chunks (device.ChunkedGather) reads the first call's decision
+ * (agx_last_query_order: 0 as given, 1 binned) and pins it for the rest (agx_set_query_order_mode; -1 = decide per
+ * call again), so that the host can enqueue chunk c+1 while chunk c runs.  Both are per host thread.            */
+void agx_set_query_order_mode(int mode);
+int agx_last_query_order(void);
+
 /* ---- cut-off (radius) search -------------------------------------------------------------------
  * Replaces `radius_neighbors_graph(target, radius)` (edges/builder.py:366): every reference point
  * with rdist <= sin^2(radius/2) (inclusive).  count -> scan -> fill; output grouped by query, in

@@ -1,8 +1,8 @@
 """BASELINE.json config 5 across GPUs (run under torchrun on the GPU box): KNN / cut-off edges between 1 M uniform
 reference points and 100 M uniform query points through the builder API, query nodes sharded over the ranks
 (``device.shard_world``: 100 M >= AGX_SHARD_MIN_QUERIES), per-rank blocks all-gathered so that every rank ends
-with the complete edge list (``device.PeerPush``: chunks pushed into the peers' buffers while the search runs;
-AGX_PEER_PUSH=0: NCCL all-gather after the search).  Times are CUDA events around ``compute_edge_index`` + the wait for the gathers, max over
+with the complete edge list (``device.ChunkedGather``: every finished chunk of the search is all-gathered on a
+second stream while the next one is searched).  Times are CUDA events around ``compute_edge_index`` + the wait for the gathers, max over
 ranks; a second column gives the time without the all-gather (each rank keeps its block).
 
     python -m torch.distributed.run --nproc-per-node N tools/scale_sweep.py [--queries 100000000] [--ks 3,16]
@@ -58,13 +58,12 @@ def main():
                 ei = builder.get_edge_index_device(graph)
                 agx_device.wait_for(ei)
             else:  # the rank's own block only: the search without the exchange
-                saved, agx_device.all_gather_v = agx_device.all_gather_v, lambda full, counts, dim, async_op=False: full
-                saved_push, agx_device.PEER_PUSH = agx_device.PEER_PUSH, False
+                saved = agx_device.ChunkedGather.chunk_done
+                agx_device.ChunkedGather.chunk_done = lambda self, c, ready=None: None
                 try:
                     ei = builder.get_edge_index_device(graph)
                 finally:
-                    agx_device.all_gather_v = saved
-                    agx_device.PEER_PUSH = saved_push
+                    agx_device.ChunkedGather.chunk_done = saved
             b.record()
             torch.cuda.synchronize()
             ms = a.elapsed_time(b)
