@@ -619,40 +619,56 @@ class ChunkedGather:
                 col += c
             self.offsets.append(row)
         assert col == full.shape[1], (col, tuple(full.shape))
-        self.side = torch.cuda.Stream(device=full.device, priority=-1)
-        self.group = _gather_group()
+        self.on_device = full.is_cuda
+        if self.on_device:
+            self.side = torch.cuda.Stream(device=full.device, priority=-1)
+            self.group = _gather_group()
+        else:  # host tensors (gloo, the CPU tests of the bookkeeping): same steps, inline, default group
+            self.side = None
+            self.group = None
 
-    def mark(self) -> torch.cuda.Event:
+    def mark(self):
         """Event after the kernels of the chunk just enqueued on the current stream."""
+        if not self.on_device:
+            return None
         ready = torch.cuda.Event()
         ready.record()
         return ready
 
-    def chunk_done(self, c: int, ready: torch.cuda.Event | None = None) -> None:
-        """Exchange chunk ``c`` once ``ready`` (default: everything enqueued so far) has completed.  Call it AFTER
-        enqueuing the search of chunk c + 1, so that the main stream never waits for this host work."""
+    def _exchange(self, c: int, widest: int) -> None:
         import torch.distributed as dist
 
+        full, rank = self.full, self.rank
+        slots = torch.empty((self.w, 2, widest), dtype=full.dtype, device=full.device)
+        mine, o = self.counts[rank][c], self.offsets[rank][c]
+        if mine:
+            slots[rank, :, :mine].copy_(full[:, o : o + mine])
+        dist.all_gather_into_tensor(slots.view(-1), slots[rank].reshape(-1), group=self.group)
+        for r in range(self.w):
+            n, o = self.counts[r][c], self.offsets[r][c]
+            if r != rank and n:
+                full[:, o : o + n].copy_(slots[r, :, :n])
+        return slots
+
+    def chunk_done(self, c: int, ready=None) -> None:
+        """Exchange chunk ``c`` once ``ready`` (default: everything enqueued so far) has completed.  Call it AFTER
+        enqueuing the search of chunk c + 1, so that the main stream never waits for this host work."""
         widest = max(self.counts[r][c] for r in range(self.w))
         if widest == 0:
             return
-        full, rank = self.full, self.rank
+        if not self.on_device:
+            self._exchange(c, widest)
+            return
         if ready is None:
             ready = self.mark()
         with torch.cuda.stream(self.side):
             self.side.wait_event(ready)
-            slots = torch.empty((self.w, 2, widest), dtype=full.dtype, device=full.device)
-            mine, o = self.counts[rank][c], self.offsets[rank][c]
-            if mine:
-                slots[rank, :, :mine].copy_(full[:, o : o + mine])
-            dist.all_gather_into_tensor(slots.view(-1), slots[rank].reshape(-1), group=self.group)
-            for r in range(self.w):
-                n, o = self.counts[r][c], self.offsets[r][c]
-                if r != rank and n:
-                    full[:, o : o + n].copy_(slots[r, :, :n])
+            slots = self._exchange(c, widest)
             slots.record_stream(self.side)
 
     def finish(self) -> None:
+        if not self.on_device:
+            return
         done = torch.cuda.Event()
         done.record(self.side)
         torch.cuda.current_stream().wait_event(done)
@@ -666,7 +682,7 @@ def all_gather_count_rows(mine: list[int], device: torch.device) -> list[list[in
     _, w = world()
     t = torch.tensor(mine, dtype=torch.int64, device=device)
     out = torch.empty((w, len(mine)), dtype=torch.int64, device=device)
-    dist.all_gather_into_tensor(out, t)
+    dist.all_gather_into_tensor(out.view(-1), t)
     return [[int(v) for v in row] for row in out.tolist()]
 
 

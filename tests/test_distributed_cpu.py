@@ -64,6 +64,24 @@ def _worker(rank: int, world: int, port: int, out_dir: str) -> None:
         assert full[0].tolist() == [1] * 5 + [2] * 2 and full[1].tolist() == [1] * 5 + [2] * 2
         agx_device.flush()  # waits for `side`
         assert side[:, 0].tolist() == [1.0] * 5 + [2.0] * 2
+        # --- chunked exchange of uneven blocks (ChunkedGather): padded equal-block all-gathers per chunk, one chunk
+        #     empty on one rank, one empty on both ---------------------------------------------------------------
+        mine = [3, 0, 2, 0] if rank == 0 else [1, 4, 0, 0]
+        rows = agx_device.all_gather_count_rows(mine, torch.device("cpu"))
+        assert rows == [[3, 0, 2, 0], [1, 4, 0, 0]]
+        full = torch.full((2, 10), -1, dtype=torch.int32)
+        gather = agx_device.ChunkedGather(full, rows)
+        assert gather.offsets == [[0, 3, 3, 5], [5, 6, 10, 10]]
+        for c in range(4):
+            o, n = gather.offsets[rank][c], rows[rank][c]
+            full[0, o : o + n] = 100 * rank + 10 * c + torch.arange(n, dtype=torch.int32)  # "search" of chunk c
+            full[1, o : o + n] = c
+            gather.chunk_done(c, gather.mark())
+        gather.finish()
+        assert full[0].tolist() == [0, 1, 2, 20, 21, 100, 110, 111, 112, 113]
+        assert full[1].tolist() == [0, 0, 0, 2, 2, 0, 1, 1, 1, 1]
+        assert agx_device.query_chunks(10, 21, 3) == [(10, 13), (13, 17), (17, 21)]
+        assert agx_device.n_query_chunks(100, 2) == 1
         # --- an empty rank block --------------------------------------------------------------------
         counts = agx_device.all_gather_counts(0 if rank == 1 else 4, torch.device("cpu"))
         full = torch.zeros((sum(counts), 2), dtype=torch.float32)
