@@ -178,7 +178,25 @@ struct KnnArgs {
     unsigned long long* stats;
     uint8_t* tie_flags;  // optional: 1 for every query whose k-th boundary is a tie (the result depends on the index order)
     int only_flagged;    // 1: tie_flags is an INPUT - only queries whose flag is set are searched and written
+    const int32_t* tile_list;  // only_flagged: the tiles (of 32 consecutive queries) that hold a flagged query ...
+    const int* tile_count;     // ... and how many there are (device memory: no read-back)
 };
+
+// the tiles that hold at least one flagged query, appended in arbitrary order (the results do not depend on it)
+__global__ void __launch_bounds__(256) k_flagged_tiles(const uint8_t* __restrict__ flags, int64_t nq, int64_t n_tiles,
+                                                       int32_t* __restrict__ tile_list, int* __restrict__ tile_count) {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_tiles; t += (int64_t)gridDim.x * blockDim.x) {
+        bool any = false;
+        if (t * 32 + 32 <= nq) {
+            const uint4* w = (const uint4*)(flags + t * 32);  // 32-byte aligned: cudaMalloc'ed base, t * 32
+            uint4 a = w[0], b = w[1];
+            any = (a.x | a.y | a.z | a.w | b.x | b.y | b.z | b.w) != 0u;
+        } else {
+            for (int64_t q = t * 32; q < nq; ++q) any |= flags[q] != 0;
+        }
+        if (any) tile_list[atomicAdd(tile_count, 1)] = (int32_t)t;
+    }
+}
 
 __device__ __forceinline__ float chord2(float3 q, float4 c) {
     float dx = q.x - c.x, dy = q.y - c.y, dz = q.z - c.z;
@@ -271,15 +289,14 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn(KnnArgs a) {
     const int k = a.k;
     const int64_t n_tiles = (a.nq + 31) >> 5;
     const int64_t warps_total = (int64_t)gridDim.x * KNN_WARPS;
-    for (int64_t tile = (int64_t)blockIdx.x * KNN_WARPS + warp; tile < n_tiles; tile += warps_total) {
+    const int64_t n_work = a.only_flagged ? (int64_t)*a.tile_count : n_tiles;
+    for (int64_t work = (int64_t)blockIdx.x * KNN_WARPS + warp; work < n_work; work += warps_total) {
+        const int64_t tile = a.only_flagged ? (int64_t)a.tile_list[work] : work;
         const int64_t slot = tile * 32 + lane;
         bool active = slot < a.nq;
         const int64_t qs = active ? slot : a.nq - 1;
         const int64_t q = a.qperm ? (int64_t)__ldg(a.qperm + qs) : qs;  // binned order, results at the query's own place
-        if (a.only_flagged) {  // re-decision pass: whole tiles without a flagged query cost one byte per lane
-            active = active && a.tie_flags[q] != 0;
-            if (!__any_sync(0xffffffffu, active)) continue;
-        }
+        if (a.only_flagged) active = active && a.tie_flags[q] != 0;  // re-decision pass: the other lanes only help
         const float2 ql = a.q_latlon[q];
         const float3 qv = agx_search_xyz(ql);
         const float t2 = a.chord2_init;
@@ -507,7 +524,21 @@ int agx_knn_ex(const agx_index_t* ix, const float* q_latlon, int64_t nq, int k, 
     a.tie_flags = tie_flags;
     a.only_flagged = only_flagged;
     int32_t* perm = nullptr;
-    if (!only_flagged) {  // the re-decision pass touches a handful of queries: not worth sampling their order
+    int32_t* tile_list = nullptr;
+    a.tile_list = nullptr;
+    a.tile_count = nullptr;
+    if (only_flagged) {
+        // the re-decision pass touches a handful of queries: list the tiles that hold one (no read-back), search those
+        const int64_t n_tiles = (nq + 31) / 32;
+        agx_pool_keep_warm();
+        AGX_CUDA_OK(cudaMallocAsync(&tile_list, (n_tiles + 1) * sizeof(int32_t), stream));
+        int* count = (int*)(tile_list + n_tiles);
+        AGX_CUDA_OK(cudaMemsetAsync(count, 0, sizeof(int), stream));
+        k_flagged_tiles<<<agx_grid(n_tiles, 256, 8), 256, 0, stream>>>(tie_flags, nq, n_tiles, tile_list, count);
+        agx_note_launch(1);
+        a.tile_list = tile_list;
+        a.tile_count = count;
+    } else {
         int rc = agx_query_order(ix, a.q_latlon, nq, a.chord2_init, "AGX_KNN_BIN", &perm, stream);
         if (rc != AGX_OK) return rc;
         a.qperm = perm;
@@ -525,5 +556,6 @@ int agx_knn_ex(const agx_index_t* ix, const float* q_latlon, int64_t nq, int k, 
     AGX_LAUNCH_OK();
     agx_note_launch(1);
     if (perm) AGX_CUDA_OK(cudaFreeAsync(perm, stream));
+    if (tile_list) AGX_CUDA_OK(cudaFreeAsync(tile_list, stream));
     return AGX_OK;
 }
