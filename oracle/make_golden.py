@@ -21,6 +21,10 @@ product code is on that path, only ``anemoi_graphs_b200.grids`` for the syntheti
                      LimitedAreaTriNodes / StretchedTriNodes coordinates, multi-scale edges (x_hops 1, 2),
                      masked KNN and cut-off edges.
 * ``attr_vectors.npz`` SURVEY appendix-B style edge cases for EdgeLength / EdgeDirection.
+* ``hex.npz``        the reference's hexagonal path (generate/hex_icosahedron.py, HexNodes / LimitedAreaHexNodes,
+                     MultiScaleEdges) executed UNMODIFIED over ``oracle/shims/h3`` - the h3 calls answered by the
+                     restatement of H3's geometry, everything else (k_ring & nodes, compact / uncompact, centre
+                     children, networkx, ordering) the reference's own code.
 * ``area_weights.npz`` SphericalAreaWeights of the reference (scipy SphericalVoronoi) on an O24 grid, TriNodes(3)
                      and 3 000 random points, raw and for every norm.
 """
@@ -300,6 +304,34 @@ def make_attr_vectors() -> None:
     print("attr_vectors.npz", rot.dtype, length.dtype)
 
 
+def make_hex() -> None:
+    from anemoi.graphs.edges import MultiScaleEdges
+    from anemoi.graphs.nodes import HexNodes, LimitedAreaHexNodes
+    from torch_geometric.data import HeteroData
+
+    out: dict[str, np.ndarray] = {}
+    for tag, resolution, hops_list in (("res2", 2, (1, 2)), ("res_0_2", [0, 2], (3,))):
+        for hops in hops_list:
+            g = HexNodes(resolution, "h").update_graph(HeteroData(), {})
+            out[f"{tag}_x"] = g["h"].x.numpy()
+            g = MultiScaleEdges("h", "h", hops).update_graph(g)
+            out[f"{tag}_hops{hops}_edge_index"] = canon(g[("h", "to", "h")].edge_index.numpy())
+    # limited area: a lat/lon patch as reference nodes, 150 km margin, resolution 3
+    lat, lon = np.meshgrid(np.linspace(35.0, 65.0, 61), np.linspace(-10.0, 30.0, 81), indexing="ij")
+    data_x = np.deg2rad(np.stack([lat.reshape(-1), lon.reshape(-1)], axis=1)).astype(np.float32)
+    for hops in (1, 2):
+        g = HeteroData()
+        g["data"].x = torch.from_numpy(data_x)
+        g["data"].node_type = "LatLonNodes"
+        g = LimitedAreaHexNodes(3, "data", "lam", margin_radius_km=150.0).update_graph(g, {})
+        out["lam_data_x"] = data_x
+        out["lam_x"] = g["lam"].x.numpy()
+        g = MultiScaleEdges("lam", "lam", hops).update_graph(g)
+        out[f"lam_hops{hops}_edge_index"] = canon(g[("lam", "to", "lam")].edge_index.numpy())
+    np.savez_compressed(OUT / "hex.npz", **out)
+    print("hex.npz", {k: v.shape for k, v in out.items()})
+
+
 def make_area_weights() -> None:
     from anemoi.graphs.nodes.attributes import SphericalAreaWeights, UniformWeights
     from torch_geometric.data import HeteroData
@@ -330,6 +362,6 @@ if __name__ == "__main__":
     OUT.mkdir(parents=True, exist_ok=True)
     only = sys.argv[1:]
     for name, fn in (("attr_vectors", make_attr_vectors), ("tri", make_tri), ("toy", make_toy), ("o96", make_o96),
-                     ("lam", make_lam), ("area_weights", make_area_weights)):  # fmt: skip
+                     ("lam", make_lam), ("area_weights", make_area_weights), ("hex", make_hex)):  # fmt: skip
         if not only or name in only:
             fn()

@@ -155,6 +155,29 @@ def test_limited_area_hex_nodes_and_edges(hops):
     np.testing.assert_array_equal(canon(graph[("lam", "to", "lam")].edge_index), want)
 
 
+def test_hex_against_the_reference_control_flow(golden):
+    """tests/golden/hex.npz: the UNMODIFIED reference hexagonal path over the h3 shim (oracle/make_golden.py make_hex)."""
+    from anemoi_graphs_b200.edges import MultiScaleEdges
+    from anemoi_graphs_b200.graph import HeteroData
+    from anemoi_graphs_b200.nodes import HexNodes, LimitedAreaHexNodes
+
+    g = golden("hex")
+    for tag, resolution, hops_list in (("res2", 2, (1, 2)), ("res_0_2", [0, 2], (3,))):
+        for hops in hops_list:
+            graph = HexNodes(resolution, "h").update_graph(HeteroData(), {})
+            np.testing.assert_allclose(graph["h"].x.cpu().numpy(), g[f"{tag}_x"], rtol=0, atol=2.5e-7)
+            MultiScaleEdges("h", "h", hops).update_graph(graph)
+            np.testing.assert_array_equal(canon(graph[("h", "to", "h")].edge_index), g[f"{tag}_hops{hops}_edge_index"])
+    for hops in (1, 2):
+        graph = HeteroData()
+        graph["data"].x = torch.from_numpy(g["lam_data_x"])
+        graph["data"].node_type = "LatLonNodes"
+        graph = LimitedAreaHexNodes(3, "data", "lam", margin_radius_km=150.0).update_graph(graph, {})
+        np.testing.assert_allclose(graph["lam"].x.cpu().numpy(), g["lam_x"], rtol=0, atol=2.5e-7)
+        MultiScaleEdges("lam", "lam", hops).update_graph(graph)
+        np.testing.assert_array_equal(canon(graph[("lam", "to", "lam")].edge_index), g[f"lam_hops{hops}_edge_index"])
+
+
 def test_hex_recipe_through_graph_creator():
     """encoder / processor / decoder recipe with a hexagonal hidden mesh (docs recipe with HexNodes)."""
     from anemoi_graphs_b200 import grids

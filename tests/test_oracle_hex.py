@@ -86,3 +86,28 @@ def test_multiscale_edge_counts():
     assert np.array_equal(e, e[:, np.lexsort((e[0], e[1]))])
     back = {(int(t), int(s)) for s, t in e.T}
     assert back == {(int(s), int(t)) for s, t in e.T}
+
+
+def test_restated_hex_edges_match_the_reference_control_flow(golden):
+    """tests/golden/hex.npz was written by the UNMODIFIED reference (hex_icosahedron.py, HexNodes /
+    LimitedAreaHexNodes, MultiScaleEdges, networkx) running over oracle/shims/h3: the oracle's own restatement of
+    that control flow (k_ring & nodes, compact / uncompact, centre children) must give the same nodes and edges."""
+    from oracle import ref_path as R
+
+    g = golden("hex")
+    coords = H.hex_nodes_latlon(2)
+    order = np.argsort(-coords[:, 0], kind="stable")
+    np.testing.assert_array_equal(coords[order].astype(np.float32), g["res2_x"])
+    np.testing.assert_array_equal(g["res2_x"], g["res_0_2_x"])
+    for hops in (1, 2):
+        np.testing.assert_array_equal(H.multiscale_edges_hex([0, 1, 2], hops, order), g[f"res2_hops{hops}_edge_index"])
+    np.testing.assert_array_equal(H.multiscale_edges_hex([0, 2], 3, order), g["res_0_2_hops3_edge_index"])
+    # limited area
+    coords = H.hex_nodes_latlon(3)
+    order = np.argsort(-coords[:, 0], kind="stable")
+    mask = R.knn_area_mask(g["lam_data_x"], coords, 150.0)
+    order = order[mask[order]]
+    np.testing.assert_array_equal(coords[order].astype(np.float32), g["lam_x"])
+    for hops in (1, 2):
+        want = g[f"lam_hops{hops}_edge_index"]
+        np.testing.assert_array_equal(H.multiscale_edges_hex([0, 1, 2, 3], hops, order, in_graph=mask), want)
