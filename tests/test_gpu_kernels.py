@@ -406,3 +406,76 @@ def test_attributes_o96_samples(ops, golden):
         np.testing.assert_allclose(dr.cpu().numpy()[::stride], want, rtol=ATTR_RTOL, atol=ATTR_RTOL * np.abs(want).max())
         np.testing.assert_allclose(ln.double().sum().item(), float(g[f"{tag}_edge_length_sum64"]), rtol=1e-6)
         np.testing.assert_allclose(dr.double().abs().sum().item(), float(g[f"{tag}_edge_dirs_abs_sum64"]), rtol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------------
+# small entry points used by the provisional-numbering path, exercised directly through the C ABI
+# ------------------------------------------------------------------------------------------------
+def test_max_positive_entry_point():
+    """agx_max_positive: `dists[dists > 0].max()` (utils.py:62-63) + its first flat position; the result comes back
+    through agx_readback (mapped pinned memory, not the copy engine)."""
+    from ctypes import byref, c_double, c_int64
+
+    from anemoi_graphs_b200 import _cabi
+
+    lib = _cabi.load_library()
+    rng = np.random.default_rng(3)
+    v = rng.normal(size=100001)
+    v[::7] = 0.0
+    v[12345] = v[54321] = 9.5  # the maximum twice: the lower position is reported
+    value, index = c_double(), c_int64()
+    _cabi.check(lib.agx_max_positive(dev(v).data_ptr(), v.size, byref(value), byref(index), _cabi.current_stream()))
+    assert value.value == 9.5 and index.value == 12345
+    neg = dev(-np.abs(v))
+    _cabi.check(lib.agx_max_positive(neg.data_ptr(), v.size, byref(value), byref(index), _cabi.current_stream()))
+    assert index.value == -1  # nothing strictly positive
+
+
+def test_order_resolve_entry_point():
+    """agx_order_resolve == arange(n)[index_latitude][index_longitude[::-1]] (generate/utils.py:30-33), its inverse and
+    coords[node_ordering] (nodes/builders/from_refined_icosahedron.py:66)."""
+    from anemoi_graphs_b200 import _cabi
+
+    lib = _cabi.load_library()
+    rng = np.random.default_rng(4)
+    n = 50003
+    x = rng.normal(size=(n, 2)).astype(np.float32)
+    il = np.argsort(x[:, 1])
+    ilon = np.argsort(x[il][:, 0])
+    want = np.arange(n)[il][ilon[::-1]]
+    x_out = torch.empty((n, 2), dtype=torch.float32, device="cuda")
+    order = torch.empty(n, dtype=torch.int64, device="cuda")
+    rank = torch.empty(n, dtype=torch.int64, device="cuda")
+    xd, ild, ilond = dev(x), dev(il.astype(np.int64)), dev(ilon.astype(np.int64))
+    _cabi.check(
+        lib.agx_order_resolve(ild.data_ptr(), ilond.data_ptr(), n, xd.data_ptr(), x_out.data_ptr(), order.data_ptr(),
+                              rank.data_ptr(), _cabi.current_stream())
+    )  # fmt: skip
+    np.testing.assert_array_equal(order.cpu().numpy(), want)
+    np.testing.assert_array_equal(rank.cpu().numpy()[want], np.arange(n))
+    np.testing.assert_array_equal(x_out.cpu().numpy(), x[want])
+
+
+def test_knn_flag_and_redecide_equals_final_numbering(ops, golden):
+    """Search with permuted source labels + flags, relabel, re-decide the flagged queries: identical (as a set per
+    query) to searching with the final labels - including the tied queries of the O96 -> res 5 decoder."""
+    g = golden("o96_res5")
+    hx = g["hidden_x"]
+    lat, lon = grids.octahedral_grid(96)
+    dx = grids.latlon_deg_to_x(lat, lon).numpy()
+    k, nq, n = 3, dx.shape[0], hx.shape[0]
+    rng = np.random.default_rng(5)
+    perm = rng.permutation(n)  # provisional label p is final node perm[p]
+    hx_prov = hx[perm]
+    flags = torch.zeros(nq, dtype=torch.uint8, device="cuda")
+    with ops.NeighbourIndex(dev(hx_prov), hint_k=k) as index:
+        out = index.knn(dev(dx), k, tie_flags=flags)
+    assert int(flags.sum().item()) > 0  # the mirror-plane ties of this configuration (DESIGN.md section 4)
+    out[0] = dev(perm.astype(np.int32))[out[0].long()]  # provisional -> final labels
+    with ops.NeighbourIndex(dev(hx), hint_k=k) as index:
+        index.knn_redecide(dev(dx), k, out, flags)
+        want = index.knn(dev(dx), k)
+    np.testing.assert_array_equal(canon(out), canon(want))
+    oracle, info = R.knn_edges_canonical(hx, dx, k)  # the lower-index tie rule on the final labels
+    assert info["tied_queries"].size == int(flags.sum().item()) == 88
+    np.testing.assert_array_equal(canon(out), oracle)
