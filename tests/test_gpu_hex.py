@@ -217,3 +217,17 @@ def test_hex_recipe_through_graph_creator():
     np.testing.assert_allclose(
         graph[key]["edge_length"].cpu().numpy(), R.edge_length(hx, hx, ei, norm="unit-std"), rtol=1e-6, atol=0
     )
+
+
+def test_hex_multiscale_extreme_hops():
+    """x_hops = 8 on the 122 base cells reaches most of the sphere from every cell; 9 is refused."""
+    from anemoi_graphs_b200.edges import MultiScaleEdges
+    from anemoi_graphs_b200.graph import HeteroData
+    from anemoi_graphs_b200.nodes import HexNodes
+
+    graph = HexNodes([0], "hex").update_graph(HeteroData(), {})
+    MultiScaleEdges("hex", "hex", 8).update_graph(graph)
+    _, order = _oracle_order(0)
+    np.testing.assert_array_equal(canon(graph[("hex", "to", "hex")].edge_index), H.multiscale_edges_hex([0], 8, order))
+    with pytest.raises(NotImplementedError):
+        MultiScaleEdges("hex", "hex", 9).update_graph(HexNodes([0], "hex").update_graph(HeteroData(), {}))
