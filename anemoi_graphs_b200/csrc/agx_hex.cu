@@ -338,3 +338,73 @@ extern "C" int agx_hex_adjacency(const int32_t* knn7, const uint8_t* pentagon, i
     agx_note_launch(1);
     return AGX_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// HEALPix nodes: hp.pix2ang(nside, range(npix), nest=True, lonlat=True) + reshape_coords
+// (/root/reference/src/anemoi/graphs/nodes/builders/from_healpix.py:61-66, nodes/builders/base.py:84-101).
+// HEALPix's published pix2loc for the NESTED scheme (healpix_cxx healpix_base.cc): face = pix >> 2*order, (ix, iy) =
+// the even / odd bits of the rest, ring jr = jrll[face]*nside - ix - iy - 1, z and phi from the polar-cap or
+// equatorial formulas; theta = atan2(sin theta, z) where the library carries sin theta (|z| > 0.99), acos(z) else;
+// healpy's degrees (lon = degrees(phi), lat = 90 - degrees(theta)), numpy's deg2rad, one rounding to float32.
+// ------------------------------------------------------------------------------------------------
+namespace {
+__device__ __forceinline__ unsigned hp_compress_bits(unsigned long long v) {
+    v &= 0x5555555555555555ull;
+    v = (v | (v >> 1)) & 0x3333333333333333ull;
+    v = (v | (v >> 2)) & 0x0f0f0f0f0f0f0f0full;
+    v = (v | (v >> 4)) & 0x00ff00ff00ff00ffull;
+    v = (v | (v >> 8)) & 0x0000ffff0000ffffull;
+    v = (v | (v >> 16)) & 0x00000000ffffffffull;
+    return (unsigned)v;
+}
+
+__global__ void k_healpix_nodes(int order, int64_t npix, float2* __restrict__ latlon) {
+    const int jrll[12] = {2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4};
+    const int jpll[12] = {1, 3, 5, 7, 0, 2, 4, 6, 1, 3, 5, 7};
+    const long long nside = 1ll << order;
+    const double halfpi = 1.570796326794896619231321691639751442099;
+    const double fact2 = 4.0 / (double)npix;
+    const double fact1 = (double)(nside << 1) * fact2;
+    for (int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pix < npix; pix += (int64_t)gridDim.x * blockDim.x) {
+        const int face = (int)(pix >> (2 * order));
+        const unsigned long long p = (unsigned long long)pix & (unsigned long long)(nside * nside - 1);
+        const long long ix = hp_compress_bits(p), iy = hp_compress_bits(p >> 1);
+        const long long jr = ((long long)jrll[face] << order) - ix - iy - 1;
+        long long nr;
+        double z, sth = 0.0;
+        bool have_sth = false;
+        if (jr < nside) {
+            nr = jr;
+            double tmp = (double)(nr * nr) * fact2;
+            z = 1.0 - tmp;
+            if (z > 0.99) { sth = sqrt(tmp * (2.0 - tmp)); have_sth = true; }
+        } else if (jr > 3 * nside) {
+            nr = nside * 4 - jr;
+            double tmp = (double)(nr * nr) * fact2;
+            z = tmp - 1.0;
+            if (z < -0.99) { sth = sqrt(tmp * (2.0 - tmp)); have_sth = true; }
+        } else {
+            nr = nside;
+            z = (double)(2 * nside - jr) * fact1;
+        }
+        long long t = (long long)jpll[face] * nr + ix - iy;
+        if (t < 0) t += 8 * nr;
+        const double phi = (nr == nside) ? 0.75 * halfpi * (double)t * fact1 : (0.5 * halfpi * (double)t) / (double)nr;
+        const double theta = have_sth ? atan2(sth, z) : acos(z);
+        // healpy lonlat: np.degrees = x * (180 / pi); reference: np.deg2rad = x * (pi / 180)
+        const double lon_deg = __dmul_rn(phi, 180.0 / M_PI_), lat_deg = 90.0 - __dmul_rn(theta, 180.0 / M_PI_);
+        latlon[pix] = make_float2((float)__dmul_rn(lat_deg, M_PI_ / 180.0), (float)__dmul_rn(lon_deg, M_PI_ / 180.0));
+    }
+}
+}  // namespace
+
+extern "C" int agx_healpix_nodes(int order, float* latlon, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    AGX_REQUIRE(order >= 0 && order <= 13, AGX_ERR_ARG, "agx_healpix_nodes: resolution (log2 nside) must be in 0..13, got %d", order);
+    AGX_REQUIRE(latlon != nullptr, AGX_ERR_ARG, "agx_healpix_nodes: latlon is NULL");
+    const int64_t npix = 12ll << (2 * order);
+    k_healpix_nodes<<<agx_grid(npix, 256, 8), 256, 0, stream>>>(order, npix, (float2*)latlon);
+    AGX_LAUNCH_OK();
+    agx_note_launch(1);
+    return AGX_OK;
+}

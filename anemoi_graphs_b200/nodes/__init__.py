@@ -1,6 +1,8 @@
 from .builders.from_file import LimitedAreaNPZFileNodes
 from .builders.from_file import NPZFileNodes
 from .builders.from_file import TextNodes
+from .builders.from_healpix import HEALPixNodes
+from .builders.from_healpix import LimitedAreaHEALPixNodes
 from .builders.from_refined_icosahedron import HexNodes
 from .builders.from_refined_icosahedron import LimitedAreaHexNodes
 from .builders.from_refined_icosahedron import LimitedAreaTriNodes
@@ -12,7 +14,9 @@ __all__ = [
     "NPZFileNodes",
     "TriNodes",
     "HexNodes",
+    "HEALPixNodes",
     "LatLonNodes",
+    "LimitedAreaHEALPixNodes",
     "LimitedAreaNPZFileNodes",
     "LimitedAreaTriNodes",
     "LimitedAreaHexNodes",

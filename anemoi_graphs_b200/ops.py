@@ -629,6 +629,16 @@ def multiscale_adj_edges(levels: list[tuple], x_hops: int, walk_all: bool, n_nod
     return out
 
 
+def healpix_nodes(resolution: int, device=None) -> torch.Tensor:
+    """float32 (12 * 4**resolution, 2) (lat, lon) radians of the HEALPix pixel centres in nested order
+    (``agx_healpix_nodes``; nodes/builders/from_healpix.py:61-66)."""
+    _cabi.require_cuda()
+    device = torch.device("cuda") if device is None else device
+    out = torch.empty((12 * 4 ** int(resolution), 2), dtype=torch.float32, device=device)
+    check(load_library().agx_healpix_nodes(int(resolution), ptr(out), current_stream()))
+    return out
+
+
 # ----------------------------------------------------------------------------------------------
 # spherical Voronoi cell areas
 # ----------------------------------------------------------------------------------------------

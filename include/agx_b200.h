@@ -243,6 +243,13 @@ int agx_multiscale_adj_count(int n_levels, const int32_t* const* nb /*HOST[n_lev
                              const int32_t* const* node_cell, int x_hops, int walk_all, int64_t n_nodes,
                              int32_t* counts /*DEV n_nodes*/, int32_t* scratch /*DEV*/, void* stream);
 
+/* ---- HEALPix nodes (not on the section-8 path, kept next to the other mesh generators) ---------
+ * Replaces `hp.pix2ang(2**resolution, range(npix), nest=True, lonlat=True)` + reshape_coords
+ * (nodes/builders/from_healpix.py:61-66): float32 (lat, lon) radians of the 12 * 4^resolution pixel centres in NESTED
+ * order.  healpy is not available to this build: HEALPix's published pix2loc is restated and checked against the
+ * independent RING-scheme formulas (oracle/healpix_restated.py).                                             */
+int agx_healpix_nodes(int resolution /*log2 nside*/, float* latlon /*DEV npix*2*/, void* stream);
+
 /* ---- node attribute: spherical Voronoi cell areas -------------------------------
  * Replaces `SphericalVoronoi(points, radius, centre).calculate_areas()` in SphericalAreaWeights.get_raw_values
  * (nodes/attributes.py:199-221), points = latlon_rad_to_cartesian(x) in float32 (generate/transforms.py:106-110).

@@ -25,6 +25,8 @@ product code is on that path, only ``anemoi_graphs_b200.grids`` for the syntheti
                      MultiScaleEdges) executed UNMODIFIED over ``oracle/shims/h3`` - the h3 calls answered by the
                      restatement of H3's geometry, everything else (k_ring & nodes, compact / uncompact, centre
                      children, networkx, ordering) the reference's own code.
+* ``healpix.npz``    HEALPixNodes (resolutions 1, 3) of the UNMODIFIED reference over
+                     ``oracle/shims/healpy`` (healpy's pix2ang answered by the restated HEALPix formulas).
 * ``area_weights.npz`` SphericalAreaWeights of the reference (scipy SphericalVoronoi) on an O24 grid, TriNodes(3)
                      and 3 000 random points, raw and for every norm.
 """
@@ -332,6 +334,20 @@ def make_hex() -> None:
     print("hex.npz", {k: v.shape for k, v in out.items()})
 
 
+def make_healpix() -> None:
+    from anemoi.graphs.nodes import HEALPixNodes
+    from torch_geometric.data import HeteroData
+
+    out: dict[str, np.ndarray] = {}
+    for res in (1, 3):
+        out[f"res{res}_x"] = HEALPixNodes(res, "h").update_graph(HeteroData(), {})["h"].x.numpy()
+    # LimitedAreaHEALPixNodes cannot be run: its constructor assigns ``area_mask_builder`` BEFORE calling the base
+    # constructor, which resets it to None (from_healpix.py:84-87, nodes/builders/base.py:38), so ``register_nodes``
+    # fails with AttributeError in the reference itself.
+    np.savez_compressed(OUT / "healpix.npz", **out)
+    print("healpix.npz", {k: v.shape for k, v in out.items()})
+
+
 def make_area_weights() -> None:
     from anemoi.graphs.nodes.attributes import SphericalAreaWeights, UniformWeights
     from torch_geometric.data import HeteroData
@@ -362,6 +378,6 @@ if __name__ == "__main__":
     OUT.mkdir(parents=True, exist_ok=True)
     only = sys.argv[1:]
     for name, fn in (("attr_vectors", make_attr_vectors), ("tri", make_tri), ("toy", make_toy), ("o96", make_o96),
-                     ("lam", make_lam), ("area_weights", make_area_weights), ("hex", make_hex)):  # fmt: skip
+                     ("lam", make_lam), ("area_weights", make_area_weights), ("hex", make_hex), ("healpix", make_healpix)):  # fmt: skip
         if not only or name in only:
             fn()
