@@ -675,6 +675,197 @@ class ChunkedGather:
         self.full.record_stream(self.side)
 
 
+# --------------------------------------------------------------------------------------------------
+# VMM push (opt-in, AGX_VMM_PUSH=1): the exchange over peer-mapped memory, by the copy engines
+# --------------------------------------------------------------------------------------------------
+VMM_PUSH = __import__("os").environ.get("AGX_VMM_PUSH", "0") == "1"
+
+
+class _VmmHeap:
+    """One persistent staging buffer per rank, allocated with the driver's virtual-memory API (cuMemCreate), exported
+    as a POSIX file descriptor, passed to every other rank of the box over Unix sockets and mapped there for access
+    from THAT rank's device (cuMemMap + cuMemSetAccess).  A copy into such a mapping is a device-to-device DMA over
+    NVLink: 771 GB/s per rank with both ranks of a pair pushing (tools/vmm_probe.py), against 26 GB/s through
+    PyTorch's legacy CUDA-IPC tensor sharing (tools/ipc_probe.py); mapping a 1 GiB peer allocation takes 0.3 ms and
+    is done once."""
+
+    def __init__(self) -> None:
+        self.size = 0
+        self.own = None
+        self.own_va = 0
+        self.peer_va: dict[int, int] = {}
+        self._peer_handles: list = []
+
+    @staticmethod
+    def _ck(res):
+        from cuda.bindings import driver as cu
+
+        if res[0] != cu.CUresult.CUDA_SUCCESS:
+            raise _cabi.AgxError(f"CUDA driver call failed: {res[0]}")
+        return res[1] if len(res) == 2 else None
+
+    def _map(self, handle, size: int, device_index: int) -> int:
+        from cuda.bindings import driver as cu
+
+        va = self._ck(cu.cuMemAddressReserve(size, 0, 0, 0))
+        self._ck(cu.cuMemMap(va, size, 0, handle, 0))
+        acc = cu.CUmemAccessDesc()
+        acc.location.type = cu.CUmemLocationType.CU_MEM_LOCATION_TYPE_DEVICE
+        acc.location.id = device_index
+        acc.flags = cu.CUmemAccess_flags.CU_MEM_ACCESS_FLAGS_PROT_READWRITE
+        self._ck(cu.cuMemSetAccess(va, size, [acc], 1))
+        return int(va)
+
+    def ensure(self, nbytes: int, device: torch.device) -> None:
+        """Collective: every rank calls it with the same ``nbytes``."""
+        if nbytes <= self.size:
+            return
+        import os
+        import socket
+        import time
+
+        import torch.distributed as dist
+        from cuda.bindings import driver as cu
+
+        rank, w = world()
+        dev = device.index if device.index is not None else torch.cuda.current_device()
+        torch.cuda.synchronize()
+        dist.barrier()  # nobody still uses the old buffers
+        fd_type = cu.CUmemAllocationHandleType.CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR
+        prop = cu.CUmemAllocationProp()
+        prop.type = cu.CUmemAllocationType.CU_MEM_ALLOCATION_TYPE_PINNED
+        prop.location.type = cu.CUmemLocationType.CU_MEM_LOCATION_TYPE_DEVICE
+        prop.location.id = dev
+        prop.requestedHandleTypes = fd_type
+        gran = self._ck(cu.cuMemGetAllocationGranularity(prop, cu.CUmemAllocationGranularity_flags.CU_MEM_ALLOC_GRANULARITY_MINIMUM))
+        size = (int(nbytes * 1.25) + gran - 1) // gran * gran
+        # (the previous, smaller buffers stay mapped until the process ends: growth is rare and they are small)
+        self.own = self._ck(cu.cuMemCreate(size, prop, 0))
+        self.own_va = self._map(self.own, size, dev)
+        fd = int(self._ck(cu.cuMemExportToShareableHandle(self.own, fd_type, 0)))
+        # every rank listens, then sends its descriptor to every other rank (SCM_RIGHTS)
+        tag = f"{os.environ.get('MASTER_PORT', '0')}_{os.getppid()}_{size}"
+        path = lambda r: f"/tmp/agx_vmm_{tag}_{r}.sock"  # noqa: E731
+        if os.path.exists(path(rank)):
+            os.unlink(path(rank))
+        srv = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+        srv.bind(path(rank))
+        srv.listen(w)
+        dist.barrier()
+        outgoing = []
+        for p in range(w):
+            if p == rank:
+                continue
+            c = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+            for _ in range(200):
+                try:
+                    c.connect(path(p))
+                    break
+                except OSError:
+                    time.sleep(0.01)
+            socket.send_fds(c, [bytes([rank])], [fd])
+            outgoing.append(c)
+        self.peer_va = {}
+        for _ in range(w - 1):
+            conn, _addr = srv.accept()
+            msg, fds, _flags, _a = socket.recv_fds(conn, 16, 1)
+            handle = self._ck(cu.cuMemImportFromShareableHandle(fds[0], fd_type))
+            self._peer_handles.append(handle)
+            self.peer_va[int(msg[0])] = self._map(handle, size, dev)
+            os.close(fds[0])
+            conn.close()
+        dist.barrier()
+        for c in outgoing:
+            c.close()
+        srv.close()
+        os.unlink(path(rank))
+        os.close(fd)
+        self.size = size
+
+
+_vmm_heap = _VmmHeap()
+
+
+class VmmGather:
+    """``ChunkedGather`` with the copy engines instead of a collective: every finished chunk of the rank's block is
+    pushed into the same byte range of every peer's staging buffer (``_VmmHeap``) on a second stream while the main
+    stream searches the next chunk; after one stream-ordered barrier each rank copies the other ranks' blocks from
+    its own staging buffer into ``full``.  No SMs are used by the exchange, so - unlike an NCCL kernel - it runs
+    while the persistent search kernels occupy the whole GPU.  Opt-in (AGX_VMM_PUSH=1): validated at N = 2 only."""
+
+    def __init__(self, full: torch.Tensor, counts: list[list[int]]) -> None:
+        import torch.distributed as dist
+
+        self.rank, self.w = world()
+        self.full = full
+        self.counts = counts
+        self.offsets = []
+        col = 0
+        for r in range(self.w):
+            row = []
+            for c in counts[r]:
+                row.append(col)
+                col += c
+            self.offsets.append(row)
+        assert col == full.shape[1] and full.is_contiguous()
+        self.row_bytes = int(full.shape[1]) * full.element_size()
+        _vmm_heap.ensure(int(full.shape[0]) * self.row_bytes, full.device)
+        self.side = torch.cuda.Stream(device=full.device, priority=-1)
+        self._token = torch.zeros(1, dtype=torch.int32, device=full.device)
+        dist.all_reduce(self._token)  # every rank has finished reading its staging buffer from the previous build
+        start = torch.cuda.Event()
+        start.record()
+        self.side.wait_event(start)
+
+    def mark(self):
+        ready = torch.cuda.Event()
+        ready.record()
+        return ready
+
+    def chunk_done(self, c: int, ready=None) -> None:
+        from cuda.bindings import driver as cu
+
+        n, o = self.counts[self.rank][c], self.offsets[self.rank][c]
+        if n == 0:
+            return
+        if ready is None:
+            ready = self.mark()
+        self.side.wait_event(ready)
+        es = self.full.element_size()
+        for step in range(1, self.w):  # a different first peer on every rank: all links busy at once
+            peer = (self.rank + step) % self.w
+            for row in range(int(self.full.shape[0])):
+                off = row * self.row_bytes + o * es
+                _VmmHeap._ck(cu.cuMemcpyDtoDAsync(_vmm_heap.peer_va[peer] + off, self.full.data_ptr() + off, n * es, self.side.cuda_stream))
+
+    def finish(self) -> None:
+        import torch.distributed as dist
+        from cuda.bindings import driver as cu
+
+        done = torch.cuda.Event()
+        done.record(self.side)
+        main = torch.cuda.current_stream()
+        main.wait_event(done)
+        dist.all_reduce(self._token)  # stream-ordered barrier: every rank's pushes have landed
+        es = self.full.element_size()
+        for r in range(self.w):
+            n = sum(self.counts[r])
+            if r == self.rank or n == 0:
+                continue
+            o = self.offsets[r][0]
+            for row in range(int(self.full.shape[0])):
+                off = row * self.row_bytes + o * es
+                _VmmHeap._ck(cu.cuMemcpyDtoDAsync(self.full.data_ptr() + off, _vmm_heap.own_va + off, n * es, main.cuda_stream))
+        self.full.record_stream(self.side)
+
+
+def make_gather(full: torch.Tensor, counts: list[list[int]]):
+    """The exchange object of a sharded edge set: ``VmmGather`` when opted in (AGX_VMM_PUSH=1), else ``ChunkedGather``."""
+    if VMM_PUSH and full.is_cuda:
+        return VmmGather(full, counts)
+    return ChunkedGather(full, counts)
+
+
 def all_gather_count_rows(mine: list[int], device: torch.device) -> list[list[int]]:
     """Every rank's list of per-chunk counts: (W x C) nested list."""
     import torch.distributed as dist

@@ -267,10 +267,33 @@ class KNNEdges(BaseEdgeBuilder, NodeMaskingMixin):
         lo, hi = _device.shard_range(nq, rank, w)
         with ops.NeighbourIndex(src, hint_k=k) as index:
             out = torch.empty((2, nq * k), dtype=torch.int32, device=dst.device)
-            # equal blocks: one in-place NCCL all-gather after the search (640 GB/s per rank; chunking the search to
-            # overlap the exchange was measured and does not pay: the persistent search kernel leaves no room for
-            # the collective's CTAs until it ends - 40 M queries, N = 2: 4.8 ms chunked against 4.5 ms)
-            index.knn(dst[lo:hi], k, dst_base=lo, stats=self.stats, out=out, out_offset=lo * k)
+            masked = src_sel is not None or dst_sel is not None
+            if w > 1 and not masked and _device.VMM_PUSH:
+                # opt-in: chunks pushed into peer-mapped staging buffers by the copy engines while the next chunk is
+                # searched (device.VmmGather)
+                n_chunks = _device.n_query_chunks(nq, w)
+                ranges = [_device.query_chunks(*_device.shard_range(nq, r, w), n_chunks) for r in range(w)]
+                gather = _device.make_gather(out, [[(b - a) * k for a, b in rr] for rr in ranges])
+                lib, marks = ops.load_library(), []
+                try:
+                    for c, (a, b) in enumerate(ranges[rank]):
+                        if b > a:
+                            index.knn(dst[a:b], k, dst_base=a, stats=self.stats, out=out, out_offset=a * k)
+                            if c == 0:  # the first chunk decided the query order (one sync): pin it for the rest
+                                lib.agx_set_query_order_mode(lib.agx_last_query_order())
+                        marks.append(gather.mark())
+                        if c > 0:
+                            gather.chunk_done(c - 1, marks[c - 1])
+                    gather.chunk_done(n_chunks - 1, marks[-1])
+                finally:
+                    lib.agx_set_query_order_mode(-1)
+                gather.finish()
+                w = 1  # complete on every rank
+            else:
+                # equal blocks: one in-place NCCL all-gather after the search (640 GB/s per rank; chunking the search
+                # to overlap an NCCL exchange was measured and does not pay: the persistent search kernel leaves no
+                # room for the collective's CTAs until it ends - 40 M queries, N = 2: 4.8 ms chunked against 4.5 ms)
+                index.knn(dst[lo:hi], k, dst_base=lo, stats=self.stats, out=out, out_offset=lo * k)
         if w > 1:
             counts = [(b - a) * k for a, b in (_device.shard_range(nq, r, w) for r in range(w))]
             out = _gather_blocks(out, counts, rank, src_sel is not None or dst_sel is not None)
@@ -350,7 +373,7 @@ class CutOffEdges(BaseEdgeBuilder, NodeMaskingMixin):
                 counts = [sum(r) for r in rows]
                 out = torch.empty((2, sum(counts)), dtype=torch.int32, device=dst.device)
                 base = sum(counts[:rank])
-                gather = _device.ChunkedGather(out, rows)
+                gather = _device.make_gather(out, rows)
                 lib, marks = ops.load_library(), []
                 lib.agx_set_query_order_mode(lib.agx_last_query_order())  # as the count pass decided: no more syncs
                 try:
