@@ -77,6 +77,8 @@ class BaseNodeAttribute(ABC):
         """Get the nodes attribute: tensor of shape (N, M), on the device ``graph[nodes_name].x`` lives on."""
         nodes = graph[nodes_name]
         out = self.post_process(self.get_raw_values(nodes, **kwargs))
+        if nodes["x"].is_cuda and not out.is_cuda:  # masks read from files
+            out = out.to(nodes["x"].device)
         res = _device.like_input(out, nodes["x"])
         _device.maybe_flush()
         return res
@@ -169,21 +171,33 @@ class BooleanBaseNodeAttribute(BaseNodeAttribute, ABC):
 
 
 class NonmissingZarrVariable(BooleanBaseNodeAttribute):
-    """Mask of valid values of a Zarr dataset variable - needs anemoi-datasets (not on this path)."""
+    """Mask of valid (not missing) values of a Zarr dataset variable in the first timestep
+    (nodes/attributes.py:229-258); reads the dataset through anemoi-datasets."""
 
     def __init__(self, variable: str) -> None:
         super().__init__()
         self.variable = variable
 
     def get_raw_values(self, nodes, **kwargs) -> torch.Tensor:
-        raise NotImplementedError("NonmissingZarrVariable needs anemoi-datasets, which is outside this package's scope.")
+        from .builders.from_file import open_dataset
+
+        assert (
+            nodes["node_type"] == "ZarrDatasetNodes"
+        ), f"{self.__class__.__name__} can only be used with ZarrDatasetNodes."
+        ds = open_dataset(nodes["_dataset"], select=self.variable)[0].squeeze()
+        return torch.as_tensor(~np.isnan(np.asarray(ds)))
 
 
 class CutOutMask(BooleanBaseNodeAttribute):
-    """Cut out mask - needs anemoi-datasets (not on this path)."""
+    """Cut out mask (nodes/attributes.py:261-268): True for the limited-area part of a cutout dataset."""
 
     def get_raw_values(self, nodes, **kwargs) -> torch.Tensor:
-        raise NotImplementedError("CutOutMask needs anemoi-datasets, which is outside this package's scope.")
+        from .builders.from_file import open_dataset
+
+        assert isinstance(nodes["_dataset"], dict), "The 'dataset' attribute must be a dictionary."
+        assert "cutout" in nodes["_dataset"], "The 'dataset' attribute must contain a 'cutout' key."
+        num_lam, num_other = open_dataset(nodes["_dataset"]).grids
+        return torch.as_tensor(np.array([True] * num_lam + [False] * num_other, dtype=bool))
 
 
 class BooleanOperation(BooleanBaseNodeAttribute, ABC):
@@ -202,9 +216,9 @@ class BooleanOperation(BooleanBaseNodeAttribute, ABC):
             assert (
                 attributes.dtype == torch.bool
             ), f"The mask attribute '{mask}' must be a boolean but is {attributes.dtype}."
-            return attributes.to(_device.compute_device())
+            return attributes.to(nodes["x"].device)
 
-        return mask.get_raw_values(nodes, **kwargs)
+        return mask.get_raw_values(nodes, **kwargs).to(nodes["x"].device)
 
     @abstractmethod
     def reduce_op(self, masks: list[torch.Tensor]) -> torch.Tensor: ...

@@ -1,7 +1,7 @@
 """Nodes from files - input adaptors (/root/reference/src/anemoi/graphs/nodes/builders/from_file.py).
 
-Pure I/O; kept so unchanged recipes can feed the GPU edge path.  ``ZarrDatasetNodes`` needs
-``anemoi.datasets`` (not in this image) and is out of scope."""
+Pure I/O; kept so unchanged recipes can feed the GPU edge path.  ``ZarrDatasetNodes`` imports ``anemoi.datasets``
+when it is used (the package is not in this image; the reference imports it at module load)."""
 
 from __future__ import annotations
 
@@ -15,6 +15,49 @@ from ...generate.masks import KNNAreaMaskBuilder
 from .base import BaseNodeBuilder
 
 LOGGER = logging.getLogger(__name__)
+
+
+def open_dataset(*args, **kwargs):
+    """``anemoi.datasets.open_dataset``, imported on first use."""
+    try:
+        from anemoi.datasets import open_dataset as _open
+    except ImportError as err:  # pragma: no cover - depends on the environment
+        raise ImportError(
+            "ZarrDatasetNodes needs the anemoi-datasets package (`pip install anemoi-datasets`), as in the reference."
+        ) from err
+    return _open(*args, **kwargs)
+
+
+class ZarrDatasetNodes(BaseNodeBuilder):
+    """Nodes from Zarr dataset (from_file.py:28-63).
+
+    Attributes
+    ----------
+    dataset : str | DictConfig
+        The dataset.
+    """
+
+    def __init__(self, dataset, name: str) -> None:
+        LOGGER.info("Reading the dataset from %s.", dataset)
+        self.dataset = dataset if isinstance(dataset, str) else _to_container(dataset)
+        super().__init__(name)
+        self.hidden_attributes = BaseNodeBuilder.hidden_attributes | {"dataset"}
+
+    def get_coordinates(self) -> torch.Tensor:
+        """float32 (num_nodes, 2) coordinates of the nodes, in radians."""
+        dataset = open_dataset(self.dataset)
+        return self.reshape_coords(dataset.latitudes, dataset.longitudes)
+
+
+def _to_container(config):
+    try:  # pragma: no cover - omegaconf is not in this image
+        from omegaconf import DictConfig, OmegaConf
+
+        if isinstance(config, DictConfig):
+            return OmegaConf.to_container(config)
+    except ImportError:
+        pass
+    return dict(config) if hasattr(config, "items") else config
 
 
 class TextNodes(BaseNodeBuilder):

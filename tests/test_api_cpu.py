@@ -186,3 +186,43 @@ def test_graph_descriptor_on_a_saved_graph(tmp_path, capsys):
     d.describe()
     out = capsys.readouterr().out
     assert "Nodes summary" in out and "Edges summary" in out and "Graph ready." in out
+
+
+class _MockZarrDataset:
+    """reference tests/conftest.py MockZarrDataset."""
+
+    def __init__(self, latitudes, longitudes, grids=None):
+        self.latitudes = latitudes
+        self.longitudes = longitudes
+        self.num_nodes = len(latitudes)
+        if grids is not None:
+            self.grids = grids
+
+
+def test_zarr_dataset_nodes_and_dataset_masks(monkeypatch):
+    """reference tests/nodes/test_zarr.py + test_cutout_nodes.py: the dataset-backed node builder and masks are pure
+    input adaptors over ``anemoi.datasets.open_dataset`` (mocked, as in the reference's tests)."""
+    from anemoi_graphs_b200.graph import HeteroData
+    from anemoi_graphs_b200.nodes import ZarrDatasetNodes
+    from anemoi_graphs_b200.nodes.attributes import BooleanAndMask, BooleanNot, BooleanOrMask, CutOutMask
+    from anemoi_graphs_b200.nodes.builders import from_file
+
+    lats, lons = [-0.15, 0, 0.15], [0, 0.25, 0.5, 0.75]
+    coords = 2 * np.pi * np.array([[lat, lon] for lat in lats for lon in lons])
+    ds = _MockZarrDataset(coords[:, 0], coords[:, 1], grids=(4, 8))
+    monkeypatch.setattr(from_file, "open_dataset", lambda *a, **k: ds)
+    builder = ZarrDatasetNodes({"cutout": ["lam.zarr", "global.zarr"]}, name="test_nodes")
+    graph = builder.update_graph(HeteroData(), {})
+    x = graph["test_nodes"].x
+    assert x.dtype == torch.float32 and x.shape == (12, 2) and graph["test_nodes"].node_type == "ZarrDatasetNodes"
+    np.testing.assert_allclose(x.numpy(), np.deg2rad(coords), rtol=1e-6)
+    assert graph["test_nodes"]["_dataset"] == {"cutout": ["lam.zarr", "global.zarr"]}
+    mask = CutOutMask().compute(graph, "test_nodes")
+    assert mask.dtype == torch.bool and mask.shape == (12, 1) and mask[:, 0].tolist() == [True] * 4 + [False] * 8
+    graph["test_nodes"]["interior"] = torch.tensor([True, False] * 6)
+    both = BooleanAndMask([CutOutMask(), "interior"]).compute(graph, "test_nodes")[:, 0].tolist()
+    assert both == [True, False, True, False] + [False] * 8
+    either = BooleanOrMask([BooleanNot(CutOutMask()), "interior"]).compute(graph, "test_nodes")[:, 0].tolist()
+    assert either == [True, False, True, False] + [True] * 8
+    with pytest.raises(AssertionError):
+        BooleanNot(["interior", "interior"]).compute(graph, "test_nodes")
