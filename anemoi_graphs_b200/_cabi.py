@@ -14,6 +14,7 @@ import torch
 
 LIB_PATH = Path(__file__).resolve().parent / "lib" / "libagx_b200.so"
 
+ABI_VERSION = 1
 AGX_OK = 0
 AGX_ERR_CUDA = -1
 AGX_ERR_ARG = -2
@@ -116,8 +117,8 @@ def load_library(path: Path | None = None) -> ctypes.CDLL:
         fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
         fn.restype = restype
         fn.argtypes = argtypes
-    if lib.agx_abi_version() != 1:
-        raise RuntimeError(f"{p}: ABI version {lib.agx_abi_version()} != 1; rebuild the library")
+    if lib.agx_abi_version() != ABI_VERSION:
+        raise RuntimeError(f"{p}: ABI version {lib.agx_abi_version()} != {ABI_VERSION}; rebuild the library")
     if path is None:
         _lib = lib
     return lib

@@ -55,22 +55,56 @@ class GraphCreator:
 
             edges.append(edges_cfg)
         self.config.edges = edges
+        self._validate()
+
+    # limits of the CUDA path: found here, before any kernel runs, instead of mid-build
+    MAX_KNN_K = 64
+    MAX_X_HOPS = 8
+
+    def _validate(self) -> None:
+        """Resolve every ``_target_`` of the recipe (an unknown or unbuilt class - the ICON builders,
+        ``PlanarAreaWeights`` - raises ImportError now) and check the limits of the kernels."""
+        from .config import resolve_target
+
+        def walk(cfg):
+            if isinstance(cfg, dict):
+                if "_target_" in cfg:
+                    resolve_target(cfg["_target_"])
+                for v in cfg.values():
+                    walk(v)
+            elif isinstance(cfg, (list, tuple)):
+                for v in cfg:
+                    walk(v)
+
+        walk(self.config.get("nodes", {}))
+        walk(self.config.get("edges", []))
+        walk(self.config.get("post_processors", []))
+        for edges_cfg in self.config.get("edges", []):
+            for b in edges_cfg.get("edge_builders", []):
+                target = str(b.get("_target_", ""))
+                k, hops = b.get("num_nearest_neighbours"), b.get("x_hops")
+                if target.endswith(".KNNEdges") and isinstance(k, int) and k > self.MAX_KNN_K:
+                    raise NotImplementedError(f"KNNEdges: num_nearest_neighbours = {k} > {self.MAX_KNN_K} is not built")
+                if target.endswith(".MultiScaleEdges") and isinstance(hops, int) and hops > self.MAX_X_HOPS:
+                    raise NotImplementedError(f"MultiScaleEdges: x_hops = {hops} > {self.MAX_X_HOPS} is not built")
 
     def update_graph(self, graph):
         """Instantiate the node and edge builders of the recipe and apply them to the graph (create.py:62-92)."""
         with _device.deferred():
             for nodes_name, nodes_cfg in self.config.get("nodes", {}).items():
-                graph = instantiate(nodes_cfg.node_builder, name=nodes_name).update_graph(
-                    graph, attrs_config=nodes_cfg.get("attributes", {})
-                )
+                node_builder = instantiate(nodes_cfg.node_builder, name=nodes_name)
+                _device.flush_for(node_builder)  # a foreign (reference-style) plugin reads complete host tensors
+                graph = node_builder.update_graph(graph, attrs_config=nodes_cfg.get("attributes", {}))
 
             for edges_cfg in self.config.get("edges", {}):
                 for edge_builder_cfg in edges_cfg.edge_builders:
                     edge_builder = instantiate(
                         edge_builder_cfg, source_name=edges_cfg.source_name, target_name=edges_cfg.target_name
                     )
+                    _device.flush_for(edge_builder)
                     graph = edge_builder.update_graph(graph, attrs_config=None)
 
+                _device.flush_for(edge_builder)
                 graph = edge_builder.register_attributes(graph, edges_cfg.get("attributes", {}))
 
         return graph
@@ -89,7 +123,9 @@ class GraphCreator:
     def post_process(self, graph):
         """Apply the configured post-processors, in order (create.py:116-140)."""
         for processor in self.config.get("post_processors", []):
-            graph = instantiate(processor).update_graph(graph)
+            processor = instantiate(processor)
+            _device.flush_for(processor)
+            graph = processor.update_graph(graph)
 
         return graph
 

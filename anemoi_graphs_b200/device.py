@@ -113,6 +113,19 @@ def wait_for(t: torch.Tensor | None) -> None:
         work.wait()
 
 
+def is_device_aware(obj) -> bool:
+    """One of this package's own builders / attributes / processors (they work from the cached device copies and
+    know about provisional numbering).  Anything else - a reference-style plugin named by a recipe ``_target_`` - may
+    read ``graph[n].x`` / ``edge_index`` on the host, so callers ``flush()`` before handing the graph to it."""
+    return bool(getattr(type(obj), "_agx_device_aware", False))
+
+
+def flush_for(obj) -> None:
+    """``flush()`` unless ``obj`` is one of the package's device-aware classes."""
+    if not is_device_aware(obj):
+        flush()
+
+
 def maybe_flush() -> None:
     if _defer_depth == 0:
         flush()
@@ -318,6 +331,9 @@ class Provisional:
         self.future = _pool().submit(work)
         _provisionals.append(self)
 
+    def __getstate__(self):  # never pickled with its worker future / pinned buffers
+        return {"done": True, "n": self.n}
+
     def attach(self, nodes, state: NodeState) -> None:
         self.nodes, self.state = nodes, state
         state.prov = self
@@ -404,15 +420,46 @@ def active_provisional(nodes):
     return st.prov if isinstance(st, NodeState) else None
 
 
+# Bookkeeping about a freshly built CUDA edge_index (which rows are provisional, a pending tie re-decision, which
+# columns this rank produced).  It lives in a side table keyed by the tensor's identity, NOT on the tensor: torch
+# pickles a tensor's ``__dict__``, and a device-resident graph stores these very tensors, so attributes holding a
+# ``Provisional`` (a ``Future``, pinned buffers) would break ``torch.save(graph)`` and keep the buffers alive.
+class EdgeMeta:
+    __slots__ = ("prov", "fixup", "local")
+
+    def __init__(self) -> None:
+        self.prov = (None, None)  # (source row, target row): the Provisional whose numbering the row is in
+        self.fixup = None  # Provisional that still has to re-decide KNN ties of this edge list
+        self.local = None  # (lo, hi, counts): this rank's own columns of a sharded edge list
+
+
+_edge_meta: dict[int, tuple] = {}
+
+
+def edge_meta(edge_index: torch.Tensor, create: bool = False) -> EdgeMeta | None:
+    import weakref
+
+    key = id(edge_index)
+    hit = _edge_meta.get(key)
+    if hit is not None and hit[0]() is edge_index:
+        return hit[1]
+    if not create:
+        return None
+    meta = EdgeMeta()
+    _edge_meta[key] = (weakref.ref(edge_index, lambda _r, key=key: _edge_meta.pop(key, None)), meta)
+    return meta
+
+
 def tag_rows(edge_index: torch.Tensor, src_prov, dst_prov) -> torch.Tensor:
     """Mark which rows of a freshly built CUDA (2, E) edge_index are in provisional numbering."""
     if src_prov is not None or dst_prov is not None:
-        edge_index._agx_prov = (src_prov, dst_prov)
+        edge_meta(edge_index, create=True).prov = (src_prov, dst_prov)
     return edge_index
 
 
 def row_tags(edge_index: torch.Tensor) -> tuple:
-    tags = getattr(edge_index, "_agx_prov", (None, None))
+    meta = edge_meta(edge_index)
+    tags = meta.prov if meta is not None else (None, None)
     return tuple(p if (p is not None and not p.done) else None for p in tags)
 
 
@@ -743,42 +790,52 @@ class _VmmHeap:
         self.own = self._ck(cu.cuMemCreate(size, prop, 0))
         self.own_va = self._map(self.own, size, dev)
         fd = int(self._ck(cu.cuMemExportToShareableHandle(self.own, fd_type, 0)))
-        # every rank listens, then sends its descriptor to every other rank (SCM_RIGHTS)
-        tag = f"{os.environ.get('MASTER_PORT', '0')}_{os.getppid()}_{size}"
-        path = lambda r: f"/tmp/agx_vmm_{tag}_{r}.sock"  # noqa: E731
-        if os.path.exists(path(rank)):
-            os.unlink(path(rank))
+        # every rank listens, then sends its descriptor to every other rank (SCM_RIGHTS).  The sockets live in the
+        # abstract namespace under a random token that rank 0 draws and broadcasts through the process group, the
+        # peer is checked with SO_PEERCRED (same user) and must name a rank nobody else has claimed
+        import secrets
+        import struct
+
+        token = [secrets.token_hex(16) if rank == 0 else None]
+        dist.broadcast_object_list(token, src=0)
+        name = lambda r: f"\0agx_vmm_{token[0]}_{r}"  # noqa: E731
         srv = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
-        srv.bind(path(rank))
+        srv.bind(name(rank))
         srv.listen(w)
+        srv.settimeout(60.0)
         dist.barrier()
         outgoing = []
         for p in range(w):
             if p == rank:
                 continue
             c = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
-            for _ in range(200):
+            for attempt in range(200):
                 try:
-                    c.connect(path(p))
+                    c.connect(name(p))
                     break
                 except OSError:
+                    if attempt == 199:
+                        raise _cabi.AgxError(f"VMM exchange: rank {rank} cannot reach rank {p}'s descriptor socket") from None
                     time.sleep(0.01)
             socket.send_fds(c, [bytes([rank])], [fd])
             outgoing.append(c)
         self.peer_va = {}
         for _ in range(w - 1):
             conn, _addr = srv.accept()
+            _pid, uid, _gid = struct.unpack("3i", conn.getsockopt(socket.SOL_SOCKET, socket.SO_PEERCRED, struct.calcsize("3i")))
             msg, fds, _flags, _a = socket.recv_fds(conn, 16, 1)
+            peer = int(msg[0]) if msg else -1
+            if uid != os.getuid() or not (0 <= peer < w) or peer == rank or peer in self.peer_va or len(fds) != 1:
+                raise _cabi.AgxError(f"VMM exchange: unexpected peer (uid {uid}, rank byte {peer}) on rank {rank}'s socket")
             handle = self._ck(cu.cuMemImportFromShareableHandle(fds[0], fd_type))
             self._peer_handles.append(handle)
-            self.peer_va[int(msg[0])] = self._map(handle, size, dev)
+            self.peer_va[peer] = self._map(handle, size, dev)
             os.close(fds[0])
             conn.close()
         dist.barrier()
         for c in outgoing:
             c.close()
         srv.close()
-        os.unlink(path(rank))
         os.close(fd)
         self.size = size
 

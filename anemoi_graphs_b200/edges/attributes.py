@@ -29,6 +29,8 @@ def _check_norm(norm) -> None:
 class BaseEdgeAttribute(ABC):
     """Base class for edge attributes."""
 
+    _agx_device_aware = True
+
     def __init__(self, norm: str | None = None) -> None:
         self.norm = norm
 
@@ -113,6 +115,9 @@ def compute_attributes(graph, edges_name: tuple[str, str, str], attrs: dict) -> 
     out: dict = {}
     for k, a in attrs.items():
         if k not in ours:
+            # a foreign (reference-style plugin) attribute may read ``x`` / ``edge_index`` on the host: give every
+            # provisional node set its final order and wait for the pending device->host copies first
+            _device.flush()
             out[k] = a.compute(graph, edges_name)
     if not ours:
         return out
@@ -125,7 +130,8 @@ def compute_attributes(graph, edges_name: tuple[str, str, str], attrs: dict) -> 
     # A row of the edge list may still be in the provisional numbering of its node set (device.Provisional): the
     # attributes depend on coordinates only, so they are evaluated right away against the matching (provisional)
     # node records.  Anything else - final rows against a provisional node set - needs the final order first.
-    pending = getattr(edge_index, "_agx_fixup", None)
+    meta = _device.edge_meta(edge_index)
+    pending = meta.fixup if meta is not None else None
     if pending is not None:  # KNN edges whose index-order ties are re-decided when the node order resolves
         pending.resolve()
     tags = _device.row_tags(edge_index)
@@ -142,7 +148,7 @@ def compute_attributes(graph, edges_name: tuple[str, str, str], attrs: dict) -> 
     lengths = [(k, a) for k, a in ours.items() if isinstance(a, EdgeLength)]
     dirs = [(k, a) for k, a in ours.items() if isinstance(a, EdgeDirection)]
     _, w = _device.world()
-    local = getattr(edge_index, "_agx_local", None)  # set by a sharded builder: this rank's own columns
+    local = meta.local if meta is not None else None  # set by a sharded builder: this rank's own columns
     while lengths or dirs:
         kl = lengths.pop(0) if lengths else None
         kd = dirs.pop(0) if dirs else None

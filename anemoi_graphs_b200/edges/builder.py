@@ -19,7 +19,6 @@ from __future__ import annotations
 
 import logging
 from abc import ABC
-from abc import abstractmethod
 
 import numpy as np
 import torch
@@ -55,9 +54,24 @@ class BaseEdgeBuilder(ABC):
         """Name of the edge subgraph."""
         return self.source_name, "to", self.target_name
 
-    @abstractmethod
+    _agx_device_aware = True
+
     def compute_edge_index(self, source_nodes, target_nodes) -> torch.Tensor:
-        """CUDA int32 (2, E): row 0 source index, row 1 target index (edges/builder.py:86-87)."""
+        """CUDA int32 (2, E): row 0 source index, row 1 target index (edges/builder.py:86-87).
+
+        The package's builders override this.  A builder written for the REFERENCE's plugin contract - a subclass that
+        provides ``get_adjacency_matrix(source_nodes, target_nodes)`` returning a scipy COO matrix (targets x sources,
+        edges/builder.py:63) - works unchanged: its matrix is turned into the edge list the way the reference does
+        (``edge_index = [col; row]``, :86-87) and uploaded."""
+        if type(self).get_adjacency_matrix is BaseEdgeBuilder.get_adjacency_matrix:
+            raise NotImplementedError(
+                f"{type(self).__name__} must implement compute_edge_index (device) or get_adjacency_matrix (reference contract)."
+            )
+        _device.flush()  # the plugin reads host tensors
+        adjmat = self.get_adjacency_matrix(source_nodes, target_nodes)
+        adjmat = adjmat.tocoo() if hasattr(adjmat, "tocoo") else adjmat
+        edge_index = torch.from_numpy(np.stack([adjmat.col, adjmat.row], axis=0).astype(np.int32))
+        return edge_index.to(_device.compute_device())
 
     def get_adjacency_matrix(self, source_nodes, target_nodes):
         """scipy COO (targets x sources) connectivity - the reference's intermediate form
@@ -183,13 +197,13 @@ class NodeMaskingMixin:
 
 def _gather_blocks(full: torch.Tensor, counts: list[int], rank: int, masked: bool) -> torch.Tensor:
     """All-gather the per-rank column blocks of ``full`` (2, E).  Without node masks the exchange is asynchronous
-    and ``full`` remembers which columns this rank produced itself (``_agx_local``), so the attribute kernel can
+    and ``full`` remembers which columns this rank produced itself (``device.edge_meta(full).local``), so the attribute kernel can
     start on them while the other ranks' blocks are still in flight."""
     if masked:
         return _device.all_gather_v(full, counts, dim=1)  # undo_masking reads every column next
     _device.all_gather_v(full, counts, dim=1, async_op=True)
     lo = sum(counts[:rank])
-    full._agx_local = (lo, lo + counts[rank], list(counts))
+    _device.edge_meta(full, create=True).local = (lo, lo + counts[rank], list(counts))
     return full
 
 
@@ -235,7 +249,7 @@ class KNNEdges(BaseEdgeBuilder, NodeMaskingMixin):
         """Runs inside ``Provisional.resolve``: row 0 of ``out`` already carries final source labels."""
         with ops.NeighbourIndex(prov.x_final, hint_k=k) as index:
             index.knn_redecide(queries, k, out, flags)
-        out._agx_fixup = None
+        _device.edge_meta(out, create=True).fixup = None
 
     def compute_edge_index(self, source_nodes, target_nodes) -> torch.Tensor:
         src, dst, src_sel, dst_sel = self.get_node_coordinates(source_nodes, target_nodes)
@@ -261,7 +275,7 @@ class KNNEdges(BaseEdgeBuilder, NodeMaskingMixin):
             with ops.NeighbourIndex(src, hint_k=k) as index:
                 out = index.knn(dst, k, stats=self.stats, tie_flags=flags)
             out = _device.tag_rows(out, src_prov, None)
-            out._agx_fixup = src_prov
+            _device.edge_meta(out, create=True).fixup = src_prov
             src_prov.add_fixup(lambda prov, out=out, flags=flags, dst=dst, k=k: self._redecide_ties(prov, out, flags, dst, k))
             return out
         lo, hi = _device.shard_range(nq, rank, w)
@@ -389,7 +403,7 @@ class CutOffEdges(BaseEdgeBuilder, NodeMaskingMixin):
                 finally:
                     lib.agx_set_query_order_mode(-1)
                 gather.finish()
-                out._agx_local = (base, base + counts[rank], list(counts))
+                _device.edge_meta(out, create=True).local = (base, base + counts[rank], list(counts))
                 w = 1  # complete on every rank
             else:
                 counts = _device.all_gather_counts(total, dst.device) if w > 1 else [total]

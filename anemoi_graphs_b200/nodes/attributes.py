@@ -57,6 +57,8 @@ _TORCH_DTYPES = {"float32": torch.float32, "float64": torch.float64, "float16": 
 class BaseNodeAttribute(ABC):
     """Base class for the weights of the nodes."""
 
+    _agx_device_aware = True
+
     def __init__(self, norm: str | None = None, dtype: str = "float32") -> None:
         self.norm = norm
         self.dtype = dtype
@@ -225,7 +227,18 @@ class BooleanOperation(BooleanBaseNodeAttribute, ABC):
 
     def get_raw_values(self, nodes, **kwargs) -> torch.Tensor:
         mask_values = [BooleanOperation.get_mask_values(mask, nodes, **kwargs) for mask in self.masks]
-        return self.reduce_op(mask_values)
+        # a stored attribute is (N, 1), a nested mask object's raw values are (N,): mixing them would broadcast to
+        # (N, N).  One shape for all; anything that is not one value per node is an error (the reference's
+        # ``np.logical_and.reduce`` on such a ragged list raises too).
+        n = int(nodes["x"].shape[0])
+        flat = []
+        for mask, values in zip(self.masks, mask_values):
+            if values.dim() == 2 and values.shape[1] == 1:
+                values = values.squeeze(-1)
+            if values.shape != (n,):
+                raise ValueError(f"The mask '{mask}' has shape {tuple(values.shape)}; expected one value per node ({n},).")
+            flat.append(values)
+        return self.reduce_op(flat)
 
 
 class BooleanNot(BooleanOperation):

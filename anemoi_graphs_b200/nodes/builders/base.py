@@ -27,6 +27,7 @@ class BaseNodeBuilder(ABC):
     """
 
     hidden_attributes: set[str] = set()
+    _agx_device_aware = True
 
     def __init__(self, name: str) -> None:
         self.name = name
@@ -47,7 +48,9 @@ class BaseNodeBuilder(ABC):
             graph[self.name][f"_{hidden_attr}"] = getattr(self, hidden_attr)
 
         for attr_name, attr_config in (config or {}).items():
-            graph[self.name][attr_name] = instantiate(attr_config).compute(graph, self.name)
+            attribute = instantiate(attr_config)
+            _device.flush_for(attribute)  # a foreign attribute object may read the host tensors
+            graph[self.name][attr_name] = attribute.compute(graph, self.name)
 
         return graph
 

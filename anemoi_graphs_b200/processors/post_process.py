@@ -22,6 +22,8 @@ LOGGER = logging.getLogger(__name__)
 
 
 class PostProcessor(ABC):
+    _agx_device_aware = True
+
     @abstractmethod
     def update_graph(self, graph):
         raise NotImplementedError(f"The {self.__class__.__name__} class does not implement the method update_graph().")

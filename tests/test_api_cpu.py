@@ -226,3 +226,93 @@ def test_zarr_dataset_nodes_and_dataset_masks(monkeypatch):
     assert either == [True, False, True, False] + [True] * 8
     with pytest.raises(AssertionError):
         BooleanNot(["interior", "interior"]).compute(graph, "test_nodes")
+
+
+# ------------------------------------------------------------------------------------------------
+# advisor findings, round 1
+# ------------------------------------------------------------------------------------------------
+def test_edge_bookkeeping_stays_off_the_tensor(tmp_path):
+    """Provisional-row / tie-fixup / shard bookkeeping lives in a side table: a tagged edge_index pickles
+    (``torch.save`` of a device-resident graph) and the entry dies with the tensor."""
+    import gc
+    import threading
+
+    import torch
+
+    from anemoi_graphs_b200 import device as D
+
+    class FakeProvisional:  # holds what the real one holds: something that cannot be pickled
+        done = False
+        lock = threading.RLock()
+
+    t = torch.arange(10, dtype=torch.int32).reshape(2, 5)
+    prov = FakeProvisional()
+    D.tag_rows(t, prov, None)
+    D.edge_meta(t, create=True).fixup = prov
+    D.edge_meta(t).local = (0, 5, [5])
+    assert D.row_tags(t) == (prov, None)
+    assert not [k for k in vars(t) if k.startswith("_agx")]
+    torch.save({"edge_index": t}, tmp_path / "g.pt")  # TypeError: cannot pickle '_thread.RLock' before the fix
+    back = torch.load(tmp_path / "g.pt", weights_only=False)["edge_index"]
+    assert torch.equal(back, t) and D.edge_meta(back) is None
+    key = id(t)
+    del t, back
+    gc.collect()
+    assert key not in D._edge_meta
+
+
+def test_boolean_masks_of_mixed_shapes_do_not_broadcast():
+    import torch
+
+    from anemoi_graphs_b200.graph import HeteroData
+    from anemoi_graphs_b200.nodes.attributes import BooleanAndMask, BooleanNot, BooleanOrMask
+
+    g = HeteroData()
+    n = 7
+    g["n"].x = torch.zeros((n, 2))
+    g["n"]["a"] = torch.tensor([1, 1, 0, 0, 1, 0, 1], dtype=torch.bool)[:, None]  # a stored attribute: (N, 1)
+    g["n"]["b"] = torch.tensor([1, 0, 1, 0, 1, 1, 0], dtype=torch.bool)[:, None]
+    nested = BooleanNot("b")  # a mask object: raw values (N,)
+    both = BooleanAndMask(["a", nested]).compute(g, "n")
+    either = BooleanOrMask(["a", nested]).compute(g, "n")
+    assert both.shape == (n, 1) and either.shape == (n, 1)
+    a, nb = g["n"]["a"][:, 0], ~g["n"]["b"][:, 0]
+    assert torch.equal(both[:, 0], a & nb) and torch.equal(either[:, 0], a | nb)
+    g["n"]["ragged"] = torch.ones((n, 2), dtype=torch.bool)
+    with pytest.raises(ValueError, match="one value per node"):
+        BooleanAndMask(["a", "ragged"]).compute(g, "n")
+
+
+def test_foreign_plugins_get_a_flushed_graph(monkeypatch):
+    """A reference-style plugin (not one of the package's device-aware classes) is only called after ``flush()``."""
+    from anemoi_graphs_b200 import device as D
+    from anemoi_graphs_b200.edges.attributes import EdgeLength
+    from anemoi_graphs_b200.edges.builder import KNNEdges
+
+    class ForeignAttribute:
+        def compute(self, graph, name):
+            return None
+
+    assert D.is_device_aware(EdgeLength()) and D.is_device_aware(KNNEdges("a", "b", 3))
+    assert not D.is_device_aware(ForeignAttribute())
+    calls = []
+    monkeypatch.setattr(D, "flush", lambda: calls.append("flush"))
+    D.flush_for(EdgeLength())
+    assert calls == []
+    D.flush_for(ForeignAttribute())
+    assert calls == ["flush"]
+
+
+def test_recipe_is_validated_up_front():
+    from anemoi_graphs_b200.create import GraphCreator
+
+    T = "anemoi.graphs."
+    ok = {"nodes": {"h": {"node_builder": {"_target_": T + "nodes.TriNodes", "resolution": 1}}},
+          "edges": [{"source_name": "h", "target_name": "h", "edge_builders": [{"_target_": T + "edges.KNNEdges", "num_nearest_neighbours": 3}]}]}  # fmt: skip
+    GraphCreator(ok)
+    bad = {"nodes": {"h": {"node_builder": {"_target_": T + "nodes.ICONNodes", "name": "x", "grid_filename": "f", "max_level": 1}}}, "edges": []}
+    with pytest.raises(ImportError):
+        GraphCreator(bad)
+    ok["edges"][0]["edge_builders"][0]["num_nearest_neighbours"] = 65
+    with pytest.raises(NotImplementedError, match="65 > 64"):
+        GraphCreator(ok)

@@ -431,3 +431,80 @@ def test_provisional_numbering_gives_the_same_graph(golden, resident):
             # the same edges with the same coordinates: identical raw values; the float64 statistics are folded in
             # edge order, which differs, so the normalised float32 values may differ in the last bit
             np.testing.assert_allclose(va, vb, rtol=3e-7, atol=1e-7 * np.abs(vb).max())
+
+
+# ------------------------------------------------------------------------------------------------
+# advisor findings, round 1
+# ------------------------------------------------------------------------------------------------
+def test_resident_graph_built_under_provisional_numbering_can_be_saved(tmp_path):
+    """``torch.save`` of a device-resident graph whose TriNodes order was computed on the worker thread: nothing
+    un-picklable (the Provisional, its Future) travels with the tensors, ``clean`` not required."""
+    from anemoi_graphs_b200 import device as D
+    from anemoi_graphs_b200.create import GraphCreator
+    from anemoi_graphs_b200.graph import HeteroData
+
+    lat, lon = grids.uniform_sphere(3000, seed=3)
+    prev = D.set_resident(True)
+    try:
+        creator = GraphCreator(
+            {
+                "nodes": {"data": latlon_nodes(lat, lon), "hidden": tri_nodes(3)},
+                "edges": [
+                    edges("data", "hidden", [{"_target_": T + "edges.CutOffEdges", "cutoff_factor": 0.6}], attr_cfg()),
+                    edges("hidden", "hidden", [{"_target_": T + "edges.MultiScaleEdges", "x_hops": 1}], attr_cfg()),
+                    edges("hidden", "data", [{"_target_": T + "edges.KNNEdges", "num_nearest_neighbours": 3}], attr_cfg()),
+                ],
+            }
+        )
+        graph = creator.update_graph(HeteroData())
+        assert graph[("hidden", "to", "data")].edge_index.is_cuda
+        torch.save(graph, tmp_path / "raw.pt")  # before clean: private attributes included
+        creator.save(creator.clean(graph), tmp_path / "graph.pt")
+    finally:
+        D.set_resident(prev)
+    back = torch.load(tmp_path / "graph.pt", weights_only=False)
+    for key in graph.edge_types:
+        assert torch.equal(back[key].edge_index.cpu(), graph[key].edge_index.cpu())
+
+
+def test_reference_contract_edge_builder_plugin(golden):
+    """An edge builder written for the REFERENCE's plugin contract (subclass providing ``get_adjacency_matrix`` ->
+    scipy COO, edges/builder.py:63) is instantiable and gives the reference's edge list; it sees complete host
+    tensors even inside GraphCreator's deferred scope."""
+    from scipy.sparse import coo_matrix
+
+    from anemoi_graphs_b200.create import GraphCreator
+    from anemoi_graphs_b200.edges.builder import BaseEdgeBuilder
+    from anemoi_graphs_b200.graph import HeteroData
+
+    seen = {}
+
+    class EveryThird(BaseEdgeBuilder):
+        def get_adjacency_matrix(self, source_nodes, target_nodes):
+            sx, tx = source_nodes["x"].numpy(), target_nodes["x"].numpy()  # host reads, like the reference's builders
+            seen["src_x"] = sx.copy()
+            rows = np.arange(tx.shape[0])
+            cols = (3 * rows) % sx.shape[0]
+            return coo_matrix((np.ones(rows.size), (rows, cols)), shape=(tx.shape[0], sx.shape[0]))
+
+    import anemoi_graphs_b200.edges as pkg
+
+    pkg.EveryThird = EveryThird
+    try:
+        lat, lon = grids.uniform_sphere(500, seed=11)
+        graph = GraphCreator(
+            {
+                "nodes": {"hidden": tri_nodes(2), "data": latlon_nodes(lat, lon)},
+                "edges": [edges("hidden", "data", [{"_target_": "anemoi_graphs_b200.edges.EveryThird"}], attr_cfg())],
+            }
+        ).update_graph(HeteroData())
+    finally:
+        del pkg.EveryThird
+    hx = golden("tri_nodes")["res2_x"]
+    np.testing.assert_array_equal(seen["src_x"].view(np.int32), hx.view(np.int32))  # final order, not a blank buffer
+    ei = graph[("hidden", "to", "data")].edge_index.numpy()
+    assert ei.dtype == np.int32
+    np.testing.assert_array_equal(ei[1], np.arange(500))
+    np.testing.assert_array_equal(ei[0], (3 * np.arange(500)) % 162)
+    want = R.edge_length(hx, graph["data"].x.numpy(), ei, "unit-std")
+    np.testing.assert_allclose(graph[("hidden", "to", "data")]["edge_length"].numpy(), want, rtol=ATTR_RTOL)

@@ -131,6 +131,128 @@ def test_o1280_attribute_samples_and_statistics(o1280_graph):
 
 
 # ------------------------------------------------------------------------------------------------
+# The north-star target, WHOLE: every edge of O1280 -> TriNodes(7) against the oracle
+# ------------------------------------------------------------------------------------------------
+O1280_TIED_QUERIES = 1088  # profiles/o1280_boundary_cases.json: all on the icosphere's mirror planes, rdist bit-equal
+
+
+@pytest.fixture(scope="module")
+def o1280_exact(o1280_graph):
+    """The exact float64 search of ``oracle/exact_search.c`` over the whole decoder / encoder query sets."""
+    from oracle import exact_search as X
+
+    g = o1280_graph
+    hx, dx = g["hidden"].x.numpy(), g["data"].x.numpy()
+    knn, info = X.knn_edges_canonical(hx, dx, 3)
+    radius = R.cutoff_radius(hx, 0.6)
+    cut, near = X.cutoff_edges(dx, hx, radius)
+    return {"knn": knn, "info": info, "cut": cut, "near": near, "radius": radius}
+
+
+def test_o1280_every_knn_edge_vs_exact_oracle(o1280_graph, o1280_exact):
+    """All 19 799 040 decoder edges, canonical (dst, src) order, bit-exact; the tie list is what the oracle says."""
+    g = o1280_graph
+    got = R.canonical_sort(g[("hidden", "to", "data")].edge_index.numpy())
+    np.testing.assert_array_equal(got, o1280_exact["knn"])
+    info = o1280_exact["info"]
+    assert info["tied_queries"].size == O1280_TIED_QUERIES
+    # every tie group is BIT-EQUAL in float64 rdist (mirror-image sources): the 2^-40 tie width never excuses a
+    # near-tie that sklearn would order by distance
+    assert all(r["rdist_bit_equal"] for r in info["report"])
+    # and no query anywhere has a k / k+1 gap between "bit-equal" and 1e-9 relative
+    rd = info["rdist"]
+    gap = (rd[:, 3] - rd[:, 2]) / rd[:, 2]
+    assert int((gap < 1e-9).sum()) == O1280_TIED_QUERIES and int((gap == 0).sum()) == O1280_TIED_QUERIES
+
+
+def test_o1280_every_knn_edge_vs_sklearn_itself(o1280_graph, o1280_exact):
+    """The reference's own call (edges/builder.py:259-265: NearestNeighbors(metric="haversine").kneighbors, k = 3) on
+    ALL 6.6 M queries, all host cores: every query outside the enumerated tie list has sklearn's neighbour set; inside
+    it sklearn keeps whichever of the bit-equal candidates its tree visits first (sklearn/utils/_heap.pyx:46)."""
+    from sklearn.neighbors import NearestNeighbors
+
+    g = o1280_graph
+    hx, dx = g["hidden"].x.numpy(), g["data"].x.numpy()
+    ref = NearestNeighbors(metric="haversine", n_jobs=-1).fit(hx).kneighbors(dx, n_neighbors=3, return_distance=False)
+    ref = np.sort(ref.astype(np.int32), axis=1)
+    got = o1280_exact["knn"][0].reshape(-1, 3)  # == the GPU result (previous test), sorted by source inside a query
+    differs = np.nonzero((ref != got).any(axis=1))[0]
+    tied = o1280_exact["info"]["tied_queries"]
+    assert np.isin(differs, tied).all(), f"{np.setdiff1d(differs, tied)[:10]} differ from sklearn without a tie"
+    by_query = {r["query"]: r for r in o1280_exact["info"]["report"]}
+    for q in differs:  # sklearn's pick is another member of the same bit-equal group
+        rep = by_query[int(q)]
+        assert set(ref[q]) - set(got[q]) <= set(rep["tied_sources"])
+
+
+def test_o1280_every_cutoff_edge_vs_exact_oracle_and_sklearn(o1280_graph, o1280_exact):
+    from sklearn.neighbors import NearestNeighbors
+
+    g = o1280_graph
+    got = R.canonical_sort(g[("data", "to", "hidden")].edge_index.numpy())
+    np.testing.assert_array_equal(got, o1280_exact["cut"])
+    assert o1280_exact["near"] == 0  # no pair within 2^-40 (relative) of sin^2(r/2)
+    hx, dx = g["hidden"].x.numpy(), g["data"].x.numpy()
+    adj = NearestNeighbors(metric="haversine", n_jobs=-1).fit(dx).radius_neighbors_graph(hx, radius=o1280_exact["radius"]).tocoo()
+    ref = R.canonical_sort(np.stack([adj.col, adj.row]).astype(np.int32))  # edges/builder.py:364-366
+    np.testing.assert_array_equal(got, ref)
+
+
+def test_o1280_device_tie_and_boundary_counters(o1280_graph, o1280_exact):
+    """What the kernels count on the device agrees with the oracle's enumeration: tied KNN queries, cut-off pairs
+    within 2^-40 of the radius; and a standalone builder run (final numbering from the start) gives the same edges
+    as the provisional-numbering path inside GraphCreator."""
+    from anemoi_graphs_b200 import ops
+    from anemoi_graphs_b200.edges import CutOffEdges, KNNEdges
+
+    g = o1280_graph
+    knn = KNNEdges("hidden", "data", 3)
+    knn.stats = ops.new_stats("cuda")
+    ei = knn.get_edge_index(g)
+    np.testing.assert_array_equal(R.canonical_sort(ei.numpy()), o1280_exact["knn"])
+    assert int(knn.stats[1].item()) == O1280_TIED_QUERIES
+    cut = CutOffEdges("data", "hidden", 0.6)
+    cut.stats = ops.new_stats("cuda")
+    ei = cut.get_edge_index(g)
+    assert cut.radius == o1280_exact["radius"]  # float64 bits of sklearn's reference distance x 0.6
+    np.testing.assert_array_equal(R.canonical_sort(ei.numpy()), o1280_exact["cut"])
+    assert int(cut.stats[1].item()) == 0
+
+
+def test_o1280_every_multiscale_edge(o1280_graph):
+    g = o1280_graph
+    order = np.asarray(g["hidden"]["_node_ordering"])
+    got = R.canonical_sort(g[("hidden", "to", "hidden")].edge_index.numpy())
+    np.testing.assert_array_equal(got, R.multiscale_edges_tri(range(8), 1, order))
+
+
+def _raw_attributes_chunked(sx, tx, ei, chunk=4_000_000):
+    """The oracle's raw (un-normalised) float32 length / float64 direction of every edge, a few million at a time."""
+    lens, dirs = [], []
+    for a in range(0, ei.shape[1], chunk):
+        sub = ei[:, a : a + chunk]
+        with np.errstate(all="ignore"):
+            lens.append(R.haversine_distance(sx[sub[0]], tx[sub[1]]))
+            dirs.append(R.edge_directions_raw(sx[sub[0]].T, tx[sub[1]].T, True).T)
+    return np.concatenate(lens)[:, None], np.concatenate(dirs)
+
+
+def test_o1280_every_attribute_within_1e6(o1280_graph):
+    """EdgeLength / EdgeDirection (unit-std) of ALL 31.5 M edges against the oracle: 1e-6 relative, with the absolute
+    floor 1e-6 x max|.| for direction components near zero."""
+    g = o1280_graph
+    for key in (("data", "to", "hidden"), ("hidden", "to", "hidden"), ("hidden", "to", "data")):
+        store = g[key]
+        ei = store.edge_index.numpy()
+        sx, tx = g[key[0]].x.numpy(), g[key[2]].x.numpy()
+        raw_len, raw_dir = _raw_attributes_chunked(sx, tx, ei)
+        want_len = R.normalise(raw_len, "unit-std").astype(np.float32)
+        want_dir = R.normalise(raw_dir, "unit-std").astype(np.float32)
+        np.testing.assert_allclose(store["edge_length"].numpy(), want_len, rtol=1e-6, atol=0)
+        np.testing.assert_allclose(store["edge_dirs"].numpy(), want_dir, rtol=1e-6, atol=1e-6 * np.abs(want_dir).max())
+
+
+# ------------------------------------------------------------------------------------------------
 # BASELINE config 2: synthetic N320 reduced Gaussian grid -> TriNodes 6, the WHOLE graph against the oracle
 # ------------------------------------------------------------------------------------------------
 def test_n320_res6_whole_graph_vs_oracle():
