@@ -41,6 +41,10 @@ SIGNATURES = {
         [c_void_p, c_void_p, c_int64, c_int, c_double, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p],
     ),
     "agx_knn_redecide": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_double, c_void_p, c_void_p, c_void_p]),
+    "agx_knn_redecide_ranked": (
+        c_int,
+        [c_void_p, c_void_p, c_int64, c_int, c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    ),
     "agx_set_query_order_mode": (None, [c_int]),
     "agx_last_query_order": (c_int, []),
     "agx_radius_count": (c_int, [c_void_p, c_void_p, c_int64, c_double, c_void_p, c_void_p]),
@@ -51,6 +55,7 @@ SIGNATURES = {
     "agx_order_resolve": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "agx_mark_nodes": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
     "agx_relabel_nodes": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
+    "agx_relabel_rows": (c_int, [POINTER(c_void_p), POINTER(c_int64), c_int, c_void_p, c_void_p]),
     "agx_node_tables": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "agx_edge_attrs": (
         c_int,
@@ -62,6 +67,11 @@ SIGNATURES = {
         c_int,
         [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
          c_void_p],
+    ),  # fmt: skip
+    "agx_edge_attrs_stats_flagged": (
+        c_int,
+        [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+         c_void_p, c_int, c_void_p],
     ),  # fmt: skip
     "agx_edge_attrs_apply": (
         c_int,

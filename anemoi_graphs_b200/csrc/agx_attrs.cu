@@ -23,6 +23,8 @@
 #define ATTR_THREADS 256
 #define ATTR_MAX_BLOCKS 4096
 #define ATTR_STAT_FIELDS 8  // len: sum, sumsq, min, max; dir: sum, sumsq, min, max
+#define AGX_ATTR_FLAGS_SKIP 1
+#define AGX_ATTR_FLAGS_ONLY 2
 
 extern "C" int64_t agx_edge_attrs_workspace(void) { return (int64_t)ATTR_STAT_FIELDS * (ATTR_MAX_BLOCKS + 2); }
 
@@ -223,7 +225,12 @@ template <bool STATS, bool WRITE, int J>
 __global__ void __launch_bounds__(ATTR_THREADS, J == 4 ? 2 : (J == 2 ? 3 : 4)) k_edge_attrs(
     const int32_t* __restrict__ esrc, const int32_t* __restrict__ edst, int64_t n_edges,
     const float4* __restrict__ s_rec, const double2* __restrict__ t_rec, int want_len, int len_invert_now,
-    float* __restrict__ out_len, int want_dir, int dir_rotated, float* __restrict__ out_dir, double* __restrict__ ws) {
+    float* __restrict__ out_len, int want_dir, int dir_rotated, float* __restrict__ out_dir, double* __restrict__ ws,
+    const uint8_t* __restrict__ dst_flags, int flag_mode) {
+    // flag_mode (with dst_flags, one byte per TARGET node): AGX_ATTR_FLAGS_SKIP = edges into a flagged target are
+    // written but left out of the statistics; AGX_ATTR_FLAGS_ONLY = only those edges are evaluated at all (the rest is
+    // neither read beyond its target index, nor written, nor counted).  KNN edges whose source set is re-decided
+    // once the node order is known use the pair: everything now, the re-decided queries again later.
     Stat4 st_len, st_dir;
     st_len.init();
     st_dir.init();
@@ -240,6 +247,15 @@ __global__ void __launch_bounds__(ATTR_THREADS, J == 4 ? 2 : (J == 2 ? 3 : 4)) k
             s[j] = __ldg(esrc + e);
             t[j] = __ldg(edst + e);
         }
+        bool flagged[J];
+#pragma unroll
+        for (int j = 0; j < J; ++j) flagged[j] = flag_mode != 0 && dst_flags[t[j]] != 0;
+        if (flag_mode == AGX_ATTR_FLAGS_ONLY) {
+            bool any = false;
+#pragma unroll
+            for (int j = 0; j < J; ++j) any |= flagged[j] && (base + 32 * j < n_edges);
+            if (!__any_sync(0xffffffffu, any)) continue;
+        }
         float4 sx[J];
         float2 sl[J];
         double2 qa[J], qb[J];
@@ -253,14 +269,15 @@ __global__ void __launch_bounds__(ATTR_THREADS, J == 4 ? 2 : (J == 2 ? 3 : 4)) k
 #pragma unroll
         for (int j = 0; j < J; ++j) {
             const int64_t e = base + 32 * j;
-            const bool live = e < n_edges;
+            const bool live = (e < n_edges) && (flag_mode != AGX_ATTR_FLAGS_ONLY || flagged[j]);
+            const bool counted = live && (flag_mode != AGX_ATTR_FLAGS_SKIP || !flagged[j]);
             long long packed = __double_as_longlong(qb[j].y);
             float2 tl = make_float2(__int_as_float((int)(packed & 0xffffffffll)), __int_as_float((int)(packed >> 32)));
             if (want_len) {
                 float st_unused, ct;
                 agx_np_sincosf(tl.x, st_unused, ct);  // numpy's float32 cos(lat) of the target
                 float v = edge_length_raw(sl[j], sx[j].w, tl, ct);
-                if (STATS && live) st_len.add((double)v, v);
+                if (STATS && counted) st_len.add((double)v, v);
                 if (WRITE && live) out_len[e] = len_invert_now ? __fsub_rn(1.0f, v) : v;
             }
             if (want_dir) {
@@ -268,7 +285,7 @@ __global__ void __launch_bounds__(ATTR_THREADS, J == 4 ? 2 : (J == 2 ? 3 : 4)) k
                     double d0, d1;
                     edge_direction_rotated(sx[j], qa[j].x, qa[j].y, qb[j].x, d0, d1);
                     float f0 = (float)d0, f1 = (float)d1;
-                    if (STATS && live) {
+                    if (STATS && counted) {
                         st_dir.add(d0, f0);
                         st_dir.add(d1, f1);
                     }
@@ -276,7 +293,7 @@ __global__ void __launch_bounds__(ATTR_THREADS, J == 4 ? 2 : (J == 2 ? 3 : 4)) k
                 } else {
                     // directional_edge_features(..., relative_to_rotated_target=False): loc2 - loc1 in float32
                     float d0 = __fsub_rn(tl.x, sl[j].x), d1 = __fsub_rn(tl.y, sl[j].y);
-                    if (STATS && live) {
+                    if (STATS && counted) {
                         st_dir.add((double)d0, d0);
                         st_dir.add((double)d1, d1);
                     }
@@ -465,29 +482,33 @@ template <int J>
 static void attrs_launch(bool stats, bool write, int grid, cudaStream_t stream, const int32_t* edge_src,
                          const int32_t* edge_dst, int64_t n_edges, const float* src_rec, const double* dst_rec,
                          int want_len, int len_invert_now, float* out_len, int want_dir, int dir_rotated, float* out_dir,
-                         double* workspace) {
+                         double* workspace, const uint8_t* dst_flags, int flag_mode) {
     if (stats && write)
         k_edge_attrs<true, true, J><<<grid, ATTR_THREADS, 0, stream>>>(ATTR_KERNEL_ARGS, want_len, len_invert_now, out_len,
-                                                                      want_dir, dir_rotated, out_dir, workspace);
+                                                                      want_dir, dir_rotated, out_dir, workspace, dst_flags,
+                                                                      flag_mode);
     else if (stats)
         k_edge_attrs<true, false, J><<<grid, ATTR_THREADS, 0, stream>>>(ATTR_KERNEL_ARGS, want_len, 0, nullptr, want_dir,
-                                                                       dir_rotated, nullptr, workspace);
+                                                                       dir_rotated, nullptr, workspace, dst_flags,
+                                                                       flag_mode);
     else
         k_edge_attrs<false, true, J><<<grid, ATTR_THREADS, 0, stream>>>(ATTR_KERNEL_ARGS, want_len, len_invert_now, out_len,
-                                                                       want_dir, dir_rotated, out_dir, workspace);
+                                                                       want_dir, dir_rotated, out_dir, workspace, dst_flags,
+                                                                       flag_mode);
 }
 
 // pass A: raw values of the local edges -> out_* (float32) and/or stats[8]
 static int attrs_raw(const int32_t* edge_src, const int32_t* edge_dst, int64_t n_edges, const float* src_rec,
                      const double* dst_rec, int want_len, int len_invert_now, float* out_len, int want_dir,
-                     int dir_rotated, float* out_dir, bool write, double* stats, double* workspace, cudaStream_t stream) {
+                     int dir_rotated, float* out_dir, bool write, double* stats, double* workspace, cudaStream_t stream,
+                     const uint8_t* dst_flags = nullptr, int flag_mode = 0) {
     int grid = 0;
     if (n_edges > 0 && (want_len || want_dir)) {
         int j = attrs_j();
         grid = attrs_grid(n_edges, j);
 #define ATTR_LAUNCH(J)                                                                                                \
     attrs_launch<J>(stats != nullptr, write, grid, stream, edge_src, edge_dst, n_edges, src_rec, dst_rec, want_len,      \
-                    len_invert_now, out_len, want_dir, dir_rotated, out_dir, workspace)
+                    len_invert_now, out_len, want_dir, dir_rotated, out_dir, workspace, dst_flags, flag_mode)
         if (j == 1)
             ATTR_LAUNCH(1);
         else if (j == 2)
@@ -537,6 +558,23 @@ extern "C" int agx_edge_attrs_stats(const int32_t* edge_src, const int32_t* edge
                 "agx_edge_attrs_stats: give every requested output buffer or none");
     return attrs_raw(edge_src, edge_dst, n_edges, src_rec, dst_rec, want_len, 0, out_len, want_dir, dir_rotated, out_dir,
                      write, stats, workspace, stream);
+}
+
+extern "C" int agx_edge_attrs_stats_flagged(const int32_t* edge_src, const int32_t* edge_dst, int64_t n_edges,
+                                            const float* src_rec, const double* dst_rec, int want_len, int want_dir,
+                                            int dir_rotated, float* out_len, float* out_dir, double* stats,
+                                            double* workspace, const uint8_t* dst_flags, int flag_mode, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    AGX_REQUIRE(stats != nullptr, AGX_ERR_ARG, "agx_edge_attrs_stats_flagged: stats is NULL");
+    AGX_REQUIRE(workspace != nullptr, AGX_ERR_ARG, "agx_edge_attrs_stats_flagged: workspace is NULL");
+    AGX_REQUIRE(flag_mode == 0 || ((flag_mode == AGX_ATTR_FLAGS_SKIP || flag_mode == AGX_ATTR_FLAGS_ONLY) && dst_flags),
+                AGX_ERR_ARG, "agx_edge_attrs_stats_flagged: flag_mode must be 0, 1 (skip) or 2 (only) with dst_flags");
+    int rc = attrs_check(edge_src, edge_dst, n_edges, src_rec, dst_rec, workspace);
+    if (rc) return rc;
+    AGX_REQUIRE((!want_len || out_len) && (!want_dir || out_dir), AGX_ERR_ARG,
+                "agx_edge_attrs_stats_flagged: give every requested output buffer");
+    return attrs_raw(edge_src, edge_dst, n_edges, src_rec, dst_rec, want_len, 0, out_len, want_dir, dir_rotated, out_dir,
+                     true, stats, workspace, stream, dst_flags, flag_mode);
 }
 
 extern "C" int agx_edge_attrs_apply(const int32_t* edge_src, const int32_t* edge_dst, int64_t n_edges,

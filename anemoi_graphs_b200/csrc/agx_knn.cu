@@ -180,7 +180,16 @@ struct KnnArgs {
     int only_flagged;    // 1: tie_flags is an INPUT - only queries whose flag is set are searched and written
     const int32_t* tile_list;  // only_flagged: the tiles (of 32 consecutive queries) that hold a flagged query ...
     const int* tile_count;     // ... and how many there are (device memory: no read-back)
+    // Re-decision against an index whose points still carry PROVISIONAL labels: ties go to the lower FINAL label
+    // tie_rank[label]; what is written is again the provisional label tie_order[final label] (the caller relabels
+    // the whole row afterwards).  Both NULL: the index labels are final.
+    const int64_t* tie_rank;
+    const int64_t* tie_order;
 };
+
+// the label the tie rule compares: the final position of a provisionally labelled point
+__device__ __forceinline__ int knn_tie_label(const KnnArgs& a, int ci) { return a.tie_rank ? (int)a.tie_rank[ci] : ci; }
+__device__ __forceinline__ int knn_out_label(const KnnArgs& a, int id) { return a.tie_order ? (int)a.tie_order[id] : id; }
 
 // the tiles that hold at least one flagged query, appended in arbitrary order (the results do not depend on it)
 __global__ void __launch_bounds__(256) k_flagged_tiles(const uint8_t* __restrict__ flags, int64_t nq, int64_t n_tiles,
@@ -254,7 +263,7 @@ __device__ __forceinline__ void knn_redecide_global(const KnnArgs& a, float2 ql,
                 float4 c = __ldg(a.pts + p);
                 if (chord2(qv, c) <= amb) {
                     int ci = __float_as_int(c.w);
-                    fin.offer(agx_rdist64(ql, a.ref_latlon[ci]), ci);
+                    fin.offer(agx_rdist64(ql, a.ref_latlon[ci]), knn_tie_label(a, ci));
                 }
             }
         }
@@ -269,7 +278,7 @@ __device__ __forceinline__ void knn_redecide_stage(const KnnArgs& a, float2 ql, 
         float4 c = stage[p];
         if (chord2(qv, c) <= amb) {
             int ci = __float_as_int(c.w);
-            fin.offer(agx_rdist64(ql, a.ref_latlon[ci]), ci);
+            fin.offer(agx_rdist64(ql, a.ref_latlon[ci]), knn_tie_label(a, ci));
         }
     }
 }
@@ -423,7 +432,7 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn(KnnArgs a) {
 #pragma unroll
                 for (int s = 0; s < CAP - 1; ++s)
                     if (s < k) {
-                        os[s] = fin.id[s];
+                        os[s] = knn_out_label(a, fin.id[s]);
                         if (a.out_rdist) a.out_rdist[q * k + s] = fin.r[s];
                     }
                 if (a.stats || a.tie_flags) {
@@ -457,7 +466,7 @@ static void launch_knn(const KnnArgs& a, cudaStream_t stream) {
 
 int agx_knn_ex(const agx_index_t* ix, const float* q_latlon, int64_t nq, int k, double max_radius, int32_t* out_src,
                int32_t* out_dst, int64_t dst_base, double* out_rdist, int64_t* stats, uint8_t* tie_flags, int only_flagged,
-               void* stream_);
+               const int64_t* tie_rank, const int64_t* tie_order, void* stream_);
 
 extern "C" int agx_knn(const agx_index_t* ix, const float* q_latlon, int64_t nq, int k, double max_radius, int32_t* out_src,
                        int32_t* out_dst, int64_t dst_base, double* out_rdist, int64_t* stats, void* stream_) {
@@ -467,18 +476,29 @@ extern "C" int agx_knn(const agx_index_t* ix, const float* q_latlon, int64_t nq,
 extern "C" int agx_knn_flagged(const agx_index_t* ix, const float* q_latlon, int64_t nq, int k, double max_radius,
                                int32_t* out_src, int32_t* out_dst, int64_t dst_base, double* out_rdist, int64_t* stats,
                                uint8_t* tie_flags, void* stream_) {
-    return agx_knn_ex(ix, q_latlon, nq, k, max_radius, out_src, out_dst, dst_base, out_rdist, stats, tie_flags, 0, stream_);
+    return agx_knn_ex(ix, q_latlon, nq, k, max_radius, out_src, out_dst, dst_base, out_rdist, stats, tie_flags, 0, nullptr,
+                      nullptr, stream_);
 }
 
 extern "C" int agx_knn_redecide(const agx_index_t* ix, const float* q_latlon, int64_t nq, int k, double max_radius,
                                 int32_t* out_src, const uint8_t* tie_flags, void* stream_) {
     AGX_REQUIRE(tie_flags != nullptr, AGX_ERR_ARG, "agx_knn_redecide: tie_flags is NULL");
-    return agx_knn_ex(ix, q_latlon, nq, k, max_radius, out_src, nullptr, 0, nullptr, nullptr, (uint8_t*)tie_flags, 1, stream_);
+    return agx_knn_ex(ix, q_latlon, nq, k, max_radius, out_src, nullptr, 0, nullptr, nullptr, (uint8_t*)tie_flags, 1, nullptr,
+                      nullptr, stream_);
+}
+
+extern "C" int agx_knn_redecide_ranked(const agx_index_t* ix, const float* q_latlon, int64_t nq, int k, double max_radius,
+                                       int32_t* out_src, const uint8_t* tie_flags, const int64_t* rank,
+                                       const int64_t* order, void* stream_) {
+    AGX_REQUIRE(tie_flags != nullptr, AGX_ERR_ARG, "agx_knn_redecide_ranked: tie_flags is NULL");
+    AGX_REQUIRE(rank != nullptr && order != nullptr, AGX_ERR_ARG, "agx_knn_redecide_ranked: rank / order is NULL");
+    return agx_knn_ex(ix, q_latlon, nq, k, max_radius, out_src, nullptr, 0, nullptr, nullptr, (uint8_t*)tie_flags, 1, rank,
+                      order, stream_);
 }
 
 int agx_knn_ex(const agx_index_t* ix, const float* q_latlon, int64_t nq, int k, double max_radius, int32_t* out_src,
                int32_t* out_dst, int64_t dst_base, double* out_rdist, int64_t* stats, uint8_t* tie_flags, int only_flagged,
-               void* stream_) {
+               const int64_t* tie_rank, const int64_t* tie_order, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     AGX_REQUIRE(ix != nullptr, AGX_ERR_ARG, "agx_knn: NULL index");
     AGX_REQUIRE(nq >= 0, AGX_ERR_ARG, "agx_knn: nq < 0");
@@ -523,6 +543,8 @@ int agx_knn_ex(const agx_index_t* ix, const float* q_latlon, int64_t nq, int k, 
     a.stats = (unsigned long long*)stats;
     a.tie_flags = tie_flags;
     a.only_flagged = only_flagged;
+    a.tie_rank = tie_rank;
+    a.tie_order = tie_order;
     int32_t* perm = nullptr;
     int32_t* tile_list = nullptr;
     a.tile_list = nullptr;

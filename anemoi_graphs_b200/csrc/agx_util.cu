@@ -361,6 +361,53 @@ extern "C" int agx_mark_nodes(const int32_t* row, int64_t n, int64_t n_nodes, in
     return AGX_OK;
 }
 
+#define RELABEL_MAX_ROWS 8
+struct RelabelRows {
+    int32_t* row[RELABEL_MAX_ROWS];
+    int64_t end[RELABEL_MAX_ROWS];  // exclusive prefix ends of the concatenated index space
+    int n_rows;
+};
+
+__global__ void __launch_bounds__(256) k_relabel_rows(RelabelRows r, const int64_t* __restrict__ new_index) {
+    const int64_t total = r.end[r.n_rows - 1];
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int which = 0;
+#pragma unroll
+        for (int w = 0; w < RELABEL_MAX_ROWS - 1; ++w) which += (w < r.n_rows - 1 && i >= r.end[w]) ? 1 : 0;
+        int64_t j = i - (which ? r.end[which - 1] : 0);
+        int32_t* row = r.row[which];
+        row[j] = (int32_t)new_index[row[j]];
+    }
+}
+
+extern "C" int agx_relabel_rows(int32_t* const* rows, const int64_t* lens, int n_rows, const int64_t* new_index,
+                                void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    AGX_REQUIRE(n_rows >= 0 && n_rows <= RELABEL_MAX_ROWS, AGX_ERR_ARG, "agx_relabel_rows: n_rows out of [0, 8]");
+    RelabelRows r;
+    r.n_rows = 0;
+    int64_t total = 0;
+    for (int i = 0; i < n_rows; ++i) {
+        AGX_REQUIRE(lens[i] >= 0, AGX_ERR_ARG, "agx_relabel_rows: negative length");
+        if (lens[i] == 0) continue;
+        AGX_REQUIRE(rows[i] != nullptr, AGX_ERR_ARG, "agx_relabel_rows: NULL row");
+        total += lens[i];
+        r.row[r.n_rows] = rows[i];
+        r.end[r.n_rows] = total;
+        r.n_rows++;
+    }
+    if (r.n_rows == 0) return AGX_OK;
+    AGX_REQUIRE(new_index != nullptr, AGX_ERR_ARG, "agx_relabel_rows: new_index is NULL");
+    for (int i = r.n_rows; i < RELABEL_MAX_ROWS; ++i) {
+        r.row[i] = nullptr;
+        r.end[i] = total;
+    }
+    k_relabel_rows<<<agx_grid(total, 256, 8), 256, 0, stream>>>(r, new_index);
+    AGX_LAUNCH_OK();
+    agx_note_launch(1);
+    return AGX_OK;
+}
+
 extern "C" int agx_relabel_nodes(int32_t* row, int64_t n, const int64_t* new_index, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     AGX_REQUIRE(n >= 0, AGX_ERR_ARG, "agx_relabel_nodes: n < 0");

@@ -228,6 +228,41 @@ def node_state(nodes, provisional_ok: bool = False) -> NodeState:
     return st
 
 
+# node sets up to this size keep their neighbour index on the node state (``NodeState.extras``), so the builders of
+# one recipe that search the same set with the same cell width share ONE build (reference distance + KNN decoder over
+# the hidden nodes); larger sets (106 MB of records for an O1280 grid) are binned per search and freed at once
+INDEX_CACHE_MAX_NODES = int(float(__import__("os").environ.get("AGX_INDEX_CACHE_MAX_NODES", "2e6")))
+
+
+class _Borrowed:
+    """Context manager handing out a cached index without closing it."""
+
+    def __init__(self, index) -> None:
+        self.index = index
+
+    def __enter__(self):
+        return self.index
+
+    def __exit__(self, *exc) -> None:
+        return None
+
+
+def neighbour_index(st: NodeState | None, x: torch.Tensor, hint_k: int = 0, hint_radius: float = 0.0):
+    """``with neighbour_index(state, x, hint_k=k) as index`` - the cell-binned index over ``x``; shared through the
+    node state when ``x`` IS the state's coordinate tensor (no mask) and the set is small, else built for this search
+    and freed when the block exits."""
+    from . import ops
+
+    if st is None or x is not st.x or int(x.shape[0]) > INDEX_CACHE_MAX_NODES:
+        return ops.NeighbourIndex(x, hint_k=hint_k, hint_radius=hint_radius)
+    cache = st.extras.setdefault("index", {})
+    key = (int(hint_k), float(hint_radius))
+    hit = cache.get(key)
+    if hit is None or hit.handle is None:
+        hit = cache[key] = ops.NeighbourIndex(x, hint_k=hint_k, hint_radius=hint_radius)
+    return _Borrowed(hit)
+
+
 def seed_node_state(nodes, x_dev: torch.Tensor) -> NodeState:
     """Install an already-resident device copy of ``nodes.x`` (e.g. coordinates generated on the GPU)."""
     st = NodeState(key=_key(nodes["x"]), x=x_dev.contiguous())
@@ -294,6 +329,8 @@ class Provisional:
         self.order_dev = None
         self.rows: list = []
         self.fixups: list = []
+        self.finalizers: list = []
+        self.rank = None  # CUDA int64 (n + 1): final position of every provisional label, once resolved
         self.nodes = None
         self.state = None
         self.on_resolved = None
@@ -345,9 +382,15 @@ class Provisional:
         self.rows.append((tensor, row, host))
 
     def add_fixup(self, fn) -> None:
-        """``fn(self)`` runs when the order resolves, after the registered rows carry final labels and before they are
-        copied to the host (KNN re-decides its index-order ties there)."""
+        """``fn(self)`` runs when the order resolves (``self.rank`` / ``self.order_dev`` are known), BEFORE the
+        registered rows are relabelled: everything is still in provisional numbering (KNN re-decides its index-order
+        ties there, the attributes of the re-decided edges are evaluated again)."""
         self.fixups.append(fn)
+
+    def add_finalizer(self, fn) -> None:
+        """``fn(self)`` runs after the registered rows carry final labels and their host copies are enqueued (the
+        normalisation of attributes whose statistics waited for a re-decision, and their host copies)."""
+        self.finalizers.append(fn)
 
     def resolve(self) -> None:
         if self.done:
@@ -387,16 +430,22 @@ class Provisional:
             torch.index_select(self.x_prov, 0, order_dev, out=self.x_final)
         to_host_into(order_dev, self.order_host)  # ``_node_ordering``: complete at flush like every host copy
         self.order_dev = order_dev
-        for tensor, row, host in self.rows:
-            wait_for(tensor)  # a sharded builder's all-gather may still be filling it
-            check(lib.agx_relabel_nodes(tensor[row].data_ptr(), int(tensor.shape[1]), rank.data_ptr(), current_stream()))
+        self.rank = rank
         fixups, self.fixups = self.fixups, []
         for fn in fixups:
             fn(self)
+        from . import ops
+
+        for tensor, row, host in self.rows:
+            wait_for(tensor)  # a sharded builder's all-gather may still be filling it
+        ops.relabel_rows([tensor[row] for tensor, row, host in self.rows], rank)  # one launch for all rows
         for tensor, row, host in self.rows:
             if host is not None:
                 to_host_into(tensor[row], host[row])
         self.rows = []
+        finalizers, self.finalizers = self.finalizers, []
+        for fn in finalizers:
+            fn(self)
         if self.x_host is not None:
             to_host_into(self.x_final, self.x_host)
         if self.state is not None:
@@ -425,11 +474,12 @@ def active_provisional(nodes):
 # pickles a tensor's ``__dict__``, and a device-resident graph stores these very tensors, so attributes holding a
 # ``Provisional`` (a ``Future``, pinned buffers) would break ``torch.save(graph)`` and keep the buffers alive.
 class EdgeMeta:
-    __slots__ = ("prov", "fixup", "local")
+    __slots__ = ("prov", "fixup", "local", "tie_flags")
 
     def __init__(self) -> None:
         self.prov = (None, None)  # (source row, target row): the Provisional whose numbering the row is in
-        self.fixup = None  # Provisional that still has to re-decide KNN ties of this edge list
+        self.fixup = None  # Provisional that still has to re-decide KNN ties of this edge list ...
+        self.tie_flags = None  # ... and the CUDA uint8 flag per TARGET node naming the queries it will re-decide
         self.local = None  # (lo, hi, counts): this rank's own columns of a sharded edge list
 
 

@@ -177,6 +177,7 @@ class NodeMaskingMixin:
         src_st = _device.node_state(source_nodes, provisional_ok=ok and self.provisional_source_ok)
         dst_st = _device.node_state(target_nodes, provisional_ok=ok and self.provisional_target_ok)
         self._row_provs = (src_st.prov, dst_st.prov)  # rows of the result that will be in provisional numbering
+        self._src_state = src_st  # its neighbour index is shared between the builders of a recipe (unmasked, small sets)
         src, dst = src_st.x, dst_st.x
         src_sel = self._selection(source_nodes, self.source_mask_attr_name, src.device)
         dst_sel = self._selection(target_nodes, self.target_mask_attr_name, dst.device)
@@ -245,11 +246,13 @@ class KNNEdges(BaseEdgeBuilder, NodeMaskingMixin):
     provisional_source_ok = True
 
     @staticmethod
-    def _redecide_ties(prov, out: torch.Tensor, flags: torch.Tensor, queries: torch.Tensor, k: int) -> None:
-        """Runs inside ``Provisional.resolve``: row 0 of ``out`` already carries final source labels."""
-        with ops.NeighbourIndex(prov.x_final, hint_k=k) as index:
-            index.knn_redecide(queries, k, out, flags)
-        _device.edge_meta(out, create=True).fixup = None
+    def _redecide_ties(prov, index, out: torch.Tensor, flags: torch.Tensor, queries: torch.Tensor, k: int) -> None:
+        """Runs inside ``Provisional.resolve`` before the rows are relabelled: ``index`` is the one the search used
+        (provisional labels); ties go to the lower FINAL label ``prov.rank[label]``, provisional labels are written."""
+        index.knn_redecide(queries, k, out, flags, rank=prov.rank, order=prov.order_dev)
+        meta = _device.edge_meta(out)
+        if meta is not None:
+            meta.fixup = None
 
     def compute_edge_index(self, source_nodes, target_nodes) -> torch.Tensor:
         src, dst, src_sel, dst_sel = self.get_node_coordinates(source_nodes, target_nodes)
@@ -272,14 +275,16 @@ class KNNEdges(BaseEdgeBuilder, NodeMaskingMixin):
             src_prov = dst_prov = None
         if src_prov is not None:
             flags = torch.zeros(nq, dtype=torch.uint8, device=dst.device)
-            with ops.NeighbourIndex(src, hint_k=k) as index:
+            with _device.neighbour_index(self._src_state, src, hint_k=k) as index:
                 out = index.knn(dst, k, stats=self.stats, tie_flags=flags)
             out = _device.tag_rows(out, src_prov, None)
-            _device.edge_meta(out, create=True).fixup = src_prov
-            src_prov.add_fixup(lambda prov, out=out, flags=flags, dst=dst, k=k: self._redecide_ties(prov, out, flags, dst, k))
+            meta = _device.edge_meta(out, create=True)
+            meta.fixup, meta.tie_flags = src_prov, flags
+            # ``index`` stays alive in the closure: the re-decision searches it again, no second index
+            src_prov.add_fixup(lambda prov, index=index, out=out, flags=flags, dst=dst, k=k: self._redecide_ties(prov, index, out, flags, dst, k))  # fmt: skip
             return out
         lo, hi = _device.shard_range(nq, rank, w)
-        with ops.NeighbourIndex(src, hint_k=k) as index:
+        with _device.neighbour_index(self._src_state if src_sel is None else None, src, hint_k=k) as index:
             out = torch.empty((2, nq * k), dtype=torch.int32, device=dst.device)
             masked = src_sel is not None or dst_sel is not None
             if w > 1 and not masked and _device.VMM_PUSH:

@@ -148,15 +148,29 @@ class NeighbourIndex:
             )  # fmt: skip
         return (out, rdist) if return_rdist else out
 
-    def knn_redecide(self, q: torch.Tensor, k: int, out: torch.Tensor, tie_flags: torch.Tensor) -> None:
+    def knn_redecide(
+        self, q: torch.Tensor, k: int, out: torch.Tensor, tie_flags: torch.Tensor, rank: torch.Tensor | None = None,
+        order: torch.Tensor | None = None,
+    ) -> None:  # fmt: skip
         """Search only the queries flagged in ``tie_flags`` and overwrite their sources in row 0 of ``out``
-        (``agx_knn_redecide``)."""
+        (``agx_knn_redecide``).  With ``rank`` / ``order`` (CUDA int64 inverse permutations) this index is still the
+        one over the PROVISIONALLY numbered points: ties go to the lower final label ``rank[label]`` and provisional
+        labels are written back (``agx_knn_redecide_ranked``) - no second index over the re-ordered points."""
         q = _dev_x(q)
         nq = int(q.shape[0])
         assert out.shape == (2, nq * k) and out.dtype == torch.int32 and out.is_contiguous()
         assert tie_flags.shape == (nq,) and tie_flags.dtype == torch.uint8
         with _span("knn_ties", nq):
-            check(self.lib.agx_knn_redecide(self.handle, ptr(q), nq, int(k), 0.0, out.data_ptr(), ptr(tie_flags), current_stream()))
+            if rank is None:
+                check(self.lib.agx_knn_redecide(self.handle, ptr(q), nq, int(k), 0.0, out.data_ptr(), ptr(tie_flags), current_stream()))
+            else:
+                assert rank.dtype == torch.int64 and order.dtype == torch.int64 and rank.numel() >= self.n and order.numel() >= self.n
+                check(
+                    self.lib.agx_knn_redecide_ranked(
+                        self.handle, ptr(q), nq, int(k), 0.0, out.data_ptr(), ptr(tie_flags), ptr(rank), ptr(order),
+                        current_stream(),
+                    )
+                )
 
     def radius_count(self, q: torch.Tensor, radius: float) -> tuple[torch.Tensor, int]:
         """Pass 1 of the cut-off search: ``(offsets (nq+1,) int64, total)``."""
@@ -425,6 +439,84 @@ def edge_attributes(
     return out_len, out_dir
 
 
+def relabel_rows(rows: list[torch.Tensor], new_index: torch.Tensor) -> None:
+    """``row[i] = new_index[row[i]]`` in place for every CUDA int32 row (views allowed when contiguous), eight rows per
+    launch (``agx_relabel_rows``)."""
+    lib = load_library()
+    rows = [r for r in rows if r.numel()]
+    for a in range(0, len(rows), 8):
+        part = rows[a : a + 8]
+        for r in part:
+            assert r.is_cuda and r.dtype == torch.int32 and r.is_contiguous()
+        ptrs = (c_void_p * len(part))(*[r.data_ptr() for r in part])
+        lens = (c_int64 * len(part))(*[int(r.numel()) for r in part])
+        with _span("relabel", sum(int(r.numel()) for r in part)):
+            check(lib.agx_relabel_rows(ptrs, lens, len(part), ptr(new_index), current_stream()))
+
+
+ATTR_FLAGS_SKIP, ATTR_FLAGS_ONLY = 1, 2
+
+
+class DeferredEdgeAttributes:
+    """EdgeLength / EdgeDirection of an edge set whose sources of a FEW targets are still to be re-decided (KNN edges
+    searched while the source numbering was provisional; ``dst_flags`` marks those targets).
+
+    ``raw()`` evaluates every edge now - the trigonometry of the whole set runs in the shadow of the host sort - but
+    keeps the flagged targets' edges out of the statistics; after the re-decision ``patch()`` evaluates exactly those
+    edges again (statistics set 2) and ``apply()`` derives the normalisation from both sets and scales in place.
+    Single rank only (a sharded build orders the nodes first)."""
+
+    def __init__(self, edge_index, src: NodeTables, dst: NodeTables, dst_flags: torch.Tensor, length=True,
+                 length_norm=None, length_invert=False, direction=True, direction_norm=None, direction_rotated=True):  # fmt: skip
+        assert edge_index.is_cuda and edge_index.dtype == torch.int32 and edge_index.is_contiguous()
+        assert dst_flags.dtype == torch.uint8 and dst_flags.is_cuda
+        self.edge_index, self.flags = edge_index, dst_flags
+        self.n_edges = int(edge_index.shape[1])
+        dev = edge_index.device
+        self.length, self.direction, self.rotated, self.invert = bool(length), bool(direction), bool(direction_rotated), bool(length_invert)
+        self.len_code = NORM_CODES[length_norm] if length else -1
+        self.dir_code = NORM_CODES[direction_norm] if direction else -1
+        self.out_len = torch.empty((self.n_edges, 1), dtype=torch.float32, device=dev) if length else None
+        self.out_dir = torch.empty((self.n_edges, 2), dtype=torch.float32, device=dev) if direction else None
+        if src is dst:
+            src.prepare(as_source=True, as_target=True)
+        self.src_rec, self.dst_rec = src.src_rec, dst.dst_rec
+        self.stats = torch.empty((2, 8), dtype=torch.float64, device=dev)
+        self.ws = _attr_workspace(dev)
+
+    def _pass(self, which: int, mode: int, tag: str) -> None:
+        if self.n_edges == 0:
+            return
+        ei = self.edge_index
+        with _span(tag, self.n_edges if mode == ATTR_FLAGS_SKIP else 0):
+            check(
+                load_library().agx_edge_attrs_stats_flagged(
+                    ei[0].data_ptr(), ei[1].data_ptr(), self.n_edges, ptr(self.src_rec), ptr(self.dst_rec),
+                    int(self.length), int(self.direction), int(self.rotated), ptr(self.out_len), ptr(self.out_dir),
+                    self.stats[which].data_ptr(), ptr(self.ws), ptr(self.flags), mode, current_stream(),
+                )
+            )
+
+    def raw(self) -> None:
+        self._pass(0, ATTR_FLAGS_SKIP, "edge_attrs_raw")
+
+    def patch(self) -> None:
+        self._pass(1, ATTR_FLAGS_ONLY, "edge_attrs_patch")
+
+    def apply(self) -> None:
+        if self.n_edges == 0:
+            return
+        ei = self.edge_index
+        with _span("edge_attrs_scale", self.n_edges):
+            check(
+                load_library().agx_edge_attrs_apply(
+                    ei[0].data_ptr(), ei[1].data_ptr(), self.n_edges, ptr(self.src_rec), ptr(self.dst_rec), self.len_code,
+                    int(self.invert), ptr(self.out_len), self.dir_code, int(self.rotated), ptr(self.out_dir),
+                    ptr(self.stats), 2, self.n_edges, 1, ptr(self.ws), current_stream(),
+                )
+            )
+
+
 # ----------------------------------------------------------------------------------------------
 # icosphere + multi-scale edges
 # ----------------------------------------------------------------------------------------------
@@ -690,6 +782,8 @@ def voronoi_areas(x: torch.Tensor, radius: float = 1.0) -> torch.Tensor:
 
 __all__ = [
     "multiscale_tri_edges_mapped",
+    "relabel_rows",
+    "DeferredEdgeAttributes",
     "voronoi_areas",
     "HexCells",
     "hex_num_cells",

@@ -97,6 +97,14 @@ int agx_knn_flagged(const agx_index_t* index, const float* q_latlon /*DEV nq*2*/
 int agx_knn_redecide(const agx_index_t* index, const float* q_latlon /*DEV nq*2*/, int64_t nq, int k, double max_radius,
                      int32_t* out_src /*DEV nq*k*/, const uint8_t* tie_flags /*DEV nq*/, void* stream);
 
+/* The same re-decision WITHOUT a second index: `index` is still the one built over the provisionally numbered points
+ * (the one agx_knn_flagged searched).  Ties go to the lower FINAL label rank[provisional label]; the k slots are
+ * written as provisional labels again (order[final label]), so that one relabel pass afterwards treats every slot
+ * of the row alike.  rank / order: DEV int64[n_reference], inverse permutations (agx_order_resolve).              */
+int agx_knn_redecide_ranked(const agx_index_t* index, const float* q_latlon /*DEV nq*2*/, int64_t nq, int k,
+                            double max_radius, int32_t* out_src /*DEV nq*k*/, const uint8_t* tie_flags /*DEV nq*/,
+                            const int64_t* rank /*DEV*/, const int64_t* order /*DEV*/, void* stream);
+
 /* Query order of the tile kernels.  agx_knn / agx_radius_* decide per call whether to walk the queries as given or in
  * a spatially binned order; for >= 262 144 queries the decision samples tile plans and synchronises the stream.
  * A caller that searches ONE query set in several chunks (device.ChunkedGather) reads the first call's decision
@@ -139,6 +147,10 @@ int agx_host_reference_rdist(const float* q_latlon /*HOST n_cand*2*/, const floa
  * agx_relabel_nodes rewrites a row in place as new_index[v] - the reference's python dict + Tensor.apply_.       */
 int agx_mark_nodes(const int32_t* row /*DEV n*/, int64_t n, int64_t n_nodes, int32_t* flags /*DEV n_nodes*/, void* stream);
 int agx_relabel_nodes(int32_t* row /*DEV n, in place*/, int64_t n, const int64_t* new_index /*DEV n_nodes+1*/, void* stream);
+/* agx_relabel_nodes over up to 8 rows in ONE launch (rows / lens: HOST arrays of n_rows device pointers / lengths):
+ * every index row that was built in a provisional node numbering, rewritten when the order resolves.            */
+int agx_relabel_rows(int32_t* const* rows /*HOST n_rows x DEV*/, const int64_t* lens /*HOST n_rows*/, int n_rows,
+                     const int64_t* new_index /*DEV*/, void* stream);
 
 /* ---- node ordering, device half ---------------------------------------------------------------------------
  * get_coordinates_ordering (generate/utils.py:15-33): the two (unstable, order-defining) argsorts stay numpy's on the
@@ -181,6 +193,16 @@ int agx_edge_attrs_stats(const int32_t* edge_src, const int32_t* edge_dst, int64
                          const double* dst_rec, int want_len, int want_dir, int dir_rotated,
                          float* out_len /*DEV E or NULL*/, float* out_dir /*DEV E*2 or NULL*/,
                          double* stats /*DEV 8*/, double* workspace, void* stream);
+/* agx_edge_attrs_stats with a per-TARGET flag byte (dst_flags: DEV uint8[n_target_nodes]).  flag_mode 1 ("skip"): every
+ * edge is evaluated and written, edges INTO a flagged target stay out of the statistics; flag_mode 2 ("only"): only
+ * the edges into flagged targets are evaluated, written and counted.  For KNN edges built while the source numbering
+ * was provisional (agx_knn_flagged): mode 1 right after the search, mode 2 after agx_knn_redecide_ranked; the two
+ * statistics sets go to agx_edge_attrs_apply (n_stat_sets = 2) - the decoder's trigonometry then runs in the shadow
+ * of the host sort and only the scaling pass follows it.                                                          */
+int agx_edge_attrs_stats_flagged(const int32_t* edge_src, const int32_t* edge_dst, int64_t n_edges,
+                                 const float* src_rec, const double* dst_rec, int want_len, int want_dir, int dir_rotated,
+                                 float* out_len, float* out_dir, double* stats /*DEV 8*/, double* workspace,
+                                 const uint8_t* dst_flags /*DEV*/, int flag_mode, void* stream);
 int agx_edge_attrs_apply(const int32_t* edge_src, const int32_t* edge_dst, int64_t n_edges, const float* src_rec,
                          const double* dst_rec, int len_norm, int len_invert, float* out_len, int dir_norm,
                          int dir_rotated, float* out_dir, const double* stats /*DEV n_stat_sets*8 or NULL if no norm*/,
