@@ -45,6 +45,11 @@ SIGNATURES = {
         c_int,
         [c_void_p, c_void_p, c_int64, c_int, c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     ),
+    "agx_knn_redecide_list": (
+        c_int,
+        [c_void_p, c_void_p, c_int64, c_int, c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    ),
+    "agx_compact_flags": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "agx_set_query_order_mode": (None, [c_int]),
     "agx_last_query_order": (c_int, []),
     "agx_radius_count": (c_int, [c_void_p, c_void_p, c_int64, c_double, c_void_p, c_void_p]),
@@ -72,6 +77,11 @@ SIGNATURES = {
         c_int,
         [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
          c_void_p, c_int, c_void_p],
+    ),  # fmt: skip
+    "agx_edge_attrs_stats_list": (
+        c_int,
+        [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
+         c_void_p, c_void_p, c_void_p, c_void_p],
     ),  # fmt: skip
     "agx_edge_attrs_apply": (
         c_int,

@@ -226,7 +226,8 @@ __global__ void __launch_bounds__(ATTR_THREADS, J == 4 ? 2 : (J == 2 ? 3 : 4)) k
     const int32_t* __restrict__ esrc, const int32_t* __restrict__ edst, int64_t n_edges,
     const float4* __restrict__ s_rec, const double2* __restrict__ t_rec, int want_len, int len_invert_now,
     float* __restrict__ out_len, int want_dir, int dir_rotated, float* __restrict__ out_dir, double* __restrict__ ws,
-    const uint8_t* __restrict__ dst_flags, int flag_mode) {
+    const uint8_t* __restrict__ dst_flags, int flag_mode, const int32_t* __restrict__ only_list,
+    const int64_t* __restrict__ only_count, int regular_k) {
     // flag_mode (with dst_flags, one byte per TARGET node): AGX_ATTR_FLAGS_SKIP = edges into a flagged target are
     // written but left out of the statistics; AGX_ATTR_FLAGS_ONLY = only those edges are evaluated at all (the rest is
     // neither read beyond its target index, nor written, nor counted).  KNN edges whose source set is re-decided
@@ -236,14 +237,20 @@ __global__ void __launch_bounds__(ATTR_THREADS, J == 4 ? 2 : (J == 2 ? 3 : 4)) k
     st_dir.init();
     const int lane = threadIdx.x & 31;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    const int64_t n_tiles = (n_edges + 32 * J - 1) / (32 * J);
+    // only_list (with regular_k: edges of target t are [t k, (t + 1) k), a KNN result): the work items are the edges of
+    // the listed targets only - item w is edge only_list[w / k] * k + w % k - instead of all n_edges
+    const int64_t n_work = only_list ? *only_count * regular_k : n_edges;
+    const int64_t n_tiles = (n_work + 32 * J - 1) / (32 * J);
     for (int64_t tile = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; tile < n_tiles; tile += n_warps) {
         const int64_t base = tile * (32 * J) + lane;
         int s[J], t[J];
+        int64_t eid[J];
 #pragma unroll
         for (int j = 0; j < J; ++j) {
-            int64_t e = base + 32 * j;
-            e = e < n_edges ? e : n_edges - 1;  // tail lanes repeat the last edge (never stored, never counted)
+            int64_t w = base + 32 * j;
+            w = w < n_work ? w : n_work - 1;  // tail lanes repeat the last item (never stored, never counted)
+            int64_t e = only_list ? (int64_t)only_list[w / regular_k] * regular_k + (w % regular_k) : w;
+            eid[j] = e;
             s[j] = __ldg(esrc + e);
             t[j] = __ldg(edst + e);
         }
@@ -253,7 +260,7 @@ __global__ void __launch_bounds__(ATTR_THREADS, J == 4 ? 2 : (J == 2 ? 3 : 4)) k
         if (flag_mode == AGX_ATTR_FLAGS_ONLY) {
             bool any = false;
 #pragma unroll
-            for (int j = 0; j < J; ++j) any |= flagged[j] && (base + 32 * j < n_edges);
+            for (int j = 0; j < J; ++j) any |= flagged[j] && (base + 32 * j < n_work);
             if (!__any_sync(0xffffffffu, any)) continue;
         }
         float4 sx[J];
@@ -268,8 +275,8 @@ __global__ void __launch_bounds__(ATTR_THREADS, J == 4 ? 2 : (J == 2 ? 3 : 4)) k
         }
 #pragma unroll
         for (int j = 0; j < J; ++j) {
-            const int64_t e = base + 32 * j;
-            const bool live = (e < n_edges) && (flag_mode != AGX_ATTR_FLAGS_ONLY || flagged[j]);
+            const int64_t e = eid[j];
+            const bool live = (base + 32 * j < n_work) && (flag_mode != AGX_ATTR_FLAGS_ONLY || flagged[j]);
             const bool counted = live && (flag_mode != AGX_ATTR_FLAGS_SKIP || !flagged[j]);
             long long packed = __double_as_longlong(qb[j].y);
             float2 tl = make_float2(__int_as_float((int)(packed & 0xffffffffll)), __int_as_float((int)(packed >> 32)));
@@ -482,19 +489,20 @@ template <int J>
 static void attrs_launch(bool stats, bool write, int grid, cudaStream_t stream, const int32_t* edge_src,
                          const int32_t* edge_dst, int64_t n_edges, const float* src_rec, const double* dst_rec,
                          int want_len, int len_invert_now, float* out_len, int want_dir, int dir_rotated, float* out_dir,
-                         double* workspace, const uint8_t* dst_flags, int flag_mode) {
+                         double* workspace, const uint8_t* dst_flags, int flag_mode, const int32_t* only_list = nullptr,
+                         const int64_t* only_count = nullptr, int regular_k = 0) {
     if (stats && write)
         k_edge_attrs<true, true, J><<<grid, ATTR_THREADS, 0, stream>>>(ATTR_KERNEL_ARGS, want_len, len_invert_now, out_len,
                                                                       want_dir, dir_rotated, out_dir, workspace, dst_flags,
-                                                                      flag_mode);
+                                                                      flag_mode, only_list, only_count, regular_k);
     else if (stats)
         k_edge_attrs<true, false, J><<<grid, ATTR_THREADS, 0, stream>>>(ATTR_KERNEL_ARGS, want_len, 0, nullptr, want_dir,
                                                                        dir_rotated, nullptr, workspace, dst_flags,
-                                                                       flag_mode);
+                                                                       flag_mode, only_list, only_count, regular_k);
     else
         k_edge_attrs<false, true, J><<<grid, ATTR_THREADS, 0, stream>>>(ATTR_KERNEL_ARGS, want_len, len_invert_now, out_len,
                                                                        want_dir, dir_rotated, out_dir, workspace, dst_flags,
-                                                                       flag_mode);
+                                                                       flag_mode, only_list, only_count, regular_k);
 }
 
 // pass A: raw values of the local edges -> out_* (float32) and/or stats[8]
@@ -575,6 +583,32 @@ extern "C" int agx_edge_attrs_stats_flagged(const int32_t* edge_src, const int32
                 "agx_edge_attrs_stats_flagged: give every requested output buffer");
     return attrs_raw(edge_src, edge_dst, n_edges, src_rec, dst_rec, want_len, 0, out_len, want_dir, dir_rotated, out_dir,
                      true, stats, workspace, stream, dst_flags, flag_mode);
+}
+
+// Raw values + statistics of the edges of a LIST of targets of a regular-k edge list (a KNN result: the edges of target
+// t are [t k, (t + 1) k)); the list length lives in device memory.  One small launch, sized for a few thousand targets.
+extern "C" int agx_edge_attrs_stats_list(const int32_t* edge_src, const int32_t* edge_dst, int64_t n_edges, int regular_k,
+                                         const int32_t* list, const int64_t* count, const float* src_rec,
+                                         const double* dst_rec, int want_len, int want_dir, int dir_rotated,
+                                         float* out_len, float* out_dir, double* stats, double* workspace, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    AGX_REQUIRE(stats && workspace && list && count, AGX_ERR_ARG, "agx_edge_attrs_stats_list: NULL buffer");
+    AGX_REQUIRE(regular_k > 0 && n_edges % regular_k == 0, AGX_ERR_ARG, "agx_edge_attrs_stats_list: n_edges is not a multiple of k");
+    int rc = attrs_check(edge_src, edge_dst, n_edges, src_rec, dst_rec, workspace);
+    if (rc) return rc;
+    AGX_REQUIRE((!want_len || out_len) && (!want_dir || out_dir), AGX_ERR_ARG,
+                "agx_edge_attrs_stats_list: give every requested output buffer");
+    int grid = 0;
+    if (n_edges > 0 && (want_len || want_dir)) {
+        grid = 32;
+        attrs_launch<1>(true, true, grid, stream, edge_src, edge_dst, n_edges, src_rec, dst_rec, want_len, 0, out_len,
+                        want_dir, dir_rotated, out_dir, workspace, nullptr, 0, list, count, regular_k);
+        agx_note_launch(1);
+    }
+    k_attr_fold<<<1, 256, 0, stream>>>(workspace, grid, stats);
+    agx_note_launch(1);
+    AGX_LAUNCH_OK();
+    return AGX_OK;
 }
 
 extern "C" int agx_edge_attrs_apply(const int32_t* edge_src, const int32_t* edge_dst, int64_t n_edges,

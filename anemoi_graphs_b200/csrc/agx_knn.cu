@@ -24,6 +24,7 @@
 // The edge SET is what parity is judged on, so the filter only has to isolate the k members; their float64
 // distances are evaluated only on request (out_rdist).
 #include <stdlib.h>
+#include <string.h>
 
 #include "agx_tile.cuh"
 
@@ -453,6 +454,81 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn(KnnArgs a) {
         }
         __syncwarp();  // every lane is done with the stage before the next tile overwrites it
     }
+}
+
+
+// Re-decision of an explicit LIST of queries (ascending query ids, count in device memory): one thread per listed
+// query searches the index from global memory and decides the set in float64 under the (ranked) tie rule.  A handful
+// of queries: no staging, no tile plan, no read-back.
+template <int CAP>
+__global__ void __launch_bounds__(128) k_knn_redecide_list(KnnArgs a, const int32_t* __restrict__ list,
+                                                           const int64_t* __restrict__ count) {
+    const int k = a.k;
+    const int64_t n = *count;
+    for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < n; w += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t q = list[w];
+        const float2 ql = a.q_latlon[q];
+        const float3 qv = agx_search_xyz(ql);
+        TopF<CAP> top;
+        AgxCap cap;
+        if (knn_thread_search<CAP>(a, qv, a.chord2_init, top, cap)) continue;  // beyond the search limit: left as it is
+        const float dk = top.d_at(k - 1);
+        const float amb = dk + 2.5f * agx_chord2_margin(dk);
+        TopD<CAP> fin;
+        fin.reset();
+        knn_redecide_global<CAP>(a, ql, qv, cap, amb, fin);
+        int32_t* os = a.out_src + q * k;
+#pragma unroll
+        for (int s = 0; s < CAP - 1; ++s)
+            if (s < k) os[s] = knn_out_label(a, fin.id[s]);
+    }
+}
+
+extern "C" int agx_knn_redecide_list(const agx_index_t* ix, const float* q_latlon, int64_t nq, int k, double max_radius,
+                                     int32_t* out_src, const int32_t* list, const int64_t* count, const int64_t* rank,
+                                     const int64_t* order, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    AGX_REQUIRE(ix != nullptr, AGX_ERR_ARG, "agx_knn_redecide_list: NULL index");
+    AGX_REQUIRE(k > 0 && (int64_t)k <= ix->n && k <= 64, AGX_ERR_ARG, "agx_knn_redecide_list: k out of range");
+    AGX_REQUIRE((rank == nullptr) == (order == nullptr), AGX_ERR_ARG, "agx_knn_redecide_list: give rank and order, or neither");
+    if (nq == 0) return AGX_OK;
+    AGX_REQUIRE(q_latlon && out_src && list && count, AGX_ERR_ARG, "agx_knn_redecide_list: NULL buffer");
+    KnnArgs a;
+    memset(&a, 0, sizeof(a));
+    a.pts = ix->pts;
+    a.cell_start = ix->cell_start;
+    a.ref_latlon = ix->latlon;
+    a.cells = ix->cells;
+    double t2 = 6.0 * (double)(k + 1) / (double)ix->n;
+    if (t2 > 4.0) t2 = 4.0;
+    a.chord2_limit = __builtin_inff();
+    if (max_radius > 0.0 && max_radius < 3.141592653589793) {
+        double sh = sin(0.5 * max_radius), c2 = 4.0 * sh * sh;
+        double lim = c2 + 5.0 * (4.2e-7 * sqrt(c2) + 1.0e-6 * c2 + 1.0e-13);
+        a.chord2_limit = (float)(lim * 1.000001);
+        if (t2 > lim) t2 = lim;
+    }
+    a.chord2_init = (float)t2;
+    a.q_latlon = (const float2*)q_latlon;
+    a.nq = nq;
+    a.k = k;
+    a.out_src = out_src;
+    a.tie_rank = rank;
+    a.tie_order = order;
+    const int grid = 32;  // a few thousand queries at most; grid-stride over the device-side count
+    if (k <= 3)
+        k_knn_redecide_list<4><<<grid, 128, 0, stream>>>(a, list, count);
+    else if (k <= 7)
+        k_knn_redecide_list<8><<<grid, 128, 0, stream>>>(a, list, count);
+    else if (k <= 16)
+        k_knn_redecide_list<17><<<grid, 128, 0, stream>>>(a, list, count);
+    else if (k <= 32)
+        k_knn_redecide_list<33><<<grid, 128, 0, stream>>>(a, list, count);
+    else
+        k_knn_redecide_list<65><<<grid, 128, 0, stream>>>(a, list, count);
+    AGX_LAUNCH_OK();
+    agx_note_launch(1);
+    return AGX_OK;
 }
 
 template <int CAP>

@@ -361,22 +361,126 @@ extern "C" int agx_mark_nodes(const int32_t* row, int64_t n, int64_t n_nodes, in
     return AGX_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// ascending list of the set bytes of a flag array (deterministic: count per tile, scan, fill)
+// ------------------------------------------------------------------------------------------------
+#define FLAG_TILE 1024  // flags per block: 256 threads x one 32-bit word
+__device__ __forceinline__ unsigned flag_word(const uint8_t* __restrict__ flags, int64_t n, int64_t i) {
+    if (i + 4 <= n) return *reinterpret_cast<const unsigned*>(flags + i);
+    unsigned w = 0;
+    for (int b = 0; b < 4; ++b)
+        if (i + b < n) w |= (unsigned)flags[i + b] << (8 * b);
+    return w;
+}
+__device__ __forceinline__ int flag_word_count(unsigned w) {
+    return ((w & 0xffu) != 0) + ((w & 0xff00u) != 0) + ((w & 0xff0000u) != 0) + ((w & 0xff000000u) != 0);
+}
+
+__global__ void __launch_bounds__(256) k_flag_counts(const uint8_t* __restrict__ flags, int64_t n, int32_t* __restrict__ counts) {
+    const int64_t i = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4;
+    int c = i < n ? flag_word_count(flag_word(flags, n, i)) : 0;
+    c = __reduce_add_sync(0xffffffffu, c);
+    __shared__ int warp_c[8];
+    if ((threadIdx.x & 31) == 0) warp_c[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w = 0; w < 8; ++w) t += warp_c[w];
+        counts[blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_flag_fill(const uint8_t* __restrict__ flags, int64_t n, const int64_t* __restrict__ offsets,
+                                                   int32_t* __restrict__ list) {
+    const int64_t i = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4;
+    unsigned w = i < n ? flag_word(flags, n, i) : 0u;
+    int c = flag_word_count(w);
+    // exclusive scan of c over the block
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    __shared__ int warp_tot[8];
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    int before = 0;
+    for (int k = 0; k < warp; ++k) before += warp_tot[k];
+    int64_t pos = offsets[blockIdx.x] + before + incl - c;
+    for (int b = 0; b < 4; ++b)
+        if ((w >> (8 * b)) & 0xffu) list[pos++] = (int32_t)(i + b);
+}
+
+extern "C" int agx_compact_flags(const uint8_t* flags, int64_t n, int32_t* list, int64_t* count, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    AGX_REQUIRE(n >= 0 && n < (int64_t)2147483647, AGX_ERR_ARG, "agx_compact_flags: n out of range");
+    AGX_REQUIRE(count != nullptr, AGX_ERR_ARG, "agx_compact_flags: count is NULL");
+    if (n == 0) {
+        AGX_CUDA_OK(cudaMemsetAsync(count, 0, sizeof(int64_t), stream));
+        return AGX_OK;
+    }
+    AGX_REQUIRE(flags && list, AGX_ERR_ARG, "agx_compact_flags: NULL buffer");
+    AGX_REQUIRE(((uintptr_t)flags & 3) == 0, AGX_ERR_ARG, "agx_compact_flags: flags must be 4-byte aligned");
+    const int64_t n_tiles = (n + FLAG_TILE - 1) / FLAG_TILE;
+    int32_t* counts = nullptr;
+    int64_t* offsets = nullptr;
+    agx_pool_keep_warm();
+    AGX_CUDA_OK(cudaMallocAsync(&counts, n_tiles * sizeof(int32_t), stream));
+    AGX_CUDA_OK(cudaMallocAsync(&offsets, (n_tiles + 1) * sizeof(int64_t), stream));
+    k_flag_counts<<<(unsigned)n_tiles, 256, 0, stream>>>(flags, n, counts);
+    agx_note_launch(1);
+    int rc = agx_exclusive_scan(counts, n_tiles, offsets, nullptr, stream);
+    if (rc == AGX_OK) {
+        k_flag_fill<<<(unsigned)n_tiles, 256, 0, stream>>>(flags, n, offsets, list);
+        agx_note_launch(1);
+        AGX_CUDA_OK(cudaMemcpyAsync(count, offsets + n_tiles, sizeof(int64_t), cudaMemcpyDeviceToDevice, stream));
+    }
+    cudaFreeAsync(counts, stream);
+    cudaFreeAsync(offsets, stream);
+    if (rc) return rc;
+    AGX_LAUNCH_OK();
+    return AGX_OK;
+}
+
 #define RELABEL_MAX_ROWS 8
 struct RelabelRows {
     int32_t* row[RELABEL_MAX_ROWS];
-    int64_t end[RELABEL_MAX_ROWS];  // exclusive prefix ends of the concatenated index space
+    int64_t len[RELABEL_MAX_ROWS];
+    int64_t end[RELABEL_MAX_ROWS];  // exclusive prefix ends of the concatenated work space (units of four entries)
     int n_rows;
 };
 
+// rows are walked in units of four entries (one 128-bit load / store when the row is 16-byte aligned; row starts of a
+// (2, E) list are only 4-byte aligned, so unaligned rows fall back to scalar accesses of the same four entries)
 __global__ void __launch_bounds__(256) k_relabel_rows(RelabelRows r, const int64_t* __restrict__ new_index) {
-    const int64_t total = r.end[r.n_rows - 1];
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t total = r.end[r.n_rows - 1];  // in units of four entries (per row: ceil(len / 4))
+    for (int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; u < total; u += (int64_t)gridDim.x * blockDim.x) {
         int which = 0;
 #pragma unroll
-        for (int w = 0; w < RELABEL_MAX_ROWS - 1; ++w) which += (w < r.n_rows - 1 && i >= r.end[w]) ? 1 : 0;
-        int64_t j = i - (which ? r.end[which - 1] : 0);
-        int32_t* row = r.row[which];
-        row[j] = (int32_t)new_index[row[j]];
+        for (int w = 0; w < RELABEL_MAX_ROWS - 1; ++w) which += (w < r.n_rows - 1 && u >= r.end[w]) ? 1 : 0;
+        int32_t* row = r.row[0];
+        int64_t len = r.len[0], first = 0;
+#pragma unroll
+        for (int w = 1; w < RELABEL_MAX_ROWS; ++w)
+            if (w == which) {
+                row = r.row[w];
+                len = r.len[w];
+                first = r.end[w - 1];
+            }
+        const int64_t j = (u - first) * 4;
+        if (j + 4 <= len && ((uintptr_t)(row + j) & 15) == 0) {
+            int4 v = *reinterpret_cast<int4*>(row + j);
+            v.x = (int32_t)new_index[v.x];
+            v.y = (int32_t)new_index[v.y];
+            v.z = (int32_t)new_index[v.z];
+            v.w = (int32_t)new_index[v.w];
+            *reinterpret_cast<int4*>(row + j) = v;
+        } else {
+            for (int64_t i = j; i < len && i < j + 4; ++i) row[i] = (int32_t)new_index[row[i]];
+        }
     }
 }
 
@@ -391,8 +495,9 @@ extern "C" int agx_relabel_rows(int32_t* const* rows, const int64_t* lens, int n
         AGX_REQUIRE(lens[i] >= 0, AGX_ERR_ARG, "agx_relabel_rows: negative length");
         if (lens[i] == 0) continue;
         AGX_REQUIRE(rows[i] != nullptr, AGX_ERR_ARG, "agx_relabel_rows: NULL row");
-        total += lens[i];
+        total += (lens[i] + 3) / 4;
         r.row[r.n_rows] = rows[i];
+        r.len[r.n_rows] = lens[i];
         r.end[r.n_rows] = total;
         r.n_rows++;
     }
@@ -400,6 +505,7 @@ extern "C" int agx_relabel_rows(int32_t* const* rows, const int64_t* lens, int n
     AGX_REQUIRE(new_index != nullptr, AGX_ERR_ARG, "agx_relabel_rows: new_index is NULL");
     for (int i = r.n_rows; i < RELABEL_MAX_ROWS; ++i) {
         r.row[i] = nullptr;
+        r.len[i] = 0;
         r.end[i] = total;
     }
     k_relabel_rows<<<agx_grid(total, 256, 8), 256, 0, stream>>>(r, new_index);

@@ -132,6 +132,15 @@ def maybe_flush() -> None:
 
 
 _copy_streams: dict = {}
+_order_streams: dict = {}
+
+
+def _order_stream(device: torch.device) -> torch.cuda.Stream:
+    """The stream a ``Provisional``'s worker thread uploads its index arrays and launches the resolve kernel on."""
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    if key not in _order_streams:
+        _order_streams[key] = torch.cuda.Stream(device=device, priority=-1)
+    return _order_streams[key]
 
 
 def _copy_stream(device: torch.device) -> torch.cuda.Stream:
@@ -313,9 +322,12 @@ class Provisional:
     Only a permutation is supported (same node count before and after)."""
 
     def __init__(self, x_prov: torch.Tensor, sorter, combine) -> None:
-        """``sorter(lat, lon)`` runs on the worker thread on contiguous host float32 columns and returns one or more
-        int64 index arrays; ``combine(*device_copies)`` turns them into the order (CUDA int64: generator index at
-        every graph position) on the device."""
+        """``sorter(lat, lon, emit)`` runs on the worker thread on contiguous host float32 columns, calls ``emit(array)``
+        for every int64 index array as soon as it is final and returns them all; ``combine`` turns them into the order
+        (CUDA int64: generator index at every graph position) on the device - ``"latlon"``: the two argsorts of
+        ``get_coordinates_ordering``, combined by ``agx_order_resolve`` which the WORKER launches on its own stream the
+        moment the second sort returns (no hand-over to the main thread in between); else a callable
+        ``combine(*device_copies)``."""
         import time
 
         self.x_prov = x_prov.contiguous()
@@ -326,15 +338,17 @@ class Provisional:
         self.x_final = torch.empty((n, 2), dtype=torch.float32, device=dev)
         self.x_host = None  # pinned (n, 2) float32 when the graph lives on the host
         self.order_host = torch.empty(n, dtype=torch.int64, pin_memory=True)  # ``_node_ordering``
-        self.order_dev = None
+        # everything the resolution needs exists before the sort ends
+        self.order_dev = torch.empty(n, dtype=torch.int64, device=dev)
+        self.rank = torch.empty(n + 1, dtype=torch.int64, device=dev)  # final position of every provisional label
         self.rows: list = []
         self.fixups: list = []
         self.finalizers: list = []
-        self.rank = None  # CUDA int64 (n + 1): final position of every provisional label, once resolved
         self.nodes = None
         self.state = None
         self.on_resolved = None
         self.done = False
+        self._order_ready = None  # event on the worker's stream: order / rank / x_final are complete
         # the worker needs the coordinates on the host, as two contiguous columns: one async copy behind the
         # kernel that produced them
         columns = self.x_prov.t().contiguous()
@@ -349,20 +363,47 @@ class Provisional:
             copied.record(side)
         columns.record_stream(side)
         self.trace = {"created": time.perf_counter()}
-        parts_pinned = torch.empty((2, n), dtype=torch.int64, pin_memory=True)  # the worker's results, ready for H2D
+        max_parts = 2
+        parts_pinned = torch.empty((max_parts, n), dtype=torch.int64, pin_memory=True)
+        parts_dev = torch.empty((max_parts, n), dtype=torch.int64, device=dev)
+        ostream = _order_stream(dev)
+        for t in (parts_dev, self.order_dev, self.rank, self.x_final, self.x_prov):
+            t.record_stream(ostream)
 
         def work():
+            from ._cabi import check, load_library
+
+            torch.cuda.set_device(dev)  # the device context is per thread
             self.trace["worker_start"] = time.perf_counter()
-            copied.synchronize()
+            copied.synchronize()  # the coordinates are on the host (and complete on the device)
             self.trace["coords_on_host"] = time.perf_counter()
             cols = staged.numpy()
-            out = sorter(cols[0], cols[1])
+            sent = []
+
+            def emit(part) -> None:  # an index array is final: pinned copy and upload while the next sort runs
+                i = len(sent)
+                if i < max_parts:
+                    parts_pinned[i].numpy()[:] = part
+                    with torch.cuda.stream(ostream):
+                        parts_dev[i].copy_(parts_pinned[i], non_blocking=True)
+                sent.append(part)
+
+            out = sorter(cols[0], cols[1], emit)
             out = out if isinstance(out, tuple) else (out,)
             self.trace["sorted"] = time.perf_counter()
-            if len(out) <= parts_pinned.shape[0]:  # hand the index arrays over in pinned memory
-                for i, part in enumerate(out):
-                    parts_pinned[i].numpy()[:] = part
-                return parts_pinned[: len(out)]
+            if self.combine == "latlon" and len(out) == 2 and len(sent) == 2:
+                # order, its inverse and the re-ordered coordinates in one kernel, launched from here
+                check(
+                    load_library().agx_order_resolve(
+                        parts_dev[0].data_ptr(), parts_dev[1].data_ptr(), n, self.x_prov.data_ptr(),
+                        self.x_final.data_ptr(), self.order_dev.data_ptr(), self.rank.data_ptr(), ostream.cuda_stream,
+                    )
+                )
+                done = torch.cuda.Event()
+                done.record(ostream)
+                self._order_ready = done
+                self.trace["order_launched"] = time.perf_counter()
+                return None
             return out
 
         self.future = _pool().submit(work)
@@ -398,33 +439,20 @@ class Provisional:
         self.done = True
         if self in _provisionals:
             _provisionals.remove(self)
-        from ._cabi import check, current_stream, load_library
-
         import time
 
         self.trace["resolve_enter"] = time.perf_counter()
-        parts = self.future.result()  # numpy int64 index arrays
+        parts = self.future.result()  # None: the worker has launched the resolve kernel itself
         self.trace["resolve_got_order"] = time.perf_counter()
         dev = self.x_prov.device
-        if isinstance(parts, torch.Tensor):
-            staged = parts
+        order_dev, rank = self.order_dev, self.rank
+        if parts is None:
+            torch.cuda.current_stream().wait_event(self._order_ready)
         else:
             staged = torch.empty((len(parts), self.n), dtype=torch.int64, pin_memory=True)
             for i, part in enumerate(parts):
                 staged[i].numpy()[:] = part
-        parts_dev = staged.to(dev, non_blocking=True)
-        lib = load_library()
-        rank = torch.empty(self.n + 1, dtype=torch.int64, device=dev)
-        if self.combine == "latlon" and int(parts_dev.shape[0]) == 2:
-            # order, its inverse and the re-ordered coordinates in one kernel
-            order_dev = torch.empty(self.n, dtype=torch.int64, device=dev)
-            check(
-                lib.agx_order_resolve(
-                    parts_dev[0].data_ptr(), parts_dev[1].data_ptr(), self.n, self.x_prov.data_ptr(),
-                    self.x_final.data_ptr(), order_dev.data_ptr(), rank.data_ptr(), current_stream(),
-                )
-            )
-        else:
+            parts_dev = staged.to(dev, non_blocking=True)
             order_dev = self.combine(*[parts_dev[i] for i in range(int(parts_dev.shape[0]))]).contiguous()
             rank[order_dev] = torch.arange(self.n, dtype=torch.int64, device=dev)
             torch.index_select(self.x_prov, 0, order_dev, out=self.x_final)
@@ -474,12 +502,14 @@ def active_provisional(nodes):
 # pickles a tensor's ``__dict__``, and a device-resident graph stores these very tensors, so attributes holding a
 # ``Provisional`` (a ``Future``, pinned buffers) would break ``torch.save(graph)`` and keep the buffers alive.
 class EdgeMeta:
-    __slots__ = ("prov", "fixup", "local", "tie_flags")
+    __slots__ = ("prov", "fixup", "local", "tie_flags", "tie_list", "regular_k")
 
     def __init__(self) -> None:
         self.prov = (None, None)  # (source row, target row): the Provisional whose numbering the row is in
         self.fixup = None  # Provisional that still has to re-decide KNN ties of this edge list ...
         self.tie_flags = None  # ... and the CUDA uint8 flag per TARGET node naming the queries it will re-decide
+        self.tie_list = None  # (list, count) = ops.compact_flags(tie_flags)
+        self.regular_k = 0  # k when the edges of target t are the columns [t k, (t + 1) k) (a KNN result)
         self.local = None  # (lo, hi, counts): this rank's own columns of a sharded edge list
 
 

@@ -131,9 +131,16 @@ def compute_attributes(graph, edges_name: tuple[str, str, str], attrs: dict) -> 
     # attributes depend on coordinates only, so they are evaluated right away against the matching (provisional)
     # node records.  Anything else - final rows against a provisional node set - needs the final order first.
     meta = _device.edge_meta(edge_index)
+    # KNN edges whose index-order ties are re-decided when the node order resolves: evaluated NOW (the trigonometry
+    # runs in the shadow of the host sort) with the re-decided targets' edges kept out of the statistics; those edges
+    # are evaluated again after the re-decision and the normalisation is applied then (``_deferred_attributes``)
     pending = meta.fixup if meta is not None else None
-    if pending is not None:  # KNN edges whose index-order ties are re-decided when the node order resolves
+    if pending is not None and pending.done:
+        pending = None
+    _, w = _device.world()
+    if pending is not None and (w > 1 or meta.tie_flags is None or len(ours) > 2):
         pending.resolve()
+        pending = None
     tags = _device.row_tags(edge_index)
     for row, name in ((0, source_name), (1, target_name)):
         prov = _device.active_provisional(graph[name])
@@ -147,7 +154,13 @@ def compute_attributes(graph, edges_name: tuple[str, str, str], attrs: dict) -> 
     dst = _device.node_tables(graph[target_name], provisional_ok=True)
     lengths = [(k, a) for k, a in ours.items() if isinstance(a, EdgeLength)]
     dirs = [(k, a) for k, a in ours.items() if isinstance(a, EdgeDirection)]
-    _, w = _device.world()
+    if pending is not None and len(lengths) <= 1 and len(dirs) <= 1:
+        out.update(_deferred_attributes(pending, meta, edge_index, src, dst, lengths, dirs, host_side))
+        return {k: out[k] for k in attrs}
+    if pending is not None:
+        pending.resolve()
+        src = _device.node_tables(graph[source_name], provisional_ok=True)
+        dst = _device.node_tables(graph[target_name], provisional_ok=True)
     local = meta.local if meta is not None else None  # set by a sharded builder: this rank's own columns
     while lengths or dirs:
         kl = lengths.pop(0) if lengths else None
@@ -163,3 +176,37 @@ def compute_attributes(graph, edges_name: tuple[str, str, str], attrs: dict) -> 
         if kd:
             out[kd[0]] = _device.to_host(dr) if host_side else dr
     return {k: out[k] for k in attrs}  # the recipe's order
+
+
+def _deferred_attributes(prov, meta, edge_index, src, dst, lengths, dirs, host_side: bool) -> dict:
+    """One EdgeLength and/or one EdgeDirection of an edge set that still waits for a KNN tie re-decision: raw pass now,
+    the re-decided edges again when the order resolves (a fixup: still provisional numbering, the same node records),
+    scaling and host copies after that (a finalizer).  Returns the tensors the graph stores: device tensors that are
+    complete in stream order, or pinned host tensors that are complete at ``flush()``."""
+    args = dict(length=False, direction=False)
+    for _, a in lengths + dirs:
+        args.update(a._kernel_args())
+    flag_list, flag_count = meta.tie_list if meta.tie_list is not None else (None, None)
+    job = ops.DeferredEdgeAttributes(
+        edge_index, src, dst, meta.tie_flags, flag_list=flag_list, flag_count=flag_count, regular_k=meta.regular_k, **args
+    )
+    job.raw()
+    prov.add_fixup(lambda p, job=job: job.patch())  # registered after the builder's re-decision: runs after it
+    results, host_targets = {}, []
+    for name, _ in lengths:
+        results[name] = job.out_len
+    for name, _ in dirs:
+        results[name] = job.out_dir
+    if host_side:
+        for name, dev_out in list(results.items()):
+            host = torch.empty(dev_out.shape, dtype=dev_out.dtype, pin_memory=True)
+            host_targets.append((dev_out, host))
+            results[name] = host
+
+    def finalize(p, job=job, host_targets=host_targets):
+        job.apply()
+        for dev_out, host in host_targets:
+            _device.to_host_into(dev_out, host)
+
+    prov.add_finalizer(finalize)
+    return results

@@ -246,10 +246,10 @@ class KNNEdges(BaseEdgeBuilder, NodeMaskingMixin):
     provisional_source_ok = True
 
     @staticmethod
-    def _redecide_ties(prov, index, out: torch.Tensor, flags: torch.Tensor, queries: torch.Tensor, k: int) -> None:
+    def _redecide_ties(prov, index, out: torch.Tensor, tie_list, queries: torch.Tensor, k: int) -> None:
         """Runs inside ``Provisional.resolve`` before the rows are relabelled: ``index`` is the one the search used
         (provisional labels); ties go to the lower FINAL label ``prov.rank[label]``, provisional labels are written."""
-        index.knn_redecide(queries, k, out, flags, rank=prov.rank, order=prov.order_dev)
+        index.knn_redecide_list(queries, k, out, tie_list[0], tie_list[1], rank=prov.rank, order=prov.order_dev)
         meta = _device.edge_meta(out)
         if meta is not None:
             meta.fixup = None
@@ -279,9 +279,10 @@ class KNNEdges(BaseEdgeBuilder, NodeMaskingMixin):
                 out = index.knn(dst, k, stats=self.stats, tie_flags=flags)
             out = _device.tag_rows(out, src_prov, None)
             meta = _device.edge_meta(out, create=True)
-            meta.fixup, meta.tie_flags = src_prov, flags
+            tie_list = ops.compact_flags(flags)  # ascending ids of the tied queries, count on the device: no read-back
+            meta.fixup, meta.tie_flags, meta.tie_list, meta.regular_k = src_prov, flags, tie_list, k
             # ``index`` stays alive in the closure: the re-decision searches it again, no second index
-            src_prov.add_fixup(lambda prov, index=index, out=out, flags=flags, dst=dst, k=k: self._redecide_ties(prov, index, out, flags, dst, k))  # fmt: skip
+            src_prov.add_fixup(lambda prov, index=index, out=out, tl=tie_list, dst=dst, k=k: self._redecide_ties(prov, index, out, tl, dst, k))  # fmt: skip
             return out
         lo, hi = _device.shard_range(nq, rank, w)
         with _device.neighbour_index(self._src_state if src_sel is None else None, src, hint_k=k) as index:
@@ -355,9 +356,8 @@ class CutOffEdges(BaseEdgeBuilder, NodeMaskingMixin):
         target_nodes = graph[self.target_name]
         mask = target_nodes[mask_attr] if mask_attr is not None else None
         # the reference distance does not depend on the numbering of the nodes
-        target_grid_reference_distance = get_grid_reference_distance(
-            _device.node_state(target_nodes, provisional_ok=True).x, mask
-        )
+        state = _device.node_state(target_nodes, provisional_ok=True)
+        target_grid_reference_distance = get_grid_reference_distance(state.x, mask, state=state)
         radius = target_grid_reference_distance * self.cutoff_factor
         return radius
 

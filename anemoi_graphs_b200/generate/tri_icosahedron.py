@@ -55,12 +55,17 @@ def _ordering_of(latlon_dev: torch.Tensor) -> torch.Tensor:
     return index_latitude[index_longitude.flip(0)]
 
 
-def _sort_columns_host(lat: np.ndarray, lon: np.ndarray):
+def _sort_columns_host(lat: np.ndarray, lon: np.ndarray, emit=None):
     """The host half of ``get_coordinates_ordering`` for a provisional node set (runs on the worker thread): the
     reference's two numpy argsorts on contiguous float32 columns and the gather between them.  Same calls on the
-    same values as ``_ordering_of`` - the permutation is numpy's."""
+    same values as ``_ordering_of`` - the permutation is numpy's.  ``emit`` receives each index array the moment it
+    is final (the first one is uploaded while the second sort runs)."""
     index_latitude = np.argsort(lon)
+    if emit is not None:
+        emit(index_latitude)
     index_longitude = np.argsort(lat[index_latitude])
+    if emit is not None:
+        emit(index_longitude)
     return index_latitude, index_longitude
 
 

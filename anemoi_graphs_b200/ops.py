@@ -172,6 +172,24 @@ class NeighbourIndex:
                     )
                 )
 
+    def knn_redecide_list(
+        self, q: torch.Tensor, k: int, out: torch.Tensor, flag_list: torch.Tensor, flag_count: torch.Tensor,
+        rank: torch.Tensor | None = None, order: torch.Tensor | None = None,
+    ) -> None:  # fmt: skip
+        """``knn_redecide`` driven by the ascending list of flagged query ids (``compact_flags``): one thread per
+        listed query (``agx_knn_redecide_list``)."""
+        q = _dev_x(q)
+        nq = int(q.shape[0])
+        assert out.shape == (2, nq * k) and out.dtype == torch.int32 and out.is_contiguous()
+        assert flag_list.dtype == torch.int32 and flag_count.dtype == torch.int64
+        with _span("knn_ties", nq):
+            check(
+                self.lib.agx_knn_redecide_list(
+                    self.handle, ptr(q), nq, int(k), 0.0, out.data_ptr(), ptr(flag_list), ptr(flag_count), ptr(rank),
+                    ptr(order), current_stream(),
+                )
+            )
+
     def radius_count(self, q: torch.Tensor, radius: float) -> tuple[torch.Tensor, int]:
         """Pass 1 of the cut-off search: ``(offsets (nq+1,) int64, total)``."""
         q = _dev_x(q)
@@ -237,7 +255,10 @@ REFDIST_K = 7  # self + 6: every neighbour that can tie for "nearest" on a degre
 REFDIST_MAX_CANDIDATES = 4096
 
 
-def grid_reference_distance(x: torch.Tensor) -> float:
+REFDIST_INDEX_HINT_K = 3  # cell width of the index the self query runs on: the one a KNN-3 decoder over the same nodes uses
+
+
+def grid_reference_distance(x: torch.Tensor, state=None) -> float:
     """``utils.get_grid_reference_distance`` (/root/reference/src/anemoi/graphs/utils.py:44-63): the largest
     strictly positive nearest-neighbour distance of a node set (column 1 of a k = 2 self query).
 
@@ -253,7 +274,11 @@ def grid_reference_distance(x: torch.Tensor) -> float:
     k = min(REFDIST_K, n)
     if k < 2:
         raise ValueError("zero-size array to reduction operation maximum which has no identity")
-    with NeighbourIndex(xd, hint_k=k) as index:
+    from . import device as _device
+
+    # the k = 7 self query of a node set is a small search whatever the cell width: it runs on the index a KNN-3
+    # decoder over the same nodes will use, so a recipe bins its hidden nodes once (device.neighbour_index)
+    with _device.neighbour_index(state, xd, hint_k=min(REFDIST_INDEX_HINT_K, k)) as index:
         ei, rdist = index.knn(xd, k, return_rdist=True, tag="knn_refdist")
     nearest = rdist[:, 1:].min(dim=1).values  # 0 where a duplicate point exists (excluded like ``dists > 0``)
     top = nearest.max()
@@ -457,6 +482,18 @@ def relabel_rows(rows: list[torch.Tensor], new_index: torch.Tensor) -> None:
 ATTR_FLAGS_SKIP, ATTR_FLAGS_ONLY = 1, 2
 
 
+def compact_flags(flags: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
+    """``(list, count)``: the ascending positions of the non-zero bytes of a CUDA uint8 array and their number (CUDA
+    int32 (n,) / int64 (1,); nothing is read back - consumers take the count from device memory)."""
+    assert flags.is_cuda and flags.dtype == torch.uint8 and flags.is_contiguous()
+    n = int(flags.numel())
+    out = torch.empty(max(n, 1), dtype=torch.int32, device=flags.device)
+    count = torch.empty(1, dtype=torch.int64, device=flags.device)
+    with _span("flag_list", n):
+        check(load_library().agx_compact_flags(ptr(flags), n, ptr(out), ptr(count), current_stream()))
+    return out, count
+
+
 class DeferredEdgeAttributes:
     """EdgeLength / EdgeDirection of an edge set whose sources of a FEW targets are still to be re-decided (KNN edges
     searched while the source numbering was provisional; ``dst_flags`` marks those targets).
@@ -467,10 +504,14 @@ class DeferredEdgeAttributes:
     Single rank only (a sharded build orders the nodes first)."""
 
     def __init__(self, edge_index, src: NodeTables, dst: NodeTables, dst_flags: torch.Tensor, length=True,
-                 length_norm=None, length_invert=False, direction=True, direction_norm=None, direction_rotated=True):  # fmt: skip
+                 length_norm=None, length_invert=False, direction=True, direction_norm=None, direction_rotated=True,
+                 flag_list=None, flag_count=None, regular_k: int = 0):  # fmt: skip
+        """``flag_list`` / ``flag_count`` (``compact_flags(dst_flags)``) with ``regular_k`` (the edges of target t are
+        columns [t k, (t + 1) k): a KNN result) let ``patch()`` touch the listed targets' edges only."""
         assert edge_index.is_cuda and edge_index.dtype == torch.int32 and edge_index.is_contiguous()
         assert dst_flags.dtype == torch.uint8 and dst_flags.is_cuda
         self.edge_index, self.flags = edge_index, dst_flags
+        self.flag_list, self.flag_count, self.regular_k = flag_list, flag_count, int(regular_k)
         self.n_edges = int(edge_index.shape[1])
         dev = edge_index.device
         self.length, self.direction, self.rotated, self.invert = bool(length), bool(direction), bool(direction_rotated), bool(length_invert)
@@ -501,7 +542,21 @@ class DeferredEdgeAttributes:
         self._pass(0, ATTR_FLAGS_SKIP, "edge_attrs_raw")
 
     def patch(self) -> None:
-        self._pass(1, ATTR_FLAGS_ONLY, "edge_attrs_patch")
+        if self.flag_list is None or self.regular_k <= 0:
+            self._pass(1, ATTR_FLAGS_ONLY, "edge_attrs_patch")
+            return
+        if self.n_edges == 0:
+            return
+        ei = self.edge_index
+        with _span("edge_attrs_patch", 0):
+            check(
+                load_library().agx_edge_attrs_stats_list(
+                    ei[0].data_ptr(), ei[1].data_ptr(), self.n_edges, self.regular_k, ptr(self.flag_list),
+                    ptr(self.flag_count), ptr(self.src_rec), ptr(self.dst_rec), int(self.length), int(self.direction),
+                    int(self.rotated), ptr(self.out_len), ptr(self.out_dir), self.stats[1].data_ptr(), ptr(self.ws),
+                    current_stream(),
+                )
+            )
 
     def apply(self) -> None:
         if self.n_edges == 0:

@@ -8,15 +8,17 @@ from . import device as _device
 from . import ops
 
 
-def get_grid_reference_distance(coords_rad: torch.Tensor, mask: torch.Tensor | None = None) -> float:
+def get_grid_reference_distance(coords_rad: torch.Tensor, mask: torch.Tensor | None = None, state=None) -> float:
     """Largest nearest-neighbour distance of a node set, float64 radians (utils.py:44-63).
 
-    Like the reference, ``mask`` is only shape-checked and otherwise ignored (utils.py:32-39)."""
+    Like the reference, ``mask`` is only shape-checked and otherwise ignored (utils.py:32-39).  ``state`` (the node
+    set's ``device.NodeState``, when ``coords_rad`` is its coordinate tensor) lets the search share the node set's
+    cached neighbour index with the other builders of the recipe."""
     assert mask is None or mask.shape == (
         coords_rad.shape[0],
         1,
     ), "Mask must have the same shape as the number of nodes."
-    return ops.grid_reference_distance(_device.to_device(coords_rad, torch.float32))
+    return ops.grid_reference_distance(_device.to_device(coords_rad, torch.float32), state=state)
 
 
 def concat_edges_device(e1: torch.Tensor, e2: torch.Tensor) -> torch.Tensor:

@@ -101,6 +101,16 @@ int agx_knn_redecide(const agx_index_t* index, const float* q_latlon /*DEV nq*2*
  * (the one agx_knn_flagged searched).  Ties go to the lower FINAL label rank[provisional label]; the k slots are
  * written as provisional labels again (order[final label]), so that one relabel pass afterwards treats every slot
  * of the row alike.  rank / order: DEV int64[n_reference], inverse permutations (agx_order_resolve).              */
+/* ... and driven by an explicit list of query ids (ascending, *count entries, device memory) instead of the flag
+ * array: one thread per listed query, no staging.  rank / order NULL: the index labels are final.               */
+int agx_knn_redecide_list(const agx_index_t* index, const float* q_latlon /*DEV nq*2*/, int64_t nq, int k,
+                          double max_radius, int32_t* out_src /*DEV nq*k*/, const int32_t* list /*DEV*/,
+                          const int64_t* count /*DEV*/, const int64_t* rank /*DEV or NULL*/,
+                          const int64_t* order /*DEV or NULL*/, void* stream);
+/* Ascending list of the positions of the non-zero bytes of flags[0..n) and its length (both device memory; list has
+ * room for n entries); no read-back.                                                                            */
+int agx_compact_flags(const uint8_t* flags /*DEV n, 4-byte aligned*/, int64_t n, int32_t* list /*DEV n*/,
+                      int64_t* count /*DEV 1*/, void* stream);
 int agx_knn_redecide_ranked(const agx_index_t* index, const float* q_latlon /*DEV nq*2*/, int64_t nq, int k,
                             double max_radius, int32_t* out_src /*DEV nq*k*/, const uint8_t* tie_flags /*DEV nq*/,
                             const int64_t* rank /*DEV*/, const int64_t* order /*DEV*/, void* stream);
@@ -203,6 +213,13 @@ int agx_edge_attrs_stats_flagged(const int32_t* edge_src, const int32_t* edge_ds
                                  const float* src_rec, const double* dst_rec, int want_len, int want_dir, int dir_rotated,
                                  float* out_len, float* out_dir, double* stats /*DEV 8*/, double* workspace,
                                  const uint8_t* dst_flags /*DEV*/, int flag_mode, void* stream);
+/* The "only" pass driven by an explicit LIST of targets of a regular-k edge list (edges of target t = [t k, (t+1) k),
+ * a KNN result; list = ascending target ids, *count = its length, both in device memory - agx_compact_flags): the few
+ * re-decided queries cost one small launch instead of a pass over every target index.                            */
+int agx_edge_attrs_stats_list(const int32_t* edge_src, const int32_t* edge_dst, int64_t n_edges, int regular_k,
+                              const int32_t* list /*DEV*/, const int64_t* count /*DEV*/, const float* src_rec,
+                              const double* dst_rec, int want_len, int want_dir, int dir_rotated, float* out_len,
+                              float* out_dir, double* stats /*DEV 8*/, double* workspace, void* stream);
 int agx_edge_attrs_apply(const int32_t* edge_src, const int32_t* edge_dst, int64_t n_edges, const float* src_rec,
                          const double* dst_rec, int len_norm, int len_invert, float* out_len, int dir_norm,
                          int dir_rotated, float* out_dir, const double* stats /*DEV n_stat_sets*8 or NULL if no norm*/,

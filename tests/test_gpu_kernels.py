@@ -479,3 +479,69 @@ def test_knn_flag_and_redecide_equals_final_numbering(ops, golden):
     oracle, info = R.knn_edges_canonical(hx, dx, k)  # the lower-index tie rule on the final labels
     assert info["tied_queries"].size == int(flags.sum().item()) == 88
     np.testing.assert_array_equal(canon(out), oracle)
+
+
+def test_knn_ranked_redecide_needs_no_second_index(ops, golden):
+    """``agx_knn_redecide_ranked``: the flagged queries are re-decided against the SAME provisionally labelled index
+    (ties by ``rank[label]``, provisional labels written), then ONE ``agx_relabel_rows`` launch gives the final row -
+    identical to searching the finally labelled points."""
+    g = golden("o96_res5")
+    hx = g["hidden_x"]
+    dx = grids.latlon_deg_to_x(*grids.octahedral_grid(96)).numpy()
+    k, nq, n = 3, dx.shape[0], hx.shape[0]
+    rng = np.random.default_rng(6)
+    perm = rng.permutation(n)  # provisional label p is final node perm[p]  => rank = perm, order = its inverse
+    rank = dev(perm.astype(np.int64))
+    order = torch.empty_like(rank)
+    order[rank] = torch.arange(n, dtype=torch.int64, device="cuda")
+    flags = torch.zeros(nq, dtype=torch.uint8, device="cuda")
+    with ops.NeighbourIndex(dev(_prov_coords(hx, perm)), hint_k=k) as index:
+        out = index.knn(dev(dx), k, tie_flags=flags)
+        before = out.clone()
+        index.knn_redecide(dev(dx), k, out, flags, rank=rank, order=order)
+    assert int(flags.sum().item()) == 88
+    changed = (before[0] != out[0]).view(nq, k).any(dim=1)
+    assert int(changed.sum().item()) > 0 and bool((flags[changed] == 1).all())  # only flagged queries are touched
+    other = torch.arange(7, dtype=torch.int32, device="cuda")  # a second row rides along in the same launch
+    want_other = rank[other.long()].to(torch.int32)
+    ops.relabel_rows([out[0], other], rank)
+    np.testing.assert_array_equal(other.cpu().numpy(), want_other.cpu().numpy())
+    oracle, info = R.knn_edges_canonical(hx, dx, k)  # the lower-index tie rule on the final labels
+    np.testing.assert_array_equal(canon(out), oracle)
+
+
+def _prov_coords(hx: np.ndarray, perm: np.ndarray) -> np.ndarray:
+    """Coordinates in provisional numbering when provisional label p is final node perm[p]."""
+    return hx[perm]
+
+
+def test_attribute_flag_modes_split_the_statistics(ops, golden):
+    """``agx_edge_attrs_stats_flagged``: "skip" + "only" partition the statistics of an edge set by target flag, and
+    the deferred three-step evaluation (raw / patch / apply) equals the one-call result."""
+    g = golden("toy")
+    dx, hx = g["data_x"], g["hidden_x"]
+    ei = dev(g["knn3_edge_index"].astype(np.int32))
+    src, dst = ops.NodeTables(dev(hx)), ops.NodeTables(dev(dx))
+    flags = torch.zeros(dx.shape[0], dtype=torch.uint8, device="cuda")
+    flags[::7] = 1
+    for norm in ("unit-std", "unit-range", "l1"):
+        want_len, want_dir = ops.edge_attributes(ei, src, dst, length_norm=norm, direction_norm=norm)
+        job = ops.DeferredEdgeAttributes(ei, src, dst, flags, length_norm=norm, direction_norm=norm)
+        job.raw()
+        job.out_len[(flags[ei[1].long()] == 1)] = float("nan")  # what "patch" must overwrite
+        job.patch()
+        job.apply()
+        np.testing.assert_allclose(job.out_len.cpu().numpy(), want_len.cpu().numpy(), rtol=3e-7)
+        np.testing.assert_allclose(job.out_dir.cpu().numpy(), want_dir.cpu().numpy(), rtol=3e-7, atol=1e-7)
+        # the two statistics sets add up to the whole set's
+        whole = torch.empty(8, dtype=torch.float64, device="cuda")
+        raw_len, raw_dir = torch.empty_like(want_len), torch.empty_like(want_dir)
+        check = __import__("anemoi_graphs_b200._cabi", fromlist=["check"]).check
+        check(ops.load_library().agx_edge_attrs_stats(ei[0].data_ptr(), ei[1].data_ptr(), int(ei.shape[1]), src.src_rec.data_ptr(),
+              dst.dst_rec.data_ptr(), 1, 1, 1, raw_len.data_ptr(), raw_dir.data_ptr(), whole.data_ptr(),
+              ops._attr_workspace(ei.device).data_ptr(), torch.cuda.current_stream().cuda_stream))  # fmt: skip
+        st = job.stats.cpu().numpy()
+        w = whole.cpu().numpy()
+        np.testing.assert_allclose(st[0, [0, 1, 4, 5]] + st[1, [0, 1, 4, 5]], w[[0, 1, 4, 5]], rtol=1e-12)
+        np.testing.assert_array_equal(np.minimum(st[0, [2, 6]], st[1, [2, 6]]), w[[2, 6]])
+        np.testing.assert_array_equal(np.maximum(st[0, [3, 7]], st[1, [3, 7]]), w[[3, 7]])
