@@ -49,6 +49,85 @@ def is_resident() -> bool:
     return _resident
 
 
+# Multi-GPU output mode.  "gather" (default): every rank ends with the complete graph (per-rank edge blocks are
+# all-gathered over NCCL).  "sharded": nothing is exchanged between the GPUs - a device-resident graph keeps each rank's
+# own block of every sharded edge set (global node ids, attributes normalised with the global statistics), and a
+# host-resident graph is assembled in ONE shared page-locked host buffer that every rank writes its block into over
+# its own PCIe link (``shm.HostArena``), so rank 0 - and every other rank - ends with the complete graph on the host.
+_sharded_output = __import__("os").environ.get("AGX_OUTPUT", "gather") == "sharded"
+_force_single = False
+_shared_host_used = False
+
+
+def set_sharded_output(flag: bool) -> bool:
+    global _sharded_output
+    prev, _sharded_output = _sharded_output, bool(flag)
+    return prev
+
+
+def sharded_output() -> bool:
+    """Sharded output mode is on AND this build runs on more than one rank."""
+    return _sharded_output and world()[1] > 1
+
+
+@contextlib.contextmanager
+def single_rank():
+    """Build as if this process were alone (parity checks of a sharded build against the one-GPU result)."""
+    global _force_single
+    prev, _force_single = _force_single, True
+    try:
+        yield
+    finally:
+        _force_single = prev
+
+
+@dataclass
+class Shard:
+    """How an edge set is spread over the ranks: ``counts[r]`` edges on rank ``r`` (blocks in rank order make the
+    single-GPU order), or ``replicated`` (every rank holds all of it: small sets are computed everywhere)."""
+
+    rank: int
+    world: int
+    counts: list
+    replicated: bool = False
+
+    @property
+    def total(self) -> int:
+        return int(self.counts[0]) if self.replicated else int(sum(self.counts))
+
+    @property
+    def offset(self) -> int:
+        return 0 if self.replicated else int(sum(self.counts[: self.rank]))
+
+    def describe(self) -> dict:
+        return {"rank": self.rank, "world": self.world, "counts": [int(c) for c in self.counts], "replicated": self.replicated}
+
+
+def host_tensor(shape, dtype: torch.dtype) -> torch.Tensor:
+    """Page-locked host tensor for a result: from the node-wide shared arena in sharded output mode (same bytes on
+    every rank), else this process's own pinned memory."""
+    if sharded_output():
+        from . import shm
+
+        arena = shm.arena()
+        if arena is not None:
+            global _shared_host_used
+            _shared_host_used = True
+            return arena.tensor(shape, dtype)
+    return torch.empty(tuple(shape), dtype=dtype, pin_memory=True)
+
+
+def exchange_counts(count: int, device: torch.device) -> list[int]:
+    """Every rank's ``count`` in rank order: through the shared-memory control block when the ranks share a node (a
+    host-side rendezvous of microseconds, the GPU queues keep running), else an NCCL all-gather + read-back."""
+    from . import shm
+
+    group = shm.local_group()
+    if group is not None:
+        return [row[0] for row in group.all_gather([int(count)])]
+    return all_gather_counts(int(count), device)
+
+
 def compute_device(like: torch.Tensor | None = None) -> torch.device:
     """The CUDA device this process computes on (raises without one: there is no CPU fallback)."""
     _cabi.require_cuda()
@@ -90,6 +169,19 @@ def flush() -> None:
     for prov in list(_provisionals):
         prov.resolve()
     wait_copies()
+    global _shared_host_used
+    if _shared_host_used:
+        # the shared host buffers are complete when EVERY rank's copies have landed
+        _shared_host_used = False
+        from . import shm
+
+        group = shm.local_group()
+        if group is not None:
+            import time
+
+            last_trace["copies_done"] = time.perf_counter()
+            group.barrier()
+            last_trace["node_barrier_done"] = time.perf_counter()
 
 
 def wait_copies() -> None:
@@ -150,14 +242,35 @@ def _copy_stream(device: torch.device) -> torch.cuda.Stream:
     return _copy_streams[key]
 
 
-def to_host(t: torch.Tensor) -> torch.Tensor:
+def to_host(t: torch.Tensor, shard: Shard | None = None, dim: int = 0) -> torch.Tensor:
     """Asynchronous copy of a CUDA tensor into a pinned host tensor (awaited by ``flush``).
 
     The copy runs on a dedicated stream behind an event recorded on the producing stream, so the PCIe transfer
-    of one edge set overlaps the kernels of the next."""
+    of one edge set overlaps the kernels of the next.  With ``shard`` (sharded output mode) ``t`` is this rank's block
+    along ``dim`` - or a replicated tensor, of which this rank copies its 1/W slice - and the result is the COMPLETE
+    tensor in the node-wide shared host buffer: every rank writes its part over its own PCIe link."""
     if not t.is_cuda:
         return t
     wait_for(t)
+    if shard is not None and shard.world > 1 and sharded_output():
+        full_shape = list(t.shape)
+        if shard.replicated:
+            lo, hi = shard_range(int(t.shape[dim]), shard.rank, shard.world)
+            src = t.narrow(dim, lo, hi - lo)
+        else:
+            full_shape[dim] = shard.total
+            lo, hi = shard.offset, shard.offset + int(t.shape[dim])
+            src = t
+        full = host_tensor(full_shape, t.dtype)
+        if hi > lo:
+            dst = full.narrow(dim, lo, hi - lo)
+            if dst.is_contiguous() and src.is_contiguous():
+                to_host_into(src, dst)
+            else:  # column block of a (R, E) row-major tensor: one contiguous run per row
+                assert t.dim() == 2 and dim == 1
+                for r in range(int(t.shape[0])):
+                    to_host_into(src[r], dst[r])
+        return full
     out = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
     if t.numel() == 0:
         return out
@@ -172,6 +285,28 @@ def to_host(t: torch.Tensor) -> torch.Tensor:
     t.record_stream(side)
     _pending.append(done)
     return out
+
+
+def copy_replicated_to_host(t: torch.Tensor, out: torch.Tensor) -> None:
+    """Copy a tensor every rank holds identically into ``out``: all of it, or - when ``out`` lives in the shared host
+    arena (sharded output mode) - this rank's 1/W slice along dim 0."""
+    if sharded_output() and _is_shared_host(out):
+        rank, w = world()
+        lo, hi = shard_range(int(t.shape[0]), rank, w)
+        if hi > lo:
+            to_host_into(t[lo:hi], out[lo:hi])
+        return
+    to_host_into(t, out)
+
+
+def _is_shared_host(t: torch.Tensor) -> bool:
+    from . import shm
+
+    arena = shm._arena
+    if arena is None:
+        return False
+    p = t.data_ptr()
+    return any(base <= p < base + size for base, size in ((seg.data_ptr(), seg.numel()) for seg in arena.segments.values()))
 
 
 def to_host_into(t: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
@@ -192,9 +327,9 @@ def to_host_into(t: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def like_input(result: torch.Tensor, reference_input: torch.Tensor) -> torch.Tensor:
+def like_input(result: torch.Tensor, reference_input: torch.Tensor, shard: Shard | None = None, dim: int = 0) -> torch.Tensor:
     """Return ``result`` (CUDA) on the device the caller's input lives on."""
-    return result if reference_input.is_cuda else to_host(result)
+    return result if reference_input.is_cuda else to_host(result, shard, dim)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -292,6 +427,8 @@ def node_tables(nodes, with_rotation: bool = True, provisional_ok: bool = False)
 # provisional numbering: edge construction that overlaps the host-side node ordering
 # --------------------------------------------------------------------------------------------------
 _provisionals: list = []
+_prov_seq = 0
+SHARED_NODE_ORDER = __import__("os").environ.get("AGX_SHARED_ORDER", "1") != "0"
 _order_pool = None
 last_trace: dict = {}  # host timestamps of the most recent provisional node set (tools/step_timeline.py)
 # AGX_LAZY_ORDER=0 restores the serial "sort, then build" order of operations (A/B measurements)
@@ -337,7 +474,7 @@ class Provisional:
         self.combine = combine
         self.x_final = torch.empty((n, 2), dtype=torch.float32, device=dev)
         self.x_host = None  # pinned (n, 2) float32 when the graph lives on the host
-        self.order_host = torch.empty(n, dtype=torch.int64, pin_memory=True)  # ``_node_ordering``
+        self.order_host = host_tensor((n,), torch.int64)  # ``_node_ordering`` (shared host buffer in sharded output mode)
         # everything the resolution needs exists before the sort ends
         self.order_dev = torch.empty(n, dtype=torch.int64, device=dev)
         self.rank = torch.empty(n + 1, dtype=torch.int64, device=dev)  # final position of every provisional label
@@ -364,8 +501,25 @@ class Provisional:
         columns.record_stream(side)
         self.trace = {"created": time.perf_counter()}
         max_parts = 2
-        parts_pinned = torch.empty((max_parts, n), dtype=torch.int64, pin_memory=True)
+        # More than one rank on this node: ONE rank sorts, the index arrays travel through the shared page-locked host
+        # arena (every rank uploads them from there), the others' workers wait on a stamp in the control block - one
+        # host sort per node instead of one per GPU (8 AVX-512 sorts side by side slow each other down).
+        group, prov_seq = None, 0
+        if SHARED_NODE_ORDER and world()[1] > 1:
+            from . import shm
+
+            group = shm.local_group()
+        if group is not None:
+            global _prov_seq
+            global _shared_host_used
+            _shared_host_used = True  # flush() ends with the node-wide barrier
+            prov_seq, _prov_seq = _prov_seq, _prov_seq + 1
+            parts_pinned = shm.arena().tensor((max_parts, n), torch.int64)
+            stamps = group.order[prov_seq % shm.RING]
+        else:
+            parts_pinned = torch.empty((max_parts, n), dtype=torch.int64, pin_memory=True)
         parts_dev = torch.empty((max_parts, n), dtype=torch.int64, device=dev)
+        follower = group is not None and group.rank != 0
         ostream = _order_stream(dev)
         for t in (parts_dev, self.order_dev, self.rank, self.x_final, self.x_prov):
             t.record_stream(ostream)
@@ -382,14 +536,29 @@ class Provisional:
 
             def emit(part) -> None:  # an index array is final: pinned copy and upload while the next sort runs
                 i = len(sent)
+                self.trace[f"part{i}_ready"] = time.perf_counter()
                 if i < max_parts:
-                    parts_pinned[i].numpy()[:] = part
+                    if part is not None:
+                        parts_pinned[i].numpy()[:] = part
+                        if group is not None:
+                            stamps[i] = prov_seq + 1  # the followers may read part i now ...
+                            group.wake_followers()  # ... and are asleep in read(2): one byte each
                     with torch.cuda.stream(ostream):
                         parts_dev[i].copy_(parts_pinned[i], non_blocking=True)
                 sent.append(part)
+                self.trace[f"part{i}_sent"] = time.perf_counter()
 
-            out = sorter(cols[0], cols[1], emit)
-            out = out if isinstance(out, tuple) else (out,)
+            if follower:
+                from . import shm
+
+                for i in range(max_parts):  # the sorting rank's arrays, as they appear: one wake-up byte per array
+                    group.sleep_until_woken()
+                    shm._spin(lambda i=i: int(stamps[i]) == prov_seq + 1, f"part {i} of node order {prov_seq}")
+                    emit(None)
+                out = (None, None)
+            else:
+                out = sorter(cols[0], cols[1], emit)
+                out = out if isinstance(out, tuple) else (out,)
             self.trace["sorted"] = time.perf_counter()
             if self.combine == "latlon" and len(out) == 2 and len(sent) == 2:
                 # order, its inverse and the re-ordered coordinates in one kernel, launched from here
@@ -402,8 +571,11 @@ class Provisional:
                 done = torch.cuda.Event()
                 done.record(ostream)
                 self._order_ready = done
+                if group is not None:
+                    _pending.append(done)  # awaited before the end-of-build barrier: the shared arrays have been read
                 self.trace["order_launched"] = time.perf_counter()
                 return None
+            assert not follower, "a shared node order needs the 'latlon' combine"
             return out
 
         self.future = _pool().submit(work)
@@ -417,10 +589,11 @@ class Provisional:
         state.prov = self
         state.x = self.x_prov
 
-    def add_row(self, tensor: torch.Tensor, row: int, host: torch.Tensor | None) -> None:
-        """``tensor[row]`` (CUDA int32 (2, E)) holds provisional indices of this node set; ``host`` is the pinned
-        (2, E) tensor whose row receives the final ones (None: the graph is device-resident)."""
-        self.rows.append((tensor, row, host))
+    def add_row(self, tensor: torch.Tensor, row: int, host_row: torch.Tensor | None, cols: tuple | None = None) -> None:
+        """``tensor[row]`` (CUDA int32 (2, E)) holds provisional indices of this node set; ``host_row`` is the pinned
+        1-D destination of the final ones (None: the graph is device-resident) - of the whole row, or of its columns
+        ``cols = (lo, hi)`` (a replicated edge set in sharded output mode: every rank copies a slice)."""
+        self.rows.append((tensor, row, host_row, cols))
 
     def add_fixup(self, fn) -> None:
         """``fn(self)`` runs when the order resolves (``self.rank`` / ``self.order_dev`` are known), BEFORE the
@@ -456,7 +629,7 @@ class Provisional:
             order_dev = self.combine(*[parts_dev[i] for i in range(int(parts_dev.shape[0]))]).contiguous()
             rank[order_dev] = torch.arange(self.n, dtype=torch.int64, device=dev)
             torch.index_select(self.x_prov, 0, order_dev, out=self.x_final)
-        to_host_into(order_dev, self.order_host)  # ``_node_ordering``: complete at flush like every host copy
+        copy_replicated_to_host(order_dev, self.order_host)  # ``_node_ordering``: complete at flush like every host copy
         self.order_dev = order_dev
         self.rank = rank
         fixups, self.fixups = self.fixups, []
@@ -464,18 +637,18 @@ class Provisional:
             fn(self)
         from . import ops
 
-        for tensor, row, host in self.rows:
+        for tensor, row, host_row, cols in self.rows:
             wait_for(tensor)  # a sharded builder's all-gather may still be filling it
-        ops.relabel_rows([tensor[row] for tensor, row, host in self.rows], rank)  # one launch for all rows
-        for tensor, row, host in self.rows:
-            if host is not None:
-                to_host_into(tensor[row], host[row])
+        ops.relabel_rows([tensor[row] for tensor, row, host_row, cols in self.rows], rank)  # one launch for all rows
+        for tensor, row, host_row, cols in self.rows:
+            if host_row is not None and host_row.numel():
+                to_host_into(tensor[row] if cols is None else tensor[row, cols[0] : cols[1]], host_row)
         self.rows = []
         finalizers, self.finalizers = self.finalizers, []
         for fn in finalizers:
             fn(self)
         if self.x_host is not None:
-            to_host_into(self.x_final, self.x_host)
+            copy_replicated_to_host(self.x_final, self.x_host)
         if self.state is not None:
             st = self.state
             st.prov = None
@@ -502,7 +675,7 @@ def active_provisional(nodes):
 # pickles a tensor's ``__dict__``, and a device-resident graph stores these very tensors, so attributes holding a
 # ``Provisional`` (a ``Future``, pinned buffers) would break ``torch.save(graph)`` and keep the buffers alive.
 class EdgeMeta:
-    __slots__ = ("prov", "fixup", "local", "tie_flags", "tie_list", "regular_k")
+    __slots__ = ("prov", "fixup", "local", "tie_flags", "tie_list", "regular_k", "shard", "flag_base")
 
     def __init__(self) -> None:
         self.prov = (None, None)  # (source row, target row): the Provisional whose numbering the row is in
@@ -510,6 +683,8 @@ class EdgeMeta:
         self.tie_flags = None  # ... and the CUDA uint8 flag per TARGET node naming the queries it will re-decide
         self.tie_list = None  # (list, count) = ops.compact_flags(tie_flags)
         self.regular_k = 0  # k when the edges of target t are the columns [t k, (t + 1) k) (a KNN result)
+        self.flag_base = 0  # tie_flags[t - flag_base] belongs to target t (a rank's block starts at its first target)
+        self.shard = None  # Shard: sharded output mode - this tensor is the rank's own block (or a replicated set)
         self.local = None  # (lo, hi, counts): this rank's own columns of a sharded edge list
 
 
@@ -543,23 +718,43 @@ def row_tags(edge_index: torch.Tensor) -> tuple:
     return tuple(p if (p is not None and not p.done) else None for p in tags)
 
 
+def edge_shard(edge_index: torch.Tensor) -> Shard | None:
+    meta = edge_meta(edge_index)
+    return meta.shard if meta is not None else None
+
+
 def edge_index_like_input(edge_dev: torch.Tensor, reference_input: torch.Tensor) -> torch.Tensor:
     """``like_input`` for an edge_index that may carry provisional rows: final rows are copied (or returned) now,
-    provisional rows are registered with their node set and complete when it resolves."""
+    provisional rows are registered with their node set and complete when it resolves.  In sharded output mode the host
+    result is the complete (2, E) list in the shared host buffer; this rank fills its own columns."""
     tags = row_tags(edge_dev)
+    shard = edge_shard(edge_dev)
+    if shard is not None and not (shard.world > 1 and sharded_output()):
+        shard = None
     if tags == (None, None):
-        return like_input(edge_dev, reference_input)
+        return like_input(edge_dev, reference_input, shard, dim=1)
     if reference_input.is_cuda:
         for row, prov in enumerate(tags):
             if prov is not None:
                 prov.add_row(edge_dev, row, None)
         return edge_dev
-    out = torch.empty(edge_dev.shape, dtype=edge_dev.dtype, pin_memory=True)
-    for row, prov in enumerate(tags):
-        if prov is None:
-            to_host_into(edge_dev[row], out[row])
+    if shard is None:
+        out = torch.empty(edge_dev.shape, dtype=edge_dev.dtype, pin_memory=True)
+        lo, hi, cols = 0, int(edge_dev.shape[1]), None
+    else:
+        out = host_tensor((2, shard.total), edge_dev.dtype)
+        if shard.replicated:
+            lo, hi = shard_range(int(edge_dev.shape[1]), shard.rank, shard.world)
+            cols = (lo, hi)  # of the (complete) device tensor
         else:
-            prov.add_row(edge_dev, row, out)
+            lo, hi, cols = shard.offset, shard.offset + int(edge_dev.shape[1]), None
+    for row, prov in enumerate(tags):
+        host_row = out[row, lo:hi]
+        if prov is None:
+            if hi > lo:
+                to_host_into(edge_dev[row] if cols is None else edge_dev[row, cols[0] : cols[1]], host_row)
+        else:
+            prov.add_row(edge_dev, row, host_row, cols)
     return out
 
 
@@ -588,7 +783,7 @@ def world() -> tuple[int, int]:
     """(rank, world_size) of the sharded build; (0, 1) when torch.distributed is not initialised."""
     import torch.distributed as dist
 
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+    if not _force_single and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         return dist.get_rank(), dist.get_world_size()
     return 0, 1
 

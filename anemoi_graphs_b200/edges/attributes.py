@@ -138,7 +138,7 @@ def compute_attributes(graph, edges_name: tuple[str, str, str], attrs: dict) -> 
     if pending is not None and pending.done:
         pending = None
     _, w = _device.world()
-    if pending is not None and (w > 1 or meta.tie_flags is None or len(ours) > 2):
+    if pending is not None and ((w > 1 and not _device.sharded_output()) or meta.tie_flags is None or len(ours) > 2):
         pending.resolve()
         pending = None
     tags = _device.row_tags(edge_index)
@@ -165,16 +165,17 @@ def compute_attributes(graph, edges_name: tuple[str, str, str], attrs: dict) -> 
     while lengths or dirs:
         kl = lengths.pop(0) if lengths else None
         kd = dirs.pop(0) if dirs else None
-        args = dict(length=False, direction=False, sharded=w > 1, local=local)
+        shard = meta.shard if (meta is not None and _device.sharded_output()) else None
+        args = dict(length=False, direction=False, sharded=w > 1, local=local, shard=shard)
         if kl:
             args.update(kl[1]._kernel_args())
         if kd:
             args.update(kd[1]._kernel_args())
         ln, dr = ops.edge_attributes(edge_index, src, dst, **args)
         if kl:
-            out[kl[0]] = _device.to_host(ln) if host_side else ln
+            out[kl[0]] = _device.to_host(ln, shard) if host_side else ln
         if kd:
-            out[kd[0]] = _device.to_host(dr) if host_side else dr
+            out[kd[0]] = _device.to_host(dr, shard) if host_side else dr
     return {k: out[k] for k in attrs}  # the recipe's order
 
 
@@ -188,7 +189,8 @@ def _deferred_attributes(prov, meta, edge_index, src, dst, lengths, dirs, host_s
         args.update(a._kernel_args())
     flag_list, flag_count = meta.tie_list if meta.tie_list is not None else (None, None)
     job = ops.DeferredEdgeAttributes(
-        edge_index, src, dst, meta.tie_flags, flag_list=flag_list, flag_count=flag_count, regular_k=meta.regular_k, **args
+        edge_index, src, dst, meta.tie_flags, flag_list=flag_list, flag_count=flag_count, regular_k=meta.regular_k,
+        flag_base=meta.flag_base, shard=meta.shard, **args
     )
     job.raw()
     prov.add_fixup(lambda p, job=job: job.patch())  # registered after the builder's re-decision: runs after it
@@ -198,15 +200,20 @@ def _deferred_attributes(prov, meta, edge_index, src, dst, lengths, dirs, host_s
     for name, _ in dirs:
         results[name] = job.out_dir
     if host_side:
+        shard = meta.shard if (meta.shard is not None and _device.sharded_output()) else None
         for name, dev_out in list(results.items()):
-            host = torch.empty(dev_out.shape, dtype=dev_out.dtype, pin_memory=True)
-            host_targets.append((dev_out, host))
+            if shard is None:
+                host = dest = torch.empty(dev_out.shape, dtype=dev_out.dtype, pin_memory=True)
+            else:  # the complete array in the shared host buffer; this rank fills its rows
+                host = _device.host_tensor((shard.total, int(dev_out.shape[1])), dev_out.dtype)
+                dest = host[shard.offset : shard.offset + int(dev_out.shape[0])]
+            host_targets.append((dev_out, dest))
             results[name] = host
 
     def finalize(p, job=job, host_targets=host_targets):
         job.apply()
-        for dev_out, host in host_targets:
-            _device.to_host_into(dev_out, host)
+        for dev_out, dest in host_targets:
+            _device.to_host_into(dev_out, dest)
 
     prov.add_finalizer(finalize)
     return results

@@ -101,7 +101,7 @@ class BaseEdgeBuilder(ABC):
         """Edge indices (2, num_edges) int32 of source and target nodes (edges/builder.py:69-87)."""
         self._provisional_ok = False
         dev = self.get_edge_index_device(graph)
-        out = _device.like_input(dev, graph[self.target_name]["x"])
+        out = _device.like_input(dev, graph[self.target_name]["x"], _device.edge_shard(dev), dim=1)
         _device.maybe_flush()
         return out
 
@@ -118,6 +118,11 @@ class BaseEdgeBuilder(ABC):
 
         if "edge_index" in store:
             # Expand current edge indices: sorted unique columns (utils.concat_edges)
+            if _device.sharded_output():
+                raise NotImplementedError(
+                    "several edge builders on one node pair are merged on complete edge lists: build this recipe in the "
+                    "default output mode (AGX_OUTPUT=gather / device.set_sharded_output(False))"
+                )
             edge_dev = concat_edges_device(_device.device_edge_index(store), edge_dev)
             if edge_type not in store["edge_type"]:
                 store["edge_type"] = store["edge_type"] + "," + edge_type
@@ -127,6 +132,9 @@ class BaseEdgeBuilder(ABC):
         out = _device.edge_index_like_input(edge_dev, x)
         store["edge_index"] = out
         _device.remember_edge_index(store, out, edge_dev)
+        shard = _device.edge_shard(edge_dev)
+        if shard is not None and x.is_cuda:
+            store["edge_shard"] = shard.describe()  # a device-resident sharded graph: which block this rank holds
         _device.maybe_flush()
         return graph
 
@@ -265,26 +273,41 @@ class KNNEdges(BaseEdgeBuilder, NodeMaskingMixin):
         )
         k = self.num_nearest_neighbours
         nq = int(dst.shape[0])
-        rank, w = _device.shard_world(nq)
+        # sharded output mode: this rank's queries only and nothing to exchange, so sharding always pays; otherwise
+        # every rank needs the complete list and small searches are replicated (``shard_world``)
+        sharded_out = _device.sharded_output()
+        rank, w = _device.world() if sharded_out else _device.shard_world(nq)
         src_prov, dst_prov = self._row_provs
-        if src_prov is not None and (w > 1 or dst_prov is not None):
-            # flag-and-redecide is built for the plain case only (one rank, final target numbering): order first
+        if src_prov is not None and ((w > 1 and not sharded_out) or dst_prov is not None):
+            # flag-and-redecide is built for final target numbering and rank-local results: order first
             src = _device.node_state(source_nodes).x
             dst = _device.node_state(target_nodes).x
             self._row_provs = (None, None)
             src_prov = dst_prov = None
+        lo, hi = _device.shard_range(nq, rank, w)
+        shard = None
+        if sharded_out:
+            shard = _device.Shard(rank, w, [(b - a) * k for a, b in (_device.shard_range(nq, r, w) for r in range(w))])
         if src_prov is not None:
-            flags = torch.zeros(nq, dtype=torch.uint8, device=dst.device)
+            q = dst[lo:hi]  # all queries on one rank
+            flags = torch.zeros(hi - lo, dtype=torch.uint8, device=dst.device)
             with _device.neighbour_index(self._src_state, src, hint_k=k) as index:
-                out = index.knn(dst, k, stats=self.stats, tie_flags=flags)
+                out = index.knn(q, k, dst_base=lo, stats=self.stats, tie_flags=flags)
             out = _device.tag_rows(out, src_prov, None)
             meta = _device.edge_meta(out, create=True)
             tie_list = ops.compact_flags(flags)  # ascending ids of the tied queries, count on the device: no read-back
-            meta.fixup, meta.tie_flags, meta.tie_list, meta.regular_k = src_prov, flags, tie_list, k
+            meta.fixup, meta.tie_flags, meta.tie_list, meta.regular_k, meta.shard = src_prov, flags, tie_list, k, shard
+            meta.flag_base = lo  # ``flags`` is indexed by target id - lo
             # ``index`` stays alive in the closure: the re-decision searches it again, no second index
-            src_prov.add_fixup(lambda prov, index=index, out=out, tl=tie_list, dst=dst, k=k: self._redecide_ties(prov, index, out, tl, dst, k))  # fmt: skip
+            src_prov.add_fixup(lambda prov, index=index, out=out, tl=tie_list, q=q, k=k: self._redecide_ties(prov, index, out, tl, q, k))  # fmt: skip
             return out
-        lo, hi = _device.shard_range(nq, rank, w)
+        if sharded_out:
+            # rank-local block, global target ids; no exchange
+            with _device.neighbour_index(self._src_state if src_sel is None else None, src, hint_k=k) as index:
+                out = index.knn(dst[lo:hi], k, dst_base=lo, stats=self.stats)
+            out = _device.tag_rows(self.undo_masking(out, src_sel, dst_sel), *self._row_provs)
+            _device.edge_meta(out, create=True).shard = shard
+            return out
         with _device.neighbour_index(self._src_state if src_sel is None else None, src, hint_k=k) as index:
             out = torch.empty((2, nq * k), dtype=torch.int32, device=dst.device)
             masked = src_sel is not None or dst_sel is not None
@@ -375,8 +398,20 @@ class CutOffEdges(BaseEdgeBuilder, NodeMaskingMixin):
             self.target_name,
         )
         nq = int(dst.shape[0])
-        rank, w = _device.shard_world(nq)
+        sharded_out = _device.sharded_output()
+        rank, w = _device.world() if sharded_out else _device.shard_world(nq)
         lo, hi = _device.shard_range(nq, rank, w)
+        if sharded_out:
+            # this rank's targets only; the blocks stay where they are (global target ids), only the counts travel
+            with ops.NeighbourIndex(src, hint_radius=self.radius) as index:
+                q = dst[lo:hi]
+                offsets, total = index.radius_count(q, self.radius)
+                out = torch.empty((2, total), dtype=torch.int32, device=dst.device)
+                index.radius_fill(q, self.radius, offsets, total, out, 0, dst_base=lo, stats=self.stats)
+            counts = _device.exchange_counts(total, dst.device)
+            out = _device.tag_rows(self.undo_masking(out, src_sel, dst_sel), *self._row_provs)
+            _device.edge_meta(out, create=True).shard = _device.Shard(rank, w, counts)
+            return out
         with ops.NeighbourIndex(src, hint_radius=self.radius) as index:
             q = dst[lo:hi]
             offsets, total = index.radius_count(q, self.radius)
@@ -474,6 +509,15 @@ class MultiScaleEdges(BaseEdgeBuilder):
                 source_nodes, resolutions=source_nodes["_resolutions"], x_hops=self.x_hops
             )
         raise ValueError(f"Invalid node type {node_type}")
+
+    def get_edge_index_device(self, graph) -> torch.Tensor:
+        out = super().get_edge_index_device(graph)
+        if _device.sharded_output():
+            # replicas only: every rank computes the whole (small) set; a host-resident graph receives 1/W
+            # of its columns from each rank
+            rank, w = _device.world()
+            _device.edge_meta(out, create=True).shard = _device.Shard(rank, w, [int(out.shape[1])], replicated=True)
+        return out
 
     def update_graph(self, graph, attrs_config: DotDict | None = None):
         node_type = graph[self.source_name].node_type

@@ -62,7 +62,7 @@ class IcosahedralNodes(BaseNodeBuilder, ABC):
             self.node_ordering = prov.order_host.numpy()
             if _device.is_resident():
                 return prov.x_final
-            prov.x_host = torch.empty((prov.n, 2), dtype=torch.float32, pin_memory=True)
+            prov.x_host = _device.host_tensor((prov.n, 2), torch.float32)
             return prov.x_host
         self.nx_graph, coords_rad, order = self.create_nodes()
         # == torch.tensor(coords_rad[node_ordering], dtype=torch.float32), gathered (and, for the float64 hexagonal

@@ -380,6 +380,7 @@ def edge_attributes(
     direction_rotated: bool = True,
     sharded: bool = False,
     local: tuple[int, int, list[int]] | None = None,
+    shard=None,
 ):
     """Fused EdgeLength / EdgeDirection: returns ``(len (E, 1) float32 | None, dir (E, 2) float32 | None)``.
 
@@ -388,7 +389,8 @@ def edge_attributes(
     all-gathered asynchronously, so every rank ends with the complete arrays (complete once ``device.wait_for`` /
     ``device.flush`` has run).  ``local = (lo, hi, counts)`` names the range this rank's own builder produced
     (its columns of ``edge_index`` are valid before the edge all-gather has finished) and every rank's block
-    size; without it the edges are split evenly."""
+    size; without it the edges are split evenly.  ``shard`` (``device.Shard``, sharded output mode): ``edge_index`` is
+    this rank's own block and so are the results - only the statistics are exchanged."""
     from . import device as _device
 
     for norm in (length_norm, direction_norm):
@@ -409,6 +411,34 @@ def edge_attributes(
     len_code = NORM_CODES[length_norm] if length else -1
     dir_code = NORM_CODES[direction_norm] if direction else -1
     rank, w = _device.world() if sharded else (0, 1)
+    if shard is not None and shard.world > 1 and not shard.replicated:
+        # sharded output mode: ``edge_index`` IS this rank's block.  One pass for the raw values and the block's
+        # statistics, the (W, 8) statistics all-gathered (folded in rank order inside the kernel), scaling in place;
+        # the attribute blocks stay on their ranks.
+        ws, stream = _attr_workspace(dev), current_stream()
+        e_src, e_dst = edge_index[0].data_ptr(), edge_index[1].data_ptr()
+        stats = None
+        if len_code > 0 or dir_code > 0:
+            stats = torch.empty(8, dtype=torch.float64, device=dev)
+            with _span("edge_attrs_stats", n_edges):
+                check(
+                    lib.agx_edge_attrs_stats(
+                        e_src, e_dst, n_edges, ptr(src_rec), ptr(dst_rec), int(length), int(direction),
+                        int(bool(direction_rotated)), ptr(out_len), ptr(out_dir), ptr(stats), ptr(ws), stream,
+                    )
+                )
+            stats = _device.all_gather_stats_raw(stats)
+        with _span("edge_attrs_apply", n_edges):
+            check(
+                lib.agx_edge_attrs_apply(
+                    e_src, e_dst, n_edges, ptr(src_rec), ptr(dst_rec), len_code, int(bool(length_invert)), ptr(out_len),
+                    dir_code, int(bool(direction_rotated)), ptr(out_dir), ptr(stats), shard.world if stats is not None else 0,
+                    shard.total, 1 if stats is not None else 0, ptr(ws), stream,
+                )
+            )
+        return out_len, out_dir
+    if shard is not None:
+        w = 1  # a replicated set in sharded output mode: every rank evaluates all of it
     if w > 1 and local is None and n_edges < ATTR_SHARD_MIN_EDGES:
         w = 1  # small edge set: every rank evaluates all of it (identical results, no exchange)
     ws = _attr_workspace(dev)
@@ -505,13 +535,17 @@ class DeferredEdgeAttributes:
 
     def __init__(self, edge_index, src: NodeTables, dst: NodeTables, dst_flags: torch.Tensor, length=True,
                  length_norm=None, length_invert=False, direction=True, direction_norm=None, direction_rotated=True,
-                 flag_list=None, flag_count=None, regular_k: int = 0):  # fmt: skip
+                 flag_list=None, flag_count=None, regular_k: int = 0, flag_base: int = 0, shard=None):  # fmt: skip
         """``flag_list`` / ``flag_count`` (``compact_flags(dst_flags)``) with ``regular_k`` (the edges of target t are
         columns [t k, (t + 1) k): a KNN result) let ``patch()`` touch the listed targets' edges only."""
         assert edge_index.is_cuda and edge_index.dtype == torch.int32 and edge_index.is_contiguous()
         assert dst_flags.dtype == torch.uint8 and dst_flags.is_cuda
         self.edge_index, self.flags = edge_index, dst_flags
         self.flag_list, self.flag_count, self.regular_k = flag_list, flag_count, int(regular_k)
+        # flags[t - flag_base] belongs to target t; ``shard``: this is one rank's block, the statistics of all blocks
+        # are exchanged before the scaling
+        self.flag_base = int(flag_base)
+        self.shard = shard if (shard is not None and shard.world > 1 and not shard.replicated) else None
         self.n_edges = int(edge_index.shape[1])
         dev = edge_index.device
         self.length, self.direction, self.rotated, self.invert = bool(length), bool(direction), bool(direction_rotated), bool(length_invert)
@@ -522,7 +556,7 @@ class DeferredEdgeAttributes:
         if src is dst:
             src.prepare(as_source=True, as_target=True)
         self.src_rec, self.dst_rec = src.src_rec, dst.dst_rec
-        self.stats = torch.empty((2, 8), dtype=torch.float64, device=dev)
+        self.stats = torch.tensor([[0.0, 0.0, 1e300, -1e300] * 2] * 2, dtype=torch.float64, device=dev)  # "no value"
         self.ws = _attr_workspace(dev)
 
     def _pass(self, which: int, mode: int, tag: str) -> None:
@@ -534,7 +568,7 @@ class DeferredEdgeAttributes:
                 load_library().agx_edge_attrs_stats_flagged(
                     ei[0].data_ptr(), ei[1].data_ptr(), self.n_edges, ptr(self.src_rec), ptr(self.dst_rec),
                     int(self.length), int(self.direction), int(self.rotated), ptr(self.out_len), ptr(self.out_dir),
-                    self.stats[which].data_ptr(), ptr(self.ws), ptr(self.flags), mode, current_stream(),
+                    self.stats[which].data_ptr(), ptr(self.ws), self.flags.data_ptr() - self.flag_base, mode, current_stream(),
                 )
             )
 
@@ -559,6 +593,14 @@ class DeferredEdgeAttributes:
             )
 
     def apply(self) -> None:
+        stats, n_sets, n_global = self.stats, 2, self.n_edges
+        if self.shard is not None:
+            # every rank's two statistics sets, in rank order (a collective: also ranks without edges take part)
+            import torch.distributed as dist
+
+            allst = torch.empty((self.shard.world, 16), dtype=torch.float64, device=self.stats.device)
+            dist.all_gather_into_tensor(allst, self.stats.reshape(1, 16))
+            stats, n_sets, n_global = allst, 2 * self.shard.world, self.shard.total
         if self.n_edges == 0:
             return
         ei = self.edge_index
@@ -567,7 +609,7 @@ class DeferredEdgeAttributes:
                 load_library().agx_edge_attrs_apply(
                     ei[0].data_ptr(), ei[1].data_ptr(), self.n_edges, ptr(self.src_rec), ptr(self.dst_rec), self.len_code,
                     int(self.invert), ptr(self.out_len), self.dir_code, int(self.rotated), ptr(self.out_dir),
-                    ptr(self.stats), 2, self.n_edges, 1, ptr(self.ws), current_stream(),
+                    ptr(stats), n_sets, n_global, 1, ptr(self.ws), current_stream(),
                 )
             )
 

@@ -15,11 +15,15 @@ synthetic (octahedral reduced Gaussian grid, ``anemoi_graphs_b200.grids``) and a
 * ``e2e``: the same step with HOST buffers - coordinates in pinned host memory are uploaded and all
   ``edge_index`` / attribute tensors are copied back to pinned host memory inside the timed region.
 * ``roofline``: the dominant kernel, timed live with CUDA events on its launch stream during the timed steps.
-* ``cpu_baseline`` / ``--impl reference``: the oracle (the reference's own sklearn / scipy / networkx calls,
-  ``oracle/ref_path.py``) timed on this host's cores on a bounded sample of the same workload.
+* ``cpu_baseline``: the oracle port (``oracle/ref_path.py``: the reference's own sklearn / scipy / networkx calls)
+  timed on this host's cores on a bounded sample of the same workload, with its error against a full pass stated.
+* ``--impl reference``: ONE full, unsampled pass of the UNMODIFIED reference (``oracle/_ref``, vendored byte for byte by
+  ``oracle/build_ref.py``) through its own ``GraphCreator.update_graph`` on the box's host cores.
 
-Multi-GPU (torchrun, one rank per GPU): query nodes are sharded by rank, per-rank edge blocks are all-gathered
-over NCCL, every rank ends with the complete graph; total work is fixed => "scaling": "strong".
+Multi-GPU (torchrun, one rank per GPU): sharded OUTPUT mode - query (target) nodes are sharded by rank, reference nodes
+replicated, nothing is exchanged between the GPUs except the attribute statistics (8 doubles per rank).  ``value``
+leaves every rank's block in its own HBM; ``e2e`` has every rank copy its block over its own PCIe link into ONE shared
+page-locked host buffer, so the host ends with the complete graph.  Total work is fixed => "scaling": "strong".
 """
 
 from __future__ import annotations
@@ -161,8 +165,17 @@ def run_step(creator, data_x: torch.Tensor):
     return creator.update_graph(graph)
 
 
-def graph_edges(graph) -> int:
-    return sum(int(graph[k].edge_index.shape[1]) for k in EDGE_KEYS)
+def edge_set_sizes(graph) -> dict:
+    """GLOBAL number of edges of every edge set (a device-resident sharded graph holds one rank's block and says so in
+    ``edge_shard``)."""
+    sizes = {}
+    for k in EDGE_KEYS:
+        info = graph[k].get("edge_shard", None)
+        if info is None:
+            sizes[k] = int(graph[k].edge_index.shape[1])
+        else:
+            sizes[k] = int(info["counts"][0] if info["replicated"] else sum(info["counts"]))
+    return sizes
 
 
 def output_bytes(graph) -> int:
@@ -174,18 +187,31 @@ def output_bytes(graph) -> int:
     return n
 
 
-def sharding_note(world: int, n_queries: int) -> str:
-    from anemoi_graphs_b200 import device as agx_device
-
+def sharding_note(world: int) -> str:
     if world == 1:
         return "single GPU"
-    if n_queries < agx_device.SHARD_MIN_QUERIES:
-        return (
-            f"{world} ranks, every rank builds the full graph: {n_queries} query nodes < AGX_SHARD_MIN_QUERIES = "
-            f"{agx_device.SHARD_MIN_QUERIES} (all-gathering a sharded build costs more than the search it saves; "
-            "DESIGN.md section 5)"
-        )
-    return f"query nodes over {world} rank(s), all-gather of edge blocks"
+    return (
+        f"sharded output over {world} ranks: cut-off and KNN searches and their attributes by query (target) node, "
+        "reference nodes replicated, multi-scale edges and node generation replicated (SURVEY 8e); one rank sorts the "
+        "hidden nodes, the order reaches the others through shared host memory; no edge data crosses NVLink: `value` "
+        "leaves every rank's block in its HBM, `e2e` has every rank copy its block over its own PCIe link into one "
+        "shared page-locked host buffer (the complete graph on the host); attribute statistics are all-gathered (8 "
+        "doubles per rank, NCCL)"
+    )
+
+
+def knn_probe(x_dev: torch.Tensor, res: int, lo: int, hi: int) -> dict:
+    """Counters of the dominant kernel on this rank's queries (one extra launch outside the timed region): staged
+    candidates per tile (`stats[3]`), float64 re-decisions, ties."""
+    from anemoi_graphs_b200 import ops
+
+    ico = ops.Icosphere(res, x_dev.device)
+    stats = ops.new_stats(x_dev.device)
+    with ops.NeighbourIndex(ico.latlon, hint_k=KNN_K) as index:
+        index.knn(x_dev[lo:hi], KNN_K, stats=stats, tag="knn_probe")
+    torch.cuda.synchronize()
+    st = [int(v) for v in stats.cpu().tolist()]
+    return {"refined_f64": st[0], "tied": st[1], "widened": st[2], "staged_candidates": st[3]}
 
 
 def bench_b200(args) -> dict:
@@ -203,6 +229,7 @@ def bench_b200(args) -> dict:
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        agx_device.set_sharded_output(True)
     if world != args.gpus and rank == 0:
         print(f"note: --gpus {args.gpus} but WORLD_SIZE={world}; using {world}", file=sys.stderr)
 
@@ -230,11 +257,15 @@ def bench_b200(args) -> dict:
         torch.cuda.synchronize()
         ms = start.elapsed_time(end)
         if world > 1:
-            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
+            mine = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            every = torch.empty(world, dtype=torch.float64, device="cuda")
+            dist.all_gather_into_tensor(every, mine)
+            by_rank.append([round(float(v) / steps, 4) for v in every.tolist()])
+            ms = float(every.max().item())
         barrier()
         return ms, out
+
+    by_rank: list = []  # per timed region: ms per step of every rank (the reported time is the maximum)
 
     # ---- device-resident: `value` -------------------------------------------------------------------
     agx_device.set_resident(True)
@@ -242,7 +273,8 @@ def bench_b200(args) -> dict:
     for _ in range(args.warmup):
         graph = None
         graph = run_step(creator, x_dev)
-    n_edges = graph_edges(graph)
+    sizes = edge_set_sizes(graph)
+    n_edges = sum(sizes.values())
     graph = None
     clocks = ClockSampler(local_rank)
     if rank == 0:
@@ -257,16 +289,20 @@ def bench_b200(args) -> dict:
     clock_info = clocks.stop() if rank == 0 else {}
     ms_per_step = ms_total / args.steps
     value = n_edges / (ms_per_step * 1e-3)
-    sizes = {k: int(graph[k].edge_index.shape[1]) for k in EDGE_KEYS}
     n_data, n_hidden = int(x_dev.shape[0]), int(graph["hidden"].x.shape[0])
     del graph
+    if world > 1:
+        t = torch.tensor([launches], dtype=torch.int64, device="cuda")
+        dist.all_reduce(t)
+        launches = int(t.item())
 
     # ---- end to end with host buffers: `e2e` ---------------------------------------------------------
     agx_device.set_resident(False)
     for _ in range(args.warmup):
         graph = None
         graph = run_step(creator, x_host)
-    d2h = output_bytes(graph)
+    d2h = output_bytes(graph)  # the complete host graph (at N > 1: each byte written once, by the rank that owns it)
+    assert sum(int(graph[k].edge_index.shape[1]) for k in EDGE_KEYS) == n_edges
     graph = None
     e2e_steps = max(1, args.steps)
     ms_e2e, graph = timed(lambda: run_step(creator, x_host), e2e_steps)
@@ -274,13 +310,12 @@ def bench_b200(args) -> dict:
     del graph
 
     # ---- roofline of the dominant kernel ---------------------------------------------------------------
-    # spans: one per C-ABI call, timed with CUDA events on the launch stream during the timed steps.  "knn" is the
-    # decoder's k_knn<4> launch alone (the reference-distance self query has its own span); an "edge_attrs" span is
-    # the raw-value kernel + the in-place scaling kernel of ONE edge set, so its per-launch figure is taken for
-    # the largest edge set (KNN edges) separately below.
+    # spans: one per C-ABI call, timed with CUDA events on the launch stream during the timed steps (rank 0's).  "knn"
+    # is the decoder's k_knn<4> launch alone: THIS RANK's queries (all of them on one GPU, 1/W in sharded mode).
     per_step = {k: spans[k] / args.steps for k in spans}
     per_call = {k: spans[k] / span_counts[k] for k in spans}
-    nq_knn, e_knn = n_data // world, sizes[EDGE_KEYS[2]] // world
+    lo, hi = agx_device.shard_range(n_data, rank, world)
+    nq_knn, e_knn = hi - lo, (hi - lo) * KNN_K
     kern = "knn"
     algo_bytes = ALGO_BYTES["knn"](nq_knn, n_hidden, e_knn)
     achieved = algo_bytes / (per_call[kern] * 1e-3) / 1e9
@@ -292,11 +327,18 @@ def bench_b200(args) -> dict:
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
     traffic = None
     tpath = REPO / "profiles" / "traffic.json"
-    if tpath.exists():
+    if tpath.exists() and world == 1:
         traffic = json.loads(tpath.read_text()).get("k_knn")
-    staged_pairs = None
+    # FP32 FMA-pipe view of the same launch: every staged candidate is tested against all 32 queries of its tile;
+    # 8 flop per (query, candidate) pair (3 sub, 1 mul, 2 fma).  Peak = SMs x 128 lanes x 2 x clock.
+    probe = knn_probe(x_dev, res, lo, hi)
+    props = torch.cuda.get_device_properties(local_rank)
+    sm_mhz = float(clock_info.get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)) if rank == 0 else 1965.0
+    fp32_peak = props.multi_processor_count * 128 * 2 * sm_mhz * 1e6 / 1e12
+    pairs = probe["staged_candidates"] * 32
+    fp32_achieved = pairs * 8 / (per_call[kern] * 1e-3) / 1e12
     roofline = {
-        "kernel": "k_knn<4> (KNNEdges decoder, one launch per step)",
+        "kernel": "k_knn<4> (KNNEdges decoder, one launch per step" + (f", this rank's 1/{world} of the queries)" if world > 1 else ")"),
         "bound": "hbm",
         "achieved": round(achieved, 2),
         "peak": peak,
@@ -306,11 +348,20 @@ def bench_b200(args) -> dict:
         "traffic": traffic,
         "algorithmic_bytes_per_launch": algo_bytes,
         "ms_per_launch": round(per_call[kern], 4),
-        "note": "issue/FP32-bound, not HBM-bound: see profiles/ (smsp issue active, pairs per query)",
+        "fp32": {
+            "pairs_evaluated": pairs,
+            "pairs_per_query": round(pairs / max(nq_knn, 1), 2),
+            "flop_per_pair": 8,
+            "achieved_tflops": round(fp32_achieved, 3),
+            "peak_tflops": round(fp32_peak, 2),
+            "peak_source": f"{props.multi_processor_count} SMs x 128 FP32 lanes x 2 x {sm_mhz:.0f} MHz (clock sampled under load)",
+            "frac": round(fp32_achieved / fp32_peak, 5),
+            "counters": probe,
+        },
+        "note": "issue-bound (d = 3 distance tests against every staged candidate), neither HBM- nor FMA-bound: see profiles/",
         "stage_ms_per_step": {k: round(v, 4) for k, v in sorted(per_step.items(), key=lambda kv: -kv[1])},
         "stage_launch_groups_per_step": {k: span_counts[k] // args.steps for k in span_counts},
     }
-    _ = staged_pairs
 
     line = {
         "metric": METRIC,
@@ -326,16 +377,17 @@ def bench_b200(args) -> dict:
         "dtype": "f32 filter + f64 decisions, int32 indices",
         "data": "synthetic",
         "config": workload_config(args.workload, n_data, n_hidden, sizes),
-        "sharding": sharding_note(world, n_data),
+        "sharding": sharding_note(world),
         "e2e": {
             "value": round(e2e_value, 1),
             "unit": "edges/s",
             "ms_per_step": round(ms_e2e / e2e_steps, 4),
             "steps": e2e_steps,
-            "h2d_bytes_per_step": int(x_host.numel() * 4),
+            "h2d_bytes_per_step": int(x_host.numel() * 4) * world,  # every rank uploads the (replicated) data coordinates
             "d2h_bytes_per_step": int(d2h),
         },
         "gpu_launches": int(launches),
+        "ms_per_step_by_rank": {"value": by_rank[0], "e2e": by_rank[1]} if by_rank else None,
         "roofline": roofline,
         "clocks": clock_info,
     }  # fmt: skip
