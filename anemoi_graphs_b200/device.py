@@ -367,9 +367,37 @@ def node_state(nodes, provisional_ok: bool = False) -> NodeState:
     if isinstance(st, NodeState) and st.key == _key(x):
         return st
     wait_copies()  # x may be a pinned tensor one of our own copies is still filling
-    st = NodeState(key=_key(x), x=to_device(x, torch.float32))
+    st = NodeState(key=_key(x), x=upload_replicated(x))
     nodes[STATE_ATTR] = st
     return st
+
+
+# host node sets from this many bytes are uploaded once per NODE in a sharded multi-GPU build (each rank 1/W over its
+# own PCIe link, the rest over NVLink) instead of once per GPU
+SLICED_UPLOAD_MIN_BYTES = int(float(__import__("os").environ.get("AGX_SLICED_UPLOAD_MIN_BYTES", "4e6")))
+
+
+def upload_replicated(x: torch.Tensor) -> torch.Tensor:
+    """Device float32 copy of host node coordinates that every rank holds identically (every rank runs the same recipe
+    on the same inputs).  Sharded output mode on one node: every rank uploads only ITS 1/W of the rows and the ranks
+    all-gather the rest over NVLink - W uploads of the whole array (424 MB for O1280 on 8 GPUs) would queue on the
+    host's DMA ceiling before any search can start."""
+    if x.is_cuda or not sharded_output() or x.numel() * x.element_size() < SLICED_UPLOAD_MIN_BYTES:
+        return to_device(x, torch.float32)
+    import torch.distributed as dist
+
+    if dist.get_backend() != "nccl":
+        return to_device(x, torch.float32)
+    rank, w = world()
+    dev = compute_device()
+    n = int(x.shape[0])
+    per = (n + w - 1) // w  # equal blocks (the last one padded): NCCL's in-place all-gather
+    full = torch.empty((per * w,) + tuple(x.shape[1:]), dtype=torch.float32, device=dev)
+    lo, hi = min(rank * per, n), min((rank + 1) * per, n)
+    if hi > lo:
+        full[lo:hi].copy_(x[lo:hi], non_blocking=True)  # dtype conversion (if any) on the device side of the copy
+    dist.all_gather_into_tensor(full, full[rank * per : (rank + 1) * per])
+    return full[:n]
 
 
 # node sets up to this size keep their neighbour index on the node state (``NodeState.extras``), so the builders of
@@ -551,9 +579,24 @@ class Provisional:
             if follower:
                 from . import shm
 
-                for i in range(max_parts):  # the sorting rank's arrays, as they appear: one wake-up byte per array
-                    group.sleep_until_woken()
+                # the sorting rank's arrays, as they appear.  The first wait is long and of unknown length: asleep in
+                # read(2) until the wake-up byte.  Every later array takes about as long as the first did (the same sort
+                # on the same number of keys), so the follower sleeps 80 % of that and then polls the stamp - it picks
+                # the array up within microseconds instead of a scheduler wake-up (~0.1 ms on the critical path).
+                t_start = time.perf_counter()
+                t_first = None
+                for i in range(max_parts):
+                    if i == 0 or t_first is None:
+                        group.sleep_until_woken()
+                    else:
+                        time.sleep(max(0.0, 0.8 * t_first - (time.perf_counter() - t_prev)))
+                        while int(stamps[i]) != prov_seq + 1:
+                            time.sleep(0)
+                        group.drain_wakeups()
                     shm._spin(lambda i=i: int(stamps[i]) == prov_seq + 1, f"part {i} of node order {prov_seq}")
+                    t_prev = time.perf_counter()
+                    if i == 0:
+                        t_first = t_prev - t_start
                     emit(None)
                 out = (None, None)
             else:

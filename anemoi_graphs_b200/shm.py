@@ -103,6 +103,11 @@ class LocalGroup:
         """Follower: block (asleep in the kernel, GIL released) until rank 0's next wake-up byte."""
         os.read(self._sleep_fd, 1)
 
+    def drain_wakeups(self) -> None:
+        """Follower that found what it waited for by polling: swallow the wake-up byte that belongs to it (it may still
+        be on its way: the stamp is written before the byte)."""
+        os.read(self._sleep_fd, 1)
+
     # ---- all-gather of up to PAYLOAD int64 per rank ------------------------------------------------------------
     def all_gather(self, values) -> list[list[int]]:
         """Every rank's ``values`` (same length on all ranks), in rank order.  A rendezvous: returns when all ranks
