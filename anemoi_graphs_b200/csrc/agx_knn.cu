@@ -325,7 +325,7 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn(KnnArgs a) {
                 mbar_wait(bar, phase);
                 phase ^= 1;
             }
-            if (a.stats && lane == 0) atomicAdd(a.stats + 3, (unsigned long long)m_total);  // staged candidates
+            if (a.stats && lane == 0) atomicAdd(a.stats + 3, (unsigned long long)m_total * 32ull);  // (query, candidate) pairs
         }
         // ---- scan ------------------------------------------------------------------------------------
         TopF<CAP> top;

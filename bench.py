@@ -201,8 +201,8 @@ def sharding_note(world: int) -> str:
 
 
 def knn_probe(x_dev: torch.Tensor, res: int, lo: int, hi: int) -> dict:
-    """Counters of the dominant kernel on this rank's queries (one extra launch outside the timed region): staged
-    candidates per tile (`stats[3]`), float64 re-decisions, ties."""
+    """Counters of the dominant kernel on this rank's queries (one extra launch outside the timed region): (query, candidate)
+    pairs of the staged scans (`stats[3]`), float64 re-decisions, ties."""
     from anemoi_graphs_b200 import ops
 
     ico = ops.Icosphere(res, x_dev.device)
@@ -211,7 +211,7 @@ def knn_probe(x_dev: torch.Tensor, res: int, lo: int, hi: int) -> dict:
         index.knn(x_dev[lo:hi], KNN_K, stats=stats, tag="knn_probe")
     torch.cuda.synchronize()
     st = [int(v) for v in stats.cpu().tolist()]
-    return {"refined_f64": st[0], "tied": st[1], "widened": st[2], "staged_candidates": st[3]}
+    return {"refined_f64": st[0], "tied": st[1], "widened": st[2], "pairs": st[3]}
 
 
 def bench_b200(args) -> dict:
@@ -329,13 +329,13 @@ def bench_b200(args) -> dict:
     tpath = REPO / "profiles" / "traffic.json"
     if tpath.exists() and world == 1:
         traffic = json.loads(tpath.read_text()).get("k_knn")
-    # FP32 FMA-pipe view of the same launch: every staged candidate is tested against all 32 queries of its tile;
+    # FP32 FMA-pipe view of the same launch: every staged candidate is tested against all queries of its (half-)tile;
     # 8 flop per (query, candidate) pair (3 sub, 1 mul, 2 fma).  Peak = SMs x 128 lanes x 2 x clock.
     probe = knn_probe(x_dev, res, lo, hi)
     props = torch.cuda.get_device_properties(local_rank)
     sm_mhz = float(clock_info.get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)) if rank == 0 else 1965.0
     fp32_peak = props.multi_processor_count * 128 * 2 * sm_mhz * 1e6 / 1e12
-    pairs = probe["staged_candidates"] * 32
+    pairs = probe["pairs"]
     fp32_achieved = pairs * 8 / (per_call[kern] * 1e-3) / 1e12
     roofline = {
         "kernel": "k_knn<4> (KNNEdges decoder, one launch per step" + (f", this rank's 1/{world} of the queries)" if world > 1 else ")"),

@@ -72,7 +72,7 @@ int agx_search_vectors(const float* latlon /*DEV n*2*/, int64_t n, float* xyz /*
  * (sklearn _dist_metrics.pyx.tp:2639-2648); ties within 2^-40 relative go to the lower index.
  * out_rdist (optional, nq*k) receives the float64 rdist of every neighbour.
  * stats (optional, DEV int64[4]) += {queries refined in float64, queries with a tie at the k-th
- * boundary, queries needing a wider search, candidate records staged in shared memory (x32 = FP32 pairs)}.
+ * boundary, queries needing a wider search, (query, candidate) pairs evaluated by the staged scans on the FP32 pipe}.
  * max_radius (radians; 0 = unlimited) bounds the search, for callers that only ask "is anything within r?"
  * (KNNAreaMaskBuilder.get_mask compares the distance with a margin, generate/masks.py:94-99 - without the bound a
  * query far from a clustered reference set walks the whole sphere): a query whose k-th neighbour lies within

@@ -26,4 +26,4 @@ for cells in (0, 96, 160, 200):
         ix.knn(x, 3, out=out, stats=stats)
         st = stats.cpu().tolist()
         tiles = (x.shape[0] + 31) // 32
-        print(f"cells={ix.cells_per_face} cap_scale={scale}: {a.elapsed_time(b)/5*1e3:.1f} us  f64={st[0]} tie={st[1]} widened={st[2]} staged/tile={st[3]/tiles:.1f}", flush=True)
+        print(f"cells={ix.cells_per_face} cap_scale={scale}: {a.elapsed_time(b)/5*1e3:.1f} us  f64={st[0]} tie={st[1]} widened={st[2]} staged/tile={st[3]/32/tiles:.1f}", flush=True)

@@ -61,7 +61,7 @@ def main():
                     st = st.cpu().tolist()
                 row = dict(op="knn", order=tag, n_ref=args.refs, n_query=nq, k=k, ms=round(ms, 3), index_build_ms=round(t_build, 3),
                            edges_per_s=round(nq * k / ms * 1e3), queries_per_s=round(nq / ms * 1e3),
-                           f64_refined=st[0], tied=st[1], widened=st[2], staged_per_tile=round(st[3] / ((nq + 31) // 32), 1))  # fmt: skip
+                           f64_refined=st[0], tied=st[1], widened=st[2], staged_per_tile=round(st[3] / 32 / ((nq + 31) // 32), 1))  # fmt: skip
                 rows.append(row)
                 print(json.dumps(row), flush=True)
             for deg in [int(v) for v in args.degrees.split(",")]:
