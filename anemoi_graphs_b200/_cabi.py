@@ -14,7 +14,7 @@ import torch
 
 LIB_PATH = Path(__file__).resolve().parent / "lib" / "libagx_b200.so"
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 AGX_OK = 0
 AGX_ERR_CUDA = -1
 AGX_ERR_ARG = -2
@@ -64,29 +64,29 @@ SIGNATURES = {
     "agx_node_tables": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "agx_edge_attrs": (
         c_int,
-        [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p,
-         c_void_p],
+        [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int,
+         c_void_p, c_void_p, c_int, c_void_p],
     ),  # fmt: skip
     "agx_edge_attrs_workspace": (c_int64, []),
     "agx_edge_attrs_stats": (
         c_int,
-        [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
-         c_void_p],
+        [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,
+         c_void_p, c_void_p, c_void_p],
     ),  # fmt: skip
     "agx_edge_attrs_stats_flagged": (
         c_int,
-        [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
-         c_void_p, c_int, c_void_p],
+        [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,
+         c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p],
     ),  # fmt: skip
     "agx_edge_attrs_stats_list": (
         c_int,
-        [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
-         c_void_p, c_void_p, c_void_p, c_void_p],
+        [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+         c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     ),  # fmt: skip
     "agx_edge_attrs_apply": (
         c_int,
-        [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p,
-         c_int, c_int64, c_int, c_void_p, c_void_p],
+        [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int,
+         c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p],
     ),  # fmt: skip
     "agx_icosphere": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "agx_multiscale_tri_count": (

@@ -166,7 +166,8 @@ def compute_attributes(graph, edges_name: tuple[str, str, str], attrs: dict) -> 
         kl = lengths.pop(0) if lengths else None
         kd = dirs.pop(0) if dirs else None
         shard = meta.shard if (meta is not None and _device.sharded_output()) else None
-        args = dict(length=False, direction=False, sharded=w > 1, local=local, shard=shard)
+        args = dict(length=False, direction=False, sharded=w > 1, local=local, shard=shard,
+                    regular_k=meta.regular_k if meta is not None else 0)
         if kl:
             args.update(kl[1]._kernel_args())
         if kd:

@@ -306,7 +306,8 @@ class KNNEdges(BaseEdgeBuilder, NodeMaskingMixin):
             with _device.neighbour_index(self._src_state if src_sel is None else None, src, hint_k=k) as index:
                 out = index.knn(dst[lo:hi], k, dst_base=lo, stats=self.stats)
             out = _device.tag_rows(self.undo_masking(out, src_sel, dst_sel), *self._row_provs)
-            _device.edge_meta(out, create=True).shard = shard
+            meta = _device.edge_meta(out, create=True)
+            meta.shard, meta.regular_k = shard, k
             return out
         with _device.neighbour_index(self._src_state if src_sel is None else None, src, hint_k=k) as index:
             out = torch.empty((2, nq * k), dtype=torch.int32, device=dst.device)
@@ -340,7 +341,11 @@ class KNNEdges(BaseEdgeBuilder, NodeMaskingMixin):
         if w > 1:
             counts = [(b - a) * k for a, b in (_device.shard_range(nq, r, w) for r in range(w))]
             out = _gather_blocks(out, counts, rank, src_sel is not None or dst_sel is not None)
-        return _device.tag_rows(self.undo_masking(out, src_sel, dst_sel), *self._row_provs)
+        local = _device.edge_meta(out).local if _device.edge_meta(out) is not None else None
+        out = _device.tag_rows(self.undo_masking(out, src_sel, dst_sel), *self._row_provs)
+        meta = _device.edge_meta(out, create=True)
+        meta.regular_k, meta.local = k, local  # k edges per target, target after target: attributes walk it by target
+        return out
 
 
 class CutOffEdges(BaseEdgeBuilder, NodeMaskingMixin):

@@ -294,18 +294,28 @@ def grid_reference_distance(x: torch.Tensor, state=None) -> float:
     return 2.0 * math.asin(math.sqrt(value.value))
 
 
+# node sets with more nodes than this are NOT tabulated for the attribute kernel: it evaluates their per-node quantities
+# per edge from the 8-byte coordinates (a table costs 32 B written + 32 B gathered per node and role; the hidden mesh
+# of a recipe stays tabulated - 5 MB, L2-resident).  AGX_ATTR_COORD_MIN_NODES overrides (0: never tabulate).
+ATTR_COORD_MIN_NODES = int(float(__import__("os").environ.get("AGX_ATTR_COORD_MIN_NODES", "1e6")))
+
+
 class NodeTables:
-    """Per-node records of the attribute kernel, one 32-byte record per role, built on first use:
+    """Per-node inputs of the attribute kernel.  Small node sets: one 32-byte record per role, built on first use:
 
     * ``src_rec`` float32 (n, 8): (x, y, z, cos lat, lat, lon, 0, 0) - the node as an edge SOURCE;
     * ``dst_rec`` float64 (n, 4): (quat x, quat y, quat w, bits(lat, lon)) - the node as an edge TARGET
       (rotation to the north pole, edges/directional.py:19-37).
 
+    Large node sets (``n > ATTR_COORD_MIN_NODES``): no table - ``source_inputs()`` / ``target_inputs()`` hand the
+    kernel the coordinates and it evaluates the same quantities per edge (bit-identical results).
+
     ``with_rotation`` is accepted for compatibility; the target record always carries the quaternion."""
 
-    def __init__(self, x: torch.Tensor, with_rotation: bool = True) -> None:
+    def __init__(self, x: torch.Tensor, with_rotation: bool = True, tabulate: bool | None = None) -> None:
         self.x = _dev_x(x)
         self.n = int(self.x.shape[0])
+        self.tabulate = (self.n <= ATTR_COORD_MIN_NODES) if tabulate is None else bool(tabulate)
         self._src = None
         self._dst = None
 
@@ -332,6 +342,13 @@ class NodeTables:
                 self._dst = torch.empty((0, 4), dtype=torch.float64, device=self.x.device)
         return self
 
+    def source_inputs(self) -> tuple:
+        """``(record pointer or None, coordinate pointer or None)`` for the kernel's source side."""
+        return (ptr(self.src_rec), None) if self.tabulate else (None, ptr(self.x))
+
+    def target_inputs(self) -> tuple:
+        return (ptr(self.dst_rec), None) if self.tabulate else (None, ptr(self.x))
+
     @property
     def src_rec(self) -> torch.Tensor:
         return self.prepare(as_source=True)._src
@@ -348,6 +365,13 @@ class NodeTables:
     @property
     def quat(self) -> torch.Tensor:
         return self.dst_rec
+
+
+def _node_inputs(src: NodeTables, dst: NodeTables) -> tuple:
+    """The four node pointers of an attribute call: (src_rec, src_latlon, dst_rec, dst_latlon)."""
+    if src is dst and src.tabulate:
+        src.prepare(as_source=True, as_target=True)
+    return (*src.source_inputs(), *dst.target_inputs())
 
 
 _workspace: dict = {}
@@ -381,6 +405,7 @@ def edge_attributes(
     sharded: bool = False,
     local: tuple[int, int, list[int]] | None = None,
     shard=None,
+    regular_k: int = 0,
 ):
     """Fused EdgeLength / EdgeDirection: returns ``(len (E, 1) float32 | None, dir (E, 2) float32 | None)``.
 
@@ -390,7 +415,8 @@ def edge_attributes(
     ``device.flush`` has run).  ``local = (lo, hi, counts)`` names the range this rank's own builder produced
     (its columns of ``edge_index`` are valid before the edge all-gather has finished) and every rank's block
     size; without it the edges are split evenly.  ``shard`` (``device.Shard``, sharded output mode): ``edge_index`` is
-    this rank's own block and so are the results - only the statistics are exchanged."""
+    this rank's own block and so are the results - only the statistics are exchanged.  ``regular_k`` > 0: the edges of the
+    i-th target are the columns [i k, (i + 1) k) (a KNN result) - evaluated by target instead of by edge."""
     from . import device as _device
 
     for norm in (length_norm, direction_norm):
@@ -405,9 +431,7 @@ def edge_attributes(
     out_len = torch.empty((n_edges, 1), dtype=torch.float32, device=dev) if length else None
     out_dir = torch.empty((n_edges, 2), dtype=torch.float32, device=dev) if direction else None
     lib = load_library()
-    if src is dst:
-        src.prepare(as_source=True, as_target=True)
-    src_rec, dst_rec = src.src_rec, dst.dst_rec
+    nodes = _node_inputs(src, dst)
     len_code = NORM_CODES[length_norm] if length else -1
     dir_code = NORM_CODES[direction_norm] if direction else -1
     rank, w = _device.world() if sharded else (0, 1)
@@ -423,7 +447,7 @@ def edge_attributes(
             with _span("edge_attrs_stats", n_edges):
                 check(
                     lib.agx_edge_attrs_stats(
-                        e_src, e_dst, n_edges, ptr(src_rec), ptr(dst_rec), int(length), int(direction),
+                        e_src, e_dst, n_edges, *nodes, int(length), int(direction),
                         int(bool(direction_rotated)), ptr(out_len), ptr(out_dir), ptr(stats), ptr(ws), stream,
                     )
                 )
@@ -431,7 +455,7 @@ def edge_attributes(
         with _span("edge_attrs_apply", n_edges):
             check(
                 lib.agx_edge_attrs_apply(
-                    e_src, e_dst, n_edges, ptr(src_rec), ptr(dst_rec), len_code, int(bool(length_invert)), ptr(out_len),
+                    e_src, e_dst, n_edges, *nodes, len_code, int(bool(length_invert)), ptr(out_len),
                     dir_code, int(bool(direction_rotated)), ptr(out_dir), ptr(stats), shard.world if stats is not None else 0,
                     shard.total, 1 if stats is not None else 0, ptr(ws), stream,
                 )
@@ -448,9 +472,9 @@ def edge_attributes(
         with _span("edge_attrs", n_edges):
             check(
                 lib.agx_edge_attrs(
-                    edge_index[0].data_ptr(), edge_index[1].data_ptr(), n_edges, ptr(src_rec), ptr(dst_rec), len_code,
+                    edge_index[0].data_ptr(), edge_index[1].data_ptr(), n_edges, *nodes, len_code,
                     int(bool(length_invert)), ptr(out_len), dir_code, int(bool(direction_rotated)), ptr(out_dir),
-                    ptr(ws), stream,
+                    ptr(ws), int(regular_k), stream,
                 )
             )  # fmt: skip
         return out_len, out_dir
@@ -473,7 +497,7 @@ def edge_attributes(
         with _span("edge_attrs_stats", m):
             check(
                 lib.agx_edge_attrs_stats(
-                    e_src, e_dst, m, ptr(src_rec), ptr(dst_rec), int(length), int(direction),
+                    e_src, e_dst, m, *nodes, int(length), int(direction),
                     int(bool(direction_rotated)), o_len, o_dir, ptr(stats), ptr(ws), stream,
                 )
             )  # fmt: skip
@@ -482,7 +506,7 @@ def edge_attributes(
     with _span("edge_attrs_apply", m):
         check(
             lib.agx_edge_attrs_apply(
-                e_src, e_dst, m, ptr(src_rec), ptr(dst_rec), len_code, int(bool(length_invert)), o_len, dir_code,
+                e_src, e_dst, m, *nodes, len_code, int(bool(length_invert)), o_len, dir_code,
                 int(bool(direction_rotated)), o_dir, ptr(stats), w if stats is not None else 0, n_edges, raw_present,
                 ptr(ws), stream,
             )
@@ -553,9 +577,8 @@ class DeferredEdgeAttributes:
         self.dir_code = NORM_CODES[direction_norm] if direction else -1
         self.out_len = torch.empty((self.n_edges, 1), dtype=torch.float32, device=dev) if length else None
         self.out_dir = torch.empty((self.n_edges, 2), dtype=torch.float32, device=dev) if direction else None
-        if src is dst:
-            src.prepare(as_source=True, as_target=True)
-        self.src_rec, self.dst_rec = src.src_rec, dst.dst_rec
+        self.nodes = _node_inputs(src, dst)
+        self._keep = (src, dst)  # the tables / coordinates the pointers refer to
         self.stats = torch.tensor([[0.0, 0.0, 1e300, -1e300] * 2] * 2, dtype=torch.float64, device=dev)  # "no value"
         self.ws = _attr_workspace(dev)
 
@@ -566,9 +589,10 @@ class DeferredEdgeAttributes:
         with _span(tag, self.n_edges if mode == ATTR_FLAGS_SKIP else 0):
             check(
                 load_library().agx_edge_attrs_stats_flagged(
-                    ei[0].data_ptr(), ei[1].data_ptr(), self.n_edges, ptr(self.src_rec), ptr(self.dst_rec),
+                    ei[0].data_ptr(), ei[1].data_ptr(), self.n_edges, *self.nodes,
                     int(self.length), int(self.direction), int(self.rotated), ptr(self.out_len), ptr(self.out_dir),
-                    self.stats[which].data_ptr(), ptr(self.ws), self.flags.data_ptr() - self.flag_base, mode, current_stream(),
+                    self.stats[which].data_ptr(), ptr(self.ws), self.flags.data_ptr() - self.flag_base, mode,
+                    self.regular_k if mode == ATTR_FLAGS_SKIP else 0, current_stream(),
                 )
             )
 
@@ -586,7 +610,7 @@ class DeferredEdgeAttributes:
             check(
                 load_library().agx_edge_attrs_stats_list(
                     ei[0].data_ptr(), ei[1].data_ptr(), self.n_edges, self.regular_k, ptr(self.flag_list),
-                    ptr(self.flag_count), ptr(self.src_rec), ptr(self.dst_rec), int(self.length), int(self.direction),
+                    ptr(self.flag_count), *self.nodes, int(self.length), int(self.direction),
                     int(self.rotated), ptr(self.out_len), ptr(self.out_dir), self.stats[1].data_ptr(), ptr(self.ws),
                     current_stream(),
                 )
@@ -607,7 +631,7 @@ class DeferredEdgeAttributes:
         with _span("edge_attrs_scale", self.n_edges):
             check(
                 load_library().agx_edge_attrs_apply(
-                    ei[0].data_ptr(), ei[1].data_ptr(), self.n_edges, ptr(self.src_rec), ptr(self.dst_rec), self.len_code,
+                    ei[0].data_ptr(), ei[1].data_ptr(), self.n_edges, *self.nodes, self.len_code,
                     int(self.invert), ptr(self.out_len), self.dir_code, int(self.rotated), ptr(self.out_dir),
                     ptr(stats), n_sets, n_global, 1, ptr(self.ws), current_stream(),
                 )

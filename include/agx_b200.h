@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define AGX_ABI_VERSION 1
+#define AGX_ABI_VERSION 2
 
 #define AGX_OK 0
 #define AGX_ERR_CUDA -1      /* CUDA runtime / launch failure (includes "no device") */
@@ -185,11 +185,19 @@ int agx_order_resolve(const int64_t* index_latitude /*DEV n*/, const int64_t* in
  * dir_rotated = luse_rotated_features.                                                          */
 int agx_node_tables(const float* latlon /*DEV n*2*/, int64_t n, float* src_rec /*DEV n*8 or NULL*/,
                     double* dst_rec /*DEV n*4 or NULL, 32-byte aligned*/, void* stream);
+/* Node inputs of the attribute calls, per side EITHER a record table from agx_node_tables (src_rec / dst_rec; small node
+ * sets whose tables stay in L2) OR the node set's float32 (lat, lon) coordinates (src_latlon / dst_latlon; large node
+ * sets: the kernel evaluates xyz / the rotation quaternion per edge from 8 bytes instead of gathering a 32-byte record
+ * that had to be written first) - exactly one of the two pointers of a side is non-NULL.  Both forms give bit-identical
+ * attributes.                                                                                                       */
 int agx_edge_attrs(const int32_t* edge_src /*DEV E*/, const int32_t* edge_dst /*DEV E*/, int64_t n_edges,
-                   const float* src_rec /*source node records*/, const double* dst_rec /*target node records*/,
+                   const float* src_rec /*DEV or NULL*/, const float* src_latlon /*DEV ns*2 or NULL*/,
+                   const double* dst_rec /*DEV or NULL*/, const float* dst_latlon /*DEV nt*2 or NULL*/,
                    int len_norm /*AGX_NORM_* or -1 = skip*/, int len_invert, float* out_len /*DEV E*/,
                    int dir_norm /*AGX_NORM_* or -1 = skip*/, int dir_rotated, float* out_dir /*DEV E*2*/,
-                   double* workspace /*DEV, >= agx_edge_attrs_workspace() doubles*/, void* stream);
+                   double* workspace /*DEV, >= agx_edge_attrs_workspace() doubles*/,
+                   int regular_k /*k > 0: the edges of the i-th target are columns [i k, (i+1) k) - a KNN result; 0: any list*/,
+                   void* stream);
 int64_t agx_edge_attrs_workspace(void);
 /* The two halves of agx_edge_attrs, for callers that hold only a SHARD of the edge set (one rank of a
  * multi-GPU build).  _stats evaluates the raw values of the local edges ONCE: it writes them (float32, not yet
@@ -200,9 +208,9 @@ int64_t agx_edge_attrs_workspace(void);
  * with the global edge count, to _apply, which normalises the local block in place (raw_present = 1) or
  * evaluates the raw values first (raw_present = 0).  normalise.py:20-55.                                  */
 int agx_edge_attrs_stats(const int32_t* edge_src, const int32_t* edge_dst, int64_t n_edges, const float* src_rec,
-                         const double* dst_rec, int want_len, int want_dir, int dir_rotated,
-                         float* out_len /*DEV E or NULL*/, float* out_dir /*DEV E*2 or NULL*/,
-                         double* stats /*DEV 8*/, double* workspace, void* stream);
+                         const float* src_latlon, const double* dst_rec, const float* dst_latlon, int want_len,
+                         int want_dir, int dir_rotated, float* out_len /*DEV E or NULL*/,
+                         float* out_dir /*DEV E*2 or NULL*/, double* stats /*DEV 8*/, double* workspace, void* stream);
 /* agx_edge_attrs_stats with a per-TARGET flag byte (dst_flags: DEV uint8[n_target_nodes]).  flag_mode 1 ("skip"): every
  * edge is evaluated and written, edges INTO a flagged target stay out of the statistics; flag_mode 2 ("only"): only
  * the edges into flagged targets are evaluated, written and counted.  For KNN edges built while the source numbering
@@ -210,20 +218,23 @@ int agx_edge_attrs_stats(const int32_t* edge_src, const int32_t* edge_dst, int64
  * statistics sets go to agx_edge_attrs_apply (n_stat_sets = 2) - the decoder's trigonometry then runs in the shadow
  * of the host sort and only the scaling pass follows it.                                                          */
 int agx_edge_attrs_stats_flagged(const int32_t* edge_src, const int32_t* edge_dst, int64_t n_edges,
-                                 const float* src_rec, const double* dst_rec, int want_len, int want_dir, int dir_rotated,
-                                 float* out_len, float* out_dir, double* stats /*DEV 8*/, double* workspace,
-                                 const uint8_t* dst_flags /*DEV*/, int flag_mode, void* stream);
+                                 const float* src_rec, const float* src_latlon, const double* dst_rec,
+                                 const float* dst_latlon, int want_len, int want_dir, int dir_rotated, float* out_len,
+                                 float* out_dir, double* stats /*DEV 8*/, double* workspace,
+                                 const uint8_t* dst_flags /*DEV*/, int flag_mode, int regular_k, void* stream);
 /* The "only" pass driven by an explicit LIST of targets of a regular-k edge list (edges of target t = [t k, (t+1) k),
  * a KNN result; list = ascending target ids, *count = its length, both in device memory - agx_compact_flags): the few
  * re-decided queries cost one small launch instead of a pass over every target index.                            */
 int agx_edge_attrs_stats_list(const int32_t* edge_src, const int32_t* edge_dst, int64_t n_edges, int regular_k,
                               const int32_t* list /*DEV*/, const int64_t* count /*DEV*/, const float* src_rec,
-                              const double* dst_rec, int want_len, int want_dir, int dir_rotated, float* out_len,
-                              float* out_dir, double* stats /*DEV 8*/, double* workspace, void* stream);
+                              const float* src_latlon, const double* dst_rec, const float* dst_latlon, int want_len,
+                              int want_dir, int dir_rotated, float* out_len, float* out_dir, double* stats /*DEV 8*/,
+                              double* workspace, void* stream);
 int agx_edge_attrs_apply(const int32_t* edge_src, const int32_t* edge_dst, int64_t n_edges, const float* src_rec,
-                         const double* dst_rec, int len_norm, int len_invert, float* out_len, int dir_norm,
-                         int dir_rotated, float* out_dir, const double* stats /*DEV n_stat_sets*8 or NULL if no norm*/,
-                         int n_stat_sets, int64_t n_edges_global, int raw_present, double* workspace, void* stream);
+                         const float* src_latlon, const double* dst_rec, const float* dst_latlon, int len_norm,
+                         int len_invert, float* out_len, int dir_norm, int dir_rotated, float* out_dir,
+                         const double* stats /*DEV n_stat_sets*8 or NULL if no norm*/, int n_stat_sets,
+                         int64_t n_edges_global, int raw_present, double* workspace, void* stream);
 
 /* ---- icosphere + multi-scale edges -------------------------------------------------------------------
  * agx_icosphere: replaces trimesh.creation.icosphere (generate/tri_icosahedron.py:121,173):

@@ -61,6 +61,16 @@ def test_node_records_layout(ops):
     np.testing.assert_array_equal(packed, x.view(np.int32))
     q = dst[:, :3]
     np.testing.assert_allclose((q**2).sum(axis=1), 1.0, rtol=0, atol=1e-12)  # unit quaternion with z = 0
+    # the quaternion is evaluated without trigonometry (half-angle square roots): it is scipy's
+    # Rotation.from_rotvec(direction_vec(p, z) * arccos(p_z)) (edges/directional.py:19-37) to 1e-15
+    from scipy.spatial.transform import Rotation
+
+    xyz = R.latlon_rad_to_cartesian((x[:, 0], x[:, 1]), 1.0).astype(np.float64)
+    v = R.direction_vec(xyz.copy(), np.array([0, 0, 1]))
+    theta = np.arccos(xyz[:, 2])
+    want = Rotation.from_rotvec(np.transpose(v * theta)).as_quat()  # (x, y, z, w)
+    sign = np.where(want[:, 3] < 0, -1.0, 1.0)[:, None]
+    np.testing.assert_allclose(q, (want * sign)[:, [0, 1, 3]], rtol=0, atol=2e-15)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -538,10 +548,40 @@ def test_attribute_flag_modes_split_the_statistics(ops, golden):
         raw_len, raw_dir = torch.empty_like(want_len), torch.empty_like(want_dir)
         check = __import__("anemoi_graphs_b200._cabi", fromlist=["check"]).check
         check(ops.load_library().agx_edge_attrs_stats(ei[0].data_ptr(), ei[1].data_ptr(), int(ei.shape[1]), src.src_rec.data_ptr(),
-              dst.dst_rec.data_ptr(), 1, 1, 1, raw_len.data_ptr(), raw_dir.data_ptr(), whole.data_ptr(),
+              None, dst.dst_rec.data_ptr(), None, 1, 1, 1, raw_len.data_ptr(), raw_dir.data_ptr(), whole.data_ptr(),
               ops._attr_workspace(ei.device).data_ptr(), torch.cuda.current_stream().cuda_stream))  # fmt: skip
         st = job.stats.cpu().numpy()
         w = whole.cpu().numpy()
         np.testing.assert_allclose(st[0, [0, 1, 4, 5]] + st[1, [0, 1, 4, 5]], w[[0, 1, 4, 5]], rtol=1e-12)
         np.testing.assert_array_equal(np.minimum(st[0, [2, 6]], st[1, [2, 6]]), w[[2, 6]])
         np.testing.assert_array_equal(np.maximum(st[0, [3, 7]], st[1, [3, 7]]), w[[3, 7]])
+
+
+def test_attributes_from_coordinates_equal_tabulated_records(ops, golden):
+    """The attribute kernel evaluates per-node quantities from the 8-byte coordinates for large node sets and gathers
+    tabulated records for small ones: all four combinations give BIT-identical attributes - also for edge lists whose
+    rows are not 8-byte aligned (odd edge counts: scalar lanes instead of adjacent pairs) and at the poles."""
+    g = golden("toy")
+    dx, hx = g["data_x"].copy(), g["hidden_x"]
+    dx[:3] = np.array([[np.pi / 2, 0.0], [-np.pi / 2, 1.0], [0.0, 0.0]], dtype=np.float32)
+    for name, sx, tx in (("knn3", hx, dx), ("cutoff", dx, hx)):
+        ei_np = g[f"{name}_edge_index"].astype(np.int32)
+        for cut in (0, 1):  # odd / even number of edges: row 1 of the (2, E) list is / is not 8-byte aligned
+            ei = dev(np.ascontiguousarray(ei_np[:, : ei_np.shape[1] - cut]))
+            outs = []
+            for ts, tt in ((True, True), (False, True), (True, False), (False, False)):
+                src, dst = ops.NodeTables(dev(sx), tabulate=ts), ops.NodeTables(dev(tx), tabulate=tt)
+                ln, dr = ops.edge_attributes(ei, src, dst, length_norm="unit-max", direction_norm="unit-max")
+                outs.append((ln.cpu().numpy(), dr.cpu().numpy()))
+            if name == "knn3" and cut == 0:  # the same list walked by TARGET (k edges per target), both target forms
+                for tt in (True, False):
+                    src, dst = ops.NodeTables(dev(sx), tabulate=True), ops.NodeTables(dev(tx), tabulate=tt)
+                    ln, dr = ops.edge_attributes(ei, src, dst, length_norm="unit-max", direction_norm="unit-max", regular_k=3)
+                    outs.append((ln.cpu().numpy(), dr.cpu().numpy()))
+            for ln, dr in outs[1:]:
+                np.testing.assert_array_equal(ln.view(np.int32), outs[0][0].view(np.int32))
+                np.testing.assert_array_equal(dr.view(np.int32), outs[0][1].view(np.int32))
+            e = ei.cpu().numpy()
+            want_dir = R.edge_direction(sx, tx, e, "unit-max")
+            np.testing.assert_allclose(outs[0][1], want_dir, rtol=1e-6, atol=1e-6 * np.abs(want_dir).max())
+            np.testing.assert_allclose(outs[0][0], R.edge_length(sx, tx, e, "unit-max"), rtol=1e-6)
