@@ -18,6 +18,7 @@ void agx_note_launch(int n);  // bench.py "gpu_launches" accounting
 void agx_pool_keep_warm(void);
 // copy `words` 8-byte words from device memory to host memory WITHOUT the copy engine, then sync the stream
 int agx_readback(void* host_dst, const void* dev_src, int words, cudaStream_t stream);
+void agx_output_maps(const int64_t** src_map, const int64_t** dst_map);  // set by agx_set_output_maps (thread-local)
 int agx_order_mode(void);         // thread-local override of the query-order decision: -1 auto, 0 as given, 1 binned
 void agx_note_order(int binned);  // what the last decision was  // raise the release threshold of the device's cudaMallocAsync pool (once)
 

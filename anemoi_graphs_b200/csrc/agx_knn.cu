@@ -186,11 +186,21 @@ struct KnnArgs {
     // the whole row afterwards).  Both NULL: the index labels are final.
     const int64_t* tie_rank;
     const int64_t* tie_order;
+    // output label maps (NodeMaskingMixin.undo_masking fused into the write): what is stored is src_map[reference index]
+    // / dst_map[query index] instead of the index / dst_base + query (NULL: identity)
+    const int64_t* src_map;
+    const int64_t* dst_map;
 };
 
 // the label the tie rule compares: the final position of a provisionally labelled point
 __device__ __forceinline__ int knn_tie_label(const KnnArgs& a, int ci) { return a.tie_rank ? (int)a.tie_rank[ci] : ci; }
-__device__ __forceinline__ int knn_out_label(const KnnArgs& a, int id) { return a.tie_order ? (int)a.tie_order[id] : id; }
+__device__ __forceinline__ int knn_out_label(const KnnArgs& a, int id) {
+    if (a.tie_order) id = (int)a.tie_order[id];
+    return (a.src_map && id >= 0) ? (int)a.src_map[id] : id;
+}
+__device__ __forceinline__ int knn_dst_label(const KnnArgs& a, int64_t q) {
+    return a.dst_map ? (int)a.dst_map[q] : (int32_t)(a.dst_base + q);
+}
 
 // the tiles that hold at least one flagged query, appended in arbitrary order (the results do not depend on it)
 __global__ void __launch_bounds__(256) k_flagged_tiles(const uint8_t* __restrict__ flags, int64_t nq, int64_t n_tiles,
@@ -390,13 +400,13 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn(KnnArgs a) {
                 for (int s = 0; s < CAP - 1; ++s)
                     if (s < k) {
                         bool have = top.id[s] != 0x7fffffff;
-                        os[s] = have ? top.id[s] : -1;
+                        os[s] = have ? knn_out_label(a, top.id[s]) : -1;
                         if (a.out_rdist)
                             a.out_rdist[q * k + s] = have ? agx_rdist64(ql, a.ref_latlon[top.id[s]]) : __longlong_as_double(0x7ff0000000000000ll);
                     }
                 if (a.out_dst) {
                     int32_t* od = a.out_dst + q * k;
-                    for (int s = 0; s < k; ++s) od[s] = (int32_t)(a.dst_base + q);
+                    for (int s = 0; s < k; ++s) od[s] = knn_dst_label(a, q);
                 }
             }
         }
@@ -409,7 +419,7 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn(KnnArgs a) {
                 if (a.out_rdist == nullptr) {
 #pragma unroll
                     for (int s = 0; s < CAP - 1; ++s)
-                        if (s < k) os[s] = top.id[s];
+                        if (s < k) os[s] = knn_out_label(a, top.id[s]);
                 } else {
                     TopD<CAP> fin;
                     fin.reset();
@@ -419,7 +429,7 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn(KnnArgs a) {
 #pragma unroll
                     for (int s = 0; s < CAP - 1; ++s)
                         if (s < k) {
-                            os[s] = fin.id[s];
+                            os[s] = knn_out_label(a, fin.id[s]);
                             a.out_rdist[q * k + s] = fin.r[s];
                         }
                 }
@@ -448,7 +458,7 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn(KnnArgs a) {
             }
             if (a.out_dst) {
                 int32_t* od = a.out_dst + q * k;
-                int32_t t = (int32_t)(a.dst_base + q);
+                int32_t t = knn_dst_label(a, q);
                 for (int s = 0; s < k; ++s) od[s] = t;
             }
         }
@@ -621,6 +631,8 @@ int agx_knn_ex(const agx_index_t* ix, const float* q_latlon, int64_t nq, int k, 
     a.only_flagged = only_flagged;
     a.tie_rank = tie_rank;
     a.tie_order = tie_order;
+    agx_output_maps(&a.src_map, &a.dst_map);
+    AGX_REQUIRE(!(a.src_map && tie_order), AGX_ERR_ARG, "agx_knn: output maps and a ranked re-decision exclude each other");
     int32_t* perm = nullptr;
     int32_t* tile_list = nullptr;
     a.tile_list = nullptr;

@@ -22,7 +22,8 @@ __global__ void __launch_bounds__(256) k_radius(const float4* __restrict__ pts, 
                                                 float chord2_margin, double rdist_thr, int32_t* __restrict__ counts,
                                                 const int64_t* __restrict__ offsets, int32_t* __restrict__ out_src,
                                                 int32_t* __restrict__ out_dst, int64_t dst_base,
-                                                unsigned long long* __restrict__ stats) {
+                                                unsigned long long* __restrict__ stats, const int64_t* __restrict__ src_map,
+                                                const int64_t* __restrict__ dst_map) {
     const int lane = threadIdx.x & 31;
     const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const float t_in = chord2_thr - chord2_margin, t_out = chord2_thr + chord2_margin;
@@ -32,7 +33,7 @@ __global__ void __launch_bounds__(256) k_radius(const float4* __restrict__ pts, 
         const float2 ql = q_latlon[q];
         const float3 qv = agx_search_xyz(ql);
         int64_t out_pos = FILL ? offsets[q] : 0;
-        const int32_t dst = (int32_t)(dst_base + q);
+        const int32_t dst = dst_map ? (int32_t)dst_map[q] : (int32_t)(dst_base + q);
         int found = 0;
         // single-face fast path (the cap ends at least a cell inside the query's major face), else all six faces
         const int mface = agx_major_face(qv.x, qv.y, qv.z);
@@ -75,7 +76,7 @@ __global__ void __launch_bounds__(256) k_radius(const float4* __restrict__ pts, 
                     if (FILL) {
                         if (hit) {
                             int64_t w = out_pos + __popc(m & ((1u << lane) - 1u));
-                            out_src[w] = ci;
+                            out_src[w] = src_map ? (int32_t)src_map[ci] : ci;
                             out_dst[w] = dst;
                         }
                         out_pos += __popc(m);
@@ -109,6 +110,8 @@ struct RadiusArgs {
     int32_t* out_dst;
     int64_t dst_base;
     unsigned long long* stats;
+    const int64_t* src_map;  // output label maps (undo_masking fused into the write), NULL: identity
+    const int64_t* dst_map;
 };
 
 template <bool FILL>
@@ -145,7 +148,7 @@ __global__ void __launch_bounds__(AGX_TILE_WARPS * 32) k_radius_tile(RadiusArgs 
         }
         int found = 0;
         int64_t out_pos = (FILL && active) ? a.offsets[q] : 0;
-        const int32_t dst = (int32_t)(a.dst_base + q);
+        const int32_t dst = a.dst_map ? (int32_t)a.dst_map[q] : (int32_t)(a.dst_base + q);
         auto visit = [&](const float4 c) {
             float dx = qv.x - c.x, dy = qv.y - c.y, dz = qv.z - c.z;
             float d = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
@@ -161,7 +164,7 @@ __global__ void __launch_bounds__(AGX_TILE_WARPS * 32) k_radius_tile(RadiusArgs 
             }
             if (FILL) {
                 if (active) {
-                    a.out_src[out_pos] = ci;
+                    a.out_src[out_pos] = a.src_map ? (int32_t)a.src_map[ci] : ci;
                     a.out_dst[out_pos] = dst;
                     ++out_pos;
                 }
@@ -247,6 +250,7 @@ static int launch_radius_tile(const agx_index_t* ix, const float* q_latlon, int6
     a.out_dst = out_dst;
     a.dst_base = dst_base;
     a.stats = (unsigned long long*)stats;
+    agx_output_maps(&a.src_map, &a.dst_map);
     const int32_t* perm = nullptr;
     int rc = radius_query_order(ix, q_latlon, nq, a.t_out, FILL, &perm, stream);
     if (rc != AGX_OK) return rc;
@@ -287,7 +291,7 @@ extern "C" int agx_radius_count(const agx_index_t* ix, const float* q_latlon, in
         return launch_radius_tile<false>(ix, q_latlon, nq, c2, m, thr, counts, nullptr, nullptr, nullptr, 0, nullptr, stream);
     int grid = agx_grid(nq * 32, 256, 8);
     k_radius<false><<<grid, 256, 0, stream>>>(ix->pts, ix->cell_start, ix->latlon, ix->cells, (const float2*)q_latlon,
-                                             nq, c2, m, thr, counts, nullptr, nullptr, nullptr, 0, nullptr);
+                                             nq, c2, m, thr, counts, nullptr, nullptr, nullptr, 0, nullptr, nullptr, nullptr);
     AGX_LAUNCH_OK();
     agx_note_launch(1);
     return AGX_OK;
@@ -309,9 +313,11 @@ extern "C" int agx_radius_fill(const agx_index_t* ix, const float* q_latlon, int
     if (radius_use_tiles(ix))
         return launch_radius_tile<true>(ix, q_latlon, nq, c2, m, thr, nullptr, offsets, out_src, out_dst, dst_base, stats, stream);
     int grid = agx_grid(nq * 32, 256, 8);
+    const int64_t *src_map = nullptr, *dst_map = nullptr;
+    agx_output_maps(&src_map, &dst_map);
     k_radius<true><<<grid, 256, 0, stream>>>(ix->pts, ix->cell_start, ix->latlon, ix->cells, (const float2*)q_latlon, nq,
                                             c2, m, thr, nullptr, offsets, out_src, out_dst, dst_base,
-                                            (unsigned long long*)stats);
+                                            (unsigned long long*)stats, src_map, dst_map);
     AGX_LAUNCH_OK();
     agx_note_launch(1);
     return AGX_OK;

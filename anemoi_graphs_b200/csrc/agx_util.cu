@@ -70,6 +70,18 @@ void agx_note_order(int binned) { g_order_last = binned ? 1 : 0; }
 extern "C" void agx_set_query_order_mode(int mode) { g_order_mode = mode < 0 ? -1 : (mode ? 1 : 0); }
 extern "C" int agx_last_query_order(void) { return g_order_last; }
 
+// Output label maps of the searches (agx_b200.h agx_set_output_maps): thread-local, read at launch time.
+static thread_local const int64_t* g_src_map = nullptr;
+static thread_local const int64_t* g_dst_map = nullptr;
+extern "C" void agx_set_output_maps(const int64_t* src_map, const int64_t* dst_map) {
+    g_src_map = src_map;
+    g_dst_map = dst_map;
+}
+void agx_output_maps(const int64_t** src_map, const int64_t** dst_map) {
+    *src_map = g_src_map;
+    *dst_map = g_dst_map;
+}
+
 extern "C" const char* agx_last_error(void) { return g_err; }
 extern "C" int agx_abi_version(void) { return AGX_ABI_VERSION; }
 extern "C" int64_t agx_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }

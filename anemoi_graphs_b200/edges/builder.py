@@ -123,7 +123,9 @@ class BaseEdgeBuilder(ABC):
                     "several edge builders on one node pair are merged on complete edge lists: build this recipe in the "
                     "default output mode (AGX_OUTPUT=gather / device.set_sharded_output(False))"
                 )
-            edge_dev = concat_edges_device(_device.device_edge_index(store), edge_dev)
+            edge_dev = concat_edges_device(
+                _device.device_edge_index(store), edge_dev, int(graph[self.source_name]["x"].shape[0]), int(x.shape[0])
+            )
             if edge_type not in store["edge_type"]:
                 store["edge_type"] = store["edge_type"] + "," + edge_type
         else:
@@ -165,8 +167,9 @@ class BaseEdgeBuilder(ABC):
 class NodeMaskingMixin:
     """Mixin class for masking source/target nodes when building edges (edges/builder.py:159-193).
 
-    Row selection and the compact->original index map are device gathers instead of the reference's
-    python-dict ``np.vectorize`` remap."""
+    Row selection is a device gather; the compact->original index map (the reference's python-dict ``np.vectorize``
+    remap) is applied by the search kernels as they write (``masked_outputs``), so no pass over the edge list follows.
+    ``undo_masking`` itself remains for callers that hold compact indices."""
 
     @staticmethod
     def _selection(nodes, mask_attr_name: str | None, device) -> torch.Tensor | None:
@@ -194,6 +197,12 @@ class NodeMaskingMixin:
         if dst_sel is not None:
             dst = dst[dst_sel]
         return src, dst, src_sel, dst_sel
+
+    @staticmethod
+    def masked_outputs(src_sel, dst_sel, lo: int, hi: int):
+        """``with self.masked_outputs(src_sel, dst_sel, lo, hi):`` - searches over the query rows [lo, hi) of the masked
+        coordinates write ORIGINAL node indices (``undo_masking`` fused into the kernels' stores, ``ops.output_maps``)."""
+        return ops.output_maps(src_sel, None if dst_sel is None else dst_sel[lo:hi].contiguous())
 
     @staticmethod
     def undo_masking(edge_index: torch.Tensor, src_sel, dst_sel) -> torch.Tensor:
@@ -304,8 +313,9 @@ class KNNEdges(BaseEdgeBuilder, NodeMaskingMixin):
         if sharded_out:
             # rank-local block, global target ids; no exchange
             with _device.neighbour_index(self._src_state if src_sel is None else None, src, hint_k=k) as index:
-                out = index.knn(dst[lo:hi], k, dst_base=lo, stats=self.stats)
-            out = _device.tag_rows(self.undo_masking(out, src_sel, dst_sel), *self._row_provs)
+                with self.masked_outputs(src_sel, dst_sel, lo, hi):
+                    out = index.knn(dst[lo:hi], k, dst_base=lo, stats=self.stats)
+            out = _device.tag_rows(out, *self._row_provs)
             meta = _device.edge_meta(out, create=True)
             meta.shard, meta.regular_k = shard, k
             return out
@@ -337,12 +347,13 @@ class KNNEdges(BaseEdgeBuilder, NodeMaskingMixin):
                 # equal blocks: one in-place NCCL all-gather after the search (640 GB/s per rank; chunking the search
                 # to overlap an NCCL exchange was measured and does not pay: the persistent search kernel leaves no
                 # room for the collective's CTAs until it ends - 40 M queries, N = 2: 4.8 ms chunked against 4.5 ms)
-                index.knn(dst[lo:hi], k, dst_base=lo, stats=self.stats, out=out, out_offset=lo * k)
+                with self.masked_outputs(src_sel, dst_sel, lo, hi):  # original node indices straight from the kernel
+                    index.knn(dst[lo:hi], k, dst_base=lo, stats=self.stats, out=out, out_offset=lo * k)
         if w > 1:
             counts = [(b - a) * k for a, b in (_device.shard_range(nq, r, w) for r in range(w))]
             out = _gather_blocks(out, counts, rank, src_sel is not None or dst_sel is not None)
         local = _device.edge_meta(out).local if _device.edge_meta(out) is not None else None
-        out = _device.tag_rows(self.undo_masking(out, src_sel, dst_sel), *self._row_provs)
+        out = _device.tag_rows(out, *self._row_provs)
         meta = _device.edge_meta(out, create=True)
         meta.regular_k, meta.local = k, local  # k edges per target, target after target: attributes walk it by target
         return out
@@ -412,9 +423,10 @@ class CutOffEdges(BaseEdgeBuilder, NodeMaskingMixin):
                 q = dst[lo:hi]
                 offsets, total = index.radius_count(q, self.radius)
                 out = torch.empty((2, total), dtype=torch.int32, device=dst.device)
-                index.radius_fill(q, self.radius, offsets, total, out, 0, dst_base=lo, stats=self.stats)
+                with self.masked_outputs(src_sel, dst_sel, lo, hi):
+                    index.radius_fill(q, self.radius, offsets, total, out, 0, dst_base=lo, stats=self.stats)
             counts = _device.exchange_counts(total, dst.device)
-            out = _device.tag_rows(self.undo_masking(out, src_sel, dst_sel), *self._row_provs)
+            out = _device.tag_rows(out, *self._row_provs)
             _device.edge_meta(out, create=True).shard = _device.Shard(rank, w, counts)
             return out
         with ops.NeighbourIndex(src, hint_radius=self.radius) as index:
@@ -454,10 +466,11 @@ class CutOffEdges(BaseEdgeBuilder, NodeMaskingMixin):
                 counts = _device.all_gather_counts(total, dst.device) if w > 1 else [total]
                 out = torch.empty((2, sum(counts)), dtype=torch.int32, device=dst.device)
                 base = sum(counts[:rank])
-                index.radius_fill(q, self.radius, offsets, total, out, base, dst_base=lo, stats=self.stats)
+                with self.masked_outputs(src_sel, dst_sel, lo, hi):  # original node indices straight from the kernel
+                    index.radius_fill(q, self.radius, offsets, total, out, base, dst_base=lo, stats=self.stats)
         if w > 1:
             out = _gather_blocks(out, counts, rank, src_sel is not None or dst_sel is not None)
-        return _device.tag_rows(self.undo_masking(out, src_sel, dst_sel), *self._row_provs)
+        return _device.tag_rows(out, *self._row_provs)
 
 
 class MultiScaleEdges(BaseEdgeBuilder):

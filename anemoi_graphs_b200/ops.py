@@ -231,6 +231,25 @@ class NeighbourIndex:
         return self.radius_fill(q, radius, offsets, total, out, 0, dst_base, stats)
 
 
+class output_maps:
+    """``with output_maps(src_sel, dst_sel):`` - the searches launched inside write ``src_sel[reference index]`` /
+    ``dst_sel[query index]`` (CUDA int64, ascending: the row selections of masked node sets) instead of compact indices:
+    ``NodeMaskingMixin.undo_masking`` fused into the kernels' stores (``agx_set_output_maps``)."""
+
+    def __init__(self, src_sel: torch.Tensor | None, dst_sel: torch.Tensor | None) -> None:
+        for sel in (src_sel, dst_sel):
+            assert sel is None or (sel.is_cuda and sel.dtype == torch.int64 and sel.is_contiguous())
+        self.src_sel, self.dst_sel = src_sel, dst_sel
+
+    def __enter__(self):
+        if self.src_sel is not None or self.dst_sel is not None:
+            load_library().agx_set_output_maps(ptr(self.src_sel), ptr(self.dst_sel))
+        return self
+
+    def __exit__(self, *exc) -> None:
+        load_library().agx_set_output_maps(None, None)
+
+
 def search_vectors(x: torch.Tensor) -> torch.Tensor:
     """float32 (n, 3) unit vectors the neighbour search filters with (see ``agx_search_vectors``)."""
     x = _dev_x(x)
@@ -904,6 +923,7 @@ def voronoi_areas(x: torch.Tensor, radius: float = 1.0) -> torch.Tensor:
 __all__ = [
     "multiscale_tri_edges_mapped",
     "relabel_rows",
+    "output_maps",
     "DeferredEdgeAttributes",
     "voronoi_areas",
     "HexCells",

@@ -162,6 +162,26 @@ int agx_relabel_nodes(int32_t* row /*DEV n, in place*/, int64_t n, const int64_t
 int agx_relabel_rows(int32_t* const* rows /*HOST n_rows x DEV*/, const int64_t* lens /*HOST n_rows*/, int n_rows,
                      const int64_t* new_index /*DEV*/, void* stream);
 
+/* ---- masked node sets -------------------------------------------------------------------------------------
+ * NodeMaskingMixin.undo_masking (edges/builder.py:176-193: compact indices of the row-selected coordinates mapped back
+ * to node indices through a python dict + np.vectorize) fused into the searches' writes: while maps are set (thread-
+ * local, read when a search is launched) agx_knn* / agx_radius_fill store src_map[reference index] / dst_map[query
+ * index] instead of the index / dst_base + query.  Maps: DEV int64, ascending (np.where(mask)[0]); NULL = identity.
+ * Decisions (ties by lower index) are unaffected: an ascending map preserves the order.  Reset with (NULL, NULL).  */
+void agx_set_output_maps(const int64_t* src_map /*DEV or NULL*/, const int64_t* dst_map /*DEV or NULL*/);
+
+/* ---- merged edge lists --------------------------------------------------------------------------------
+ * utils.concat_edges (utils.py:66-81: torch.unique(torch.cat([e1, e2], dim=1), dim=1)): the columns of two (2, E) int32
+ * edge lists sorted lexicographically by (source, target), duplicates removed - what a second edge builder on the same
+ * node pair does to the edge set (edges/builder.py:105-110).  _begin packs both lists into 64-bit keys, sorts them (radix
+ * sort over the key bits the node counts can set) and returns the number of distinct columns (one read-back); the caller
+ * allocates the (2, n_unique) result and _finish unpacks into its rows and releases the scratch (call it with NULL rows
+ * to release only).  Peak extra memory: 16 bytes per input edge = twice the result.                             */
+int agx_concat_edges_begin(const int32_t* a_src /*DEV na*/, const int32_t* a_dst, int64_t na, const int32_t* b_src /*DEV nb*/,
+                           const int32_t* b_dst, int64_t nb, int64_t n_src_nodes, int64_t n_dst_nodes, void** handle,
+                           int64_t* n_unique /*HOST*/, void* stream);
+int agx_concat_edges_finish(void* handle, int32_t* out_src /*DEV n_unique*/, int32_t* out_dst /*DEV n_unique*/, void* stream);
+
 /* ---- node ordering, device half ---------------------------------------------------------------------------
  * get_coordinates_ordering (generate/utils.py:15-33): the two (unstable, order-defining) argsorts stay numpy's on the
  * host; given their results this evaluates `order = arange(n)[index_latitude][index_longitude[::-1]]`, its inverse

@@ -585,3 +585,87 @@ def test_attributes_from_coordinates_equal_tabulated_records(ops, golden):
             want_dir = R.edge_direction(sx, tx, e, "unit-max")
             np.testing.assert_allclose(outs[0][1], want_dir, rtol=1e-6, atol=1e-6 * np.abs(want_dir).max())
             np.testing.assert_allclose(outs[0][0], R.edge_length(sx, tx, e, "unit-max"), rtol=1e-6)
+
+
+def _pool_high_water(reset: bool = False) -> int:
+    """High-water mark of the device's default stream-ordered memory pool (what libagx_b200's scratch comes from)."""
+    from cuda.bindings import runtime as rt
+
+    err, pool = rt.cudaDeviceGetDefaultMemPool(torch.cuda.current_device())
+    assert int(err) == 0
+    if reset:
+        (err,) = rt.cudaMemPoolSetAttribute(pool, rt.cudaMemPoolAttr.cudaMemPoolAttrUsedMemHigh, rt.cuuint64_t(0))
+        assert int(err) == 0
+    err, value = rt.cudaMemPoolGetAttribute(pool, rt.cudaMemPoolAttr.cudaMemPoolAttrUsedMemHigh)
+    assert int(err) == 0
+    return int(value)
+
+
+def test_concat_edges_kernel_matches_torch_unique_and_reference_order():
+    """utils.concat_edges (utils.py:66-81): sorted unique columns of two edge lists - small case against the reference's
+    own expression, with duplicates inside and across the lists and an empty list."""
+    from anemoi_graphs_b200.utils import concat_edges_device
+
+    rng = np.random.default_rng(3)
+    e1 = rng.integers(0, 50, size=(2, 4000)).astype(np.int32)
+    e2 = rng.integers(0, 50, size=(2, 3001)).astype(np.int32)
+    got = concat_edges_device(dev(e1), dev(e2), 50, 50).cpu()
+    want = torch.unique(torch.cat([torch.from_numpy(e1), torch.from_numpy(e2)], dim=1), dim=1)  # the reference's line
+    assert got.dtype == torch.int32 and torch.equal(got, want)
+    assert torch.equal(concat_edges_device(dev(e1), dev(e2)).cpu(), want)  # node counts unknown: all key bits sorted
+    empty = torch.empty((2, 0), dtype=torch.int32, device="cuda")
+    assert torch.equal(concat_edges_device(dev(e1), empty, 50, 50).cpu(), torch.unique(torch.from_numpy(e1), dim=1))
+    assert concat_edges_device(empty, empty, 50, 50).shape == (2, 0)
+
+
+def test_concat_edges_120m_edges_within_twice_the_output():
+    """>= 100 M edges: two 60 M-edge lists over 6.6 M x 164 k nodes, 25 % of the second duplicating
+    the first.  Sorted, unique, the right count - and the scratch high-water mark stays within 2 x the result (+ CUB's
+    histogram scratch), where cat -> int64 -> torch.unique needs > 5 x."""
+    from anemoi_graphs_b200.utils import concat_edges_device
+
+    n_src, n_dst, m = 6_599_680, 163_842, 60_000_000
+    g = torch.Generator(device="cuda").manual_seed(1)
+    e1 = torch.stack([torch.randint(0, n_src, (m,), device="cuda", generator=g, dtype=torch.int32),
+                      torch.randint(0, n_dst, (m,), device="cuda", generator=g, dtype=torch.int32)])  # fmt: skip
+    e2 = torch.stack([torch.randint(0, n_src, (m,), device="cuda", generator=g, dtype=torch.int32),
+                      torch.randint(0, n_dst, (m,), device="cuda", generator=g, dtype=torch.int32)])  # fmt: skip
+    e2[:, : m // 4] = e1[:, : m // 4]
+    torch.cuda.synchronize()
+    _pool_high_water(reset=True)
+    out = concat_edges_device(e1, e2, n_src, n_dst)
+    torch.cuda.synchronize()
+    peak = _pool_high_water()
+    out_bytes = out.numel() * 4
+    assert peak <= 2 * out_bytes * 1.10 + (64 << 20), (peak, out_bytes)
+    key = (out[0].to(torch.int64) << 32) | out[1].to(torch.int64)
+    assert bool((key[1:] > key[:-1]).all())  # strictly ascending (src, dst): sorted and unique
+    del key
+    # the right set: the distinct keys of the inputs, counted independently in two halves of the key space
+    k1 = (e1[0].to(torch.int64) << 32) | e1[1].to(torch.int64)
+    k2 = (e2[0].to(torch.int64) << 32) | e2[1].to(torch.int64)
+    want = torch.unique(torch.cat([k1, k2]))
+    assert want.numel() == out.shape[1]
+    assert torch.equal(want, (out[0].to(torch.int64) << 32) | out[1].to(torch.int64))
+
+
+def test_masked_searches_write_original_node_indices(ops, golden):
+    """``ops.output_maps``: undo_masking fused into the KNN / cut-off writes equals searching the masked coordinates and
+    mapping the compact indices back afterwards (edges/builder.py:176-193)."""
+    g = golden("toy")
+    dx, hx = g["data_x"], g["hidden_x"]
+    rng = np.random.default_rng(11)
+    src_sel = np.sort(rng.choice(hx.shape[0], size=hx.shape[0] // 2, replace=False)).astype(np.int64)
+    dst_sel = np.sort(rng.choice(dx.shape[0], size=dx.shape[0] // 3, replace=False)).astype(np.int64)
+    with ops.NeighbourIndex(dev(hx[src_sel]), hint_k=3) as ix:
+        plain = ix.knn(dev(dx[dst_sel]), 3).cpu().numpy()
+        with ops.output_maps(dev(src_sel), dev(dst_sel)):
+            fused = ix.knn(dev(dx[dst_sel]), 3).cpu().numpy()
+        again = ix.knn(dev(dx[dst_sel]), 3).cpu().numpy()  # the maps are gone after the block
+    np.testing.assert_array_equal(fused, np.stack([src_sel[plain[0]], dst_sel[plain[1]]]).astype(np.int32))
+    np.testing.assert_array_equal(again, plain)
+    with ops.NeighbourIndex(dev(dx[dst_sel]), hint_radius=0.3) as ix:
+        plain = ix.radius(dev(hx[src_sel]), 0.3).cpu().numpy()
+        with ops.output_maps(dev(dst_sel), dev(src_sel)):
+            fused = ix.radius(dev(hx[src_sel]), 0.3).cpu().numpy()
+    np.testing.assert_array_equal(fused, np.stack([dst_sel[plain[0]], src_sel[plain[1]]]).astype(np.int32))
