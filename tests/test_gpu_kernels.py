@@ -589,12 +589,13 @@ def test_attributes_from_coordinates_equal_tabulated_records(ops, golden):
 
 def _pool_high_water(reset: bool = False) -> int:
     """High-water mark of the device's default stream-ordered memory pool (what libagx_b200's scratch comes from)."""
+    from cuda.bindings import driver as dr
     from cuda.bindings import runtime as rt
 
     err, pool = rt.cudaDeviceGetDefaultMemPool(torch.cuda.current_device())
     assert int(err) == 0
     if reset:
-        (err,) = rt.cudaMemPoolSetAttribute(pool, rt.cudaMemPoolAttr.cudaMemPoolAttrUsedMemHigh, rt.cuuint64_t(0))
+        (err,) = rt.cudaMemPoolSetAttribute(pool, rt.cudaMemPoolAttr.cudaMemPoolAttrUsedMemHigh, dr.cuuint64_t(0))
         assert int(err) == 0
     err, value = rt.cudaMemPoolGetAttribute(pool, rt.cudaMemPoolAttr.cudaMemPoolAttrUsedMemHigh)
     assert int(err) == 0
