@@ -21,16 +21,19 @@ creator = GraphCreator(bench.recipe(res))
 for resident in (True,) if os.environ.get('AGX_TRACE_RESIDENT_ONLY') else (True, False):
     agx_device.set_resident(resident)
     x = x_dev if resident else x_host
+    back_to_back = os.environ.get("AGX_TRACE_BACK_TO_BACK") == "1"  # as bench.py runs them: no sync between steps
     for rep in range(8):
         g = None
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
+        if not back_to_back or rep == 0:
             torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+                torch.cuda.synchronize()
         t0 = time.perf_counter()
         g = bench.run_step(creator, x)
         t1 = time.perf_counter()
-        torch.cuda.synchronize()
+        if not back_to_back:
+            torch.cuda.synchronize()
         t2 = time.perf_counter()
         tr = agx_device.last_trace
         if rep >= 5:
