@@ -61,12 +61,10 @@ SIGNATURES = {
     "agx_mark_nodes": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
     "agx_relabel_nodes": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "agx_set_output_maps": (None, [c_void_p, c_void_p]),
-    "agx_concat_edges_begin": (
+    "agx_concat_edges": (
         c_int,
-        [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_int64, POINTER(c_void_p), POINTER(c_int64),
-         c_void_p],
-    ),  # fmt: skip
-    "agx_concat_edges_finish": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+        [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, POINTER(c_int64), c_void_p],
+    ),
     "agx_relabel_rows": (c_int, [POINTER(c_void_p), POINTER(c_int64), c_int, c_void_p, c_void_p]),
     "agx_node_tables": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "agx_edge_attrs": (

@@ -7,7 +7,8 @@
 //   k_concat_heads     number of distinct keys per tile of 1024 (a key is a head if it differs from its predecessor)
 //   agx_exclusive_scan tile offsets (+ the total, read back: the caller allocates the result)
 //   k_concat_fill      heads unpacked straight into the two rows of the result
-// Peak extra memory: two key buffers = 16 bytes per input edge = 2 x the size of the result (plus CUB's histogram scratch).
+// The result allocation (sized for na + nb columns) doubles as the sort's alternate buffer, so the scratch besides the
+// result is ONE key buffer: 8 bytes per input edge (plus CUB's histograms).
 #include <cub/device/device_radix_sort.cuh>
 
 #include "agx_common.cuh"
@@ -82,107 +83,79 @@ __global__ void __launch_bounds__(256) k_concat_fill(const unsigned long long* _
         }
 }
 
-struct agx_concat {
-    unsigned long long* keys[2];
-    int sorted;  // which of the two buffers holds the sorted keys
-    int64_t n;
-    int64_t* offsets;
-};
-
 static int bits_for(int64_t max_value) {
     int b = 1;
     while (b < 32 && ((int64_t)1 << b) <= max_value) ++b;
     return b;
 }
 
-extern "C" int agx_concat_edges_begin(const int32_t* a_src, const int32_t* a_dst, int64_t na, const int32_t* b_src,
-                                      const int32_t* b_dst, int64_t nb, int64_t n_src_nodes, int64_t n_dst_nodes,
-                                      void** handle, int64_t* n_unique, void* stream_) {
+// `out` is the RESULT allocation, sized for the worst case (2 * (na + nb) int32 = as many bytes as one key buffer): it
+// doubles as the radix sort's alternate buffer, so the only scratch besides it is ONE key buffer (8 bytes per input
+// edge) + CUB's histograms.  On return the first 2 * n_unique int32 of `out` are the result, row-major (2, n_unique).
+extern "C" int agx_concat_edges(const int32_t* a_src, const int32_t* a_dst, int64_t na, const int32_t* b_src,
+                                const int32_t* b_dst, int64_t nb, int64_t n_src_nodes, int64_t n_dst_nodes, int32_t* out,
+                                int64_t* n_unique, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
-    AGX_REQUIRE(handle && n_unique, AGX_ERR_ARG, "agx_concat_edges_begin: NULL output");
-    *handle = nullptr;
+    AGX_REQUIRE(n_unique != nullptr, AGX_ERR_ARG, "agx_concat_edges: n_unique is NULL");
     *n_unique = 0;
-    AGX_REQUIRE(na >= 0 && nb >= 0, AGX_ERR_ARG, "agx_concat_edges_begin: negative length");
+    AGX_REQUIRE(na >= 0 && nb >= 0, AGX_ERR_ARG, "agx_concat_edges: negative length");
     AGX_REQUIRE(n_src_nodes > 0 && n_dst_nodes > 0 && n_src_nodes <= 2147483647ll && n_dst_nodes <= 2147483647ll, AGX_ERR_ARG,
-                "agx_concat_edges_begin: node counts must be in [1, 2^31)");
+                "agx_concat_edges: node counts must be in [1, 2^31)");
     const int64_t n = na + nb;
     if (n == 0) return AGX_OK;
-    AGX_REQUIRE((na == 0 || (a_src && a_dst)) && (nb == 0 || (b_src && b_dst)), AGX_ERR_ARG, "agx_concat_edges_begin: NULL buffer");
+    AGX_REQUIRE((na == 0 || (a_src && a_dst)) && (nb == 0 || (b_src && b_dst)) && out, AGX_ERR_ARG, "agx_concat_edges: NULL buffer");
+    AGX_REQUIRE(((uintptr_t)out & 7) == 0, AGX_ERR_ARG, "agx_concat_edges: out must be 8-byte aligned");
     agx_pool_keep_warm();
-    agx_concat* h = new agx_concat();
-    h->n = n;
-    h->keys[0] = h->keys[1] = nullptr;
-    h->offsets = nullptr;
+    unsigned long long* keys = nullptr;
+    unsigned long long* alt = reinterpret_cast<unsigned long long*>(out);
     void* temp = nullptr;
     int32_t* counts = nullptr;
+    int64_t* offsets = nullptr;
     const int64_t n_tiles = (n + CONCAT_TILE - 1) / CONCAT_TILE;
     cudaError_t e;
-#define CC_TRY(expr)                                                                                          \
-    if ((e = (expr)) != cudaSuccess) {                                                                        \
-        agx_set_error("%s failed: %s", #expr, cudaGetErrorString(e));                                         \
-        cudaFreeAsync(h->keys[0], stream); cudaFreeAsync(h->keys[1], stream); cudaFreeAsync(h->offsets, stream); \
-        cudaFreeAsync(temp, stream); cudaFreeAsync(counts, stream);                                           \
-        delete h;                                                                                             \
-        return AGX_ERR_CUDA;                                                                                  \
+#define CC_TRY(expr)                                                                                       \
+    if ((e = (expr)) != cudaSuccess) {                                                                     \
+        agx_set_error("%s failed: %s", #expr, cudaGetErrorString(e));                                      \
+        cudaFreeAsync(keys, stream); cudaFreeAsync(temp, stream); cudaFreeAsync(counts, stream);           \
+        cudaFreeAsync(offsets, stream);                                                                    \
+        return AGX_ERR_CUDA;                                                                               \
     }
-    CC_TRY(cudaMallocAsync(&h->keys[0], n * sizeof(unsigned long long), stream));
-    CC_TRY(cudaMallocAsync(&h->keys[1], n * sizeof(unsigned long long), stream));
-    k_concat_pack<<<agx_grid(n, 256, 8), 256, 0, stream>>>(a_src, a_dst, na, b_src, b_dst, nb, h->keys[0]);
+    CC_TRY(cudaMallocAsync(&keys, n * sizeof(unsigned long long), stream));
+    k_concat_pack<<<agx_grid(n, 256, 8), 256, 0, stream>>>(a_src, a_dst, na, b_src, b_dst, nb, keys);
     agx_note_launch(1);
-    cub::DoubleBuffer<unsigned long long> buf(h->keys[0], h->keys[1]);
-    const int end_bit = 32 + bits_for(n_src_nodes - 1);  // (the low 32 bits hold the target; radix passes over unused bits are cheap to skip
-    size_t temp_bytes = 0;                               //  only at the top, CUB sorts [begin_bit, end_bit))
-    CC_TRY(cub::DeviceRadixSort::SortKeys(nullptr, temp_bytes, buf, (long long)n, 0, end_bit, stream));
-    // the target field: skip its unused high bits by sorting in two ranges only when that saves a pass (8-bit digits)
-    CC_TRY(cudaMallocAsync(&temp, temp_bytes > 0 ? temp_bytes : 16, stream));
+    cub::DoubleBuffer<unsigned long long> buf(keys, alt);
+    const int end_bit = 32 + bits_for(n_src_nodes - 1);
     const int dst_bits = bits_for(n_dst_nodes - 1);
+    size_t temp_bytes = 0;
+    CC_TRY(cub::DeviceRadixSort::SortKeys(nullptr, temp_bytes, buf, (long long)n, 0, end_bit, stream));
+    CC_TRY(cudaMallocAsync(&temp, temp_bytes > 0 ? temp_bytes : 16, stream));
     if ((32 - dst_bits) >= 8) {
-        // LSD radix sort = stable passes from the least significant field: first the used target bits, then the source bits
+        // LSD radix sort = stable passes from the least significant field: the used target bits, then the source bits
         CC_TRY(cub::DeviceRadixSort::SortKeys(temp, temp_bytes, buf, (long long)n, 0, dst_bits, stream));
         CC_TRY(cub::DeviceRadixSort::SortKeys(temp, temp_bytes, buf, (long long)n, 32, end_bit, stream));
     } else {
         CC_TRY(cub::DeviceRadixSort::SortKeys(temp, temp_bytes, buf, (long long)n, 0, end_bit, stream));
     }
     agx_note_launch(2);
-    h->sorted = buf.selector;
-    const unsigned long long* sorted = h->keys[h->sorted];
+    if (buf.Current() != keys)  // the sorted keys must not live in the buffer the result is unpacked into
+        CC_TRY(cudaMemcpyAsync(keys, alt, n * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, stream));
     CC_TRY(cudaMallocAsync(&counts, n_tiles * sizeof(int32_t), stream));
-    CC_TRY(cudaMallocAsync(&h->offsets, (n_tiles + 1) * sizeof(int64_t), stream));
-    k_concat_heads<<<(unsigned)n_tiles, 256, 0, stream>>>(sorted, n, counts);
+    CC_TRY(cudaMallocAsync(&offsets, (n_tiles + 1) * sizeof(int64_t), stream));
+    k_concat_heads<<<(unsigned)n_tiles, 256, 0, stream>>>(keys, n, counts);
     agx_note_launch(1);
-    int rc = agx_exclusive_scan(counts, n_tiles, h->offsets, n_unique, stream);  // reads the total back (one sync)
-    cudaFreeAsync(temp, stream);
-    cudaFreeAsync(counts, stream);
-    // the unsorted buffer is no longer needed
-    cudaFreeAsync(h->keys[1 - h->sorted], stream);
-    h->keys[1 - h->sorted] = nullptr;
-    if (rc != AGX_OK) {
-        cudaFreeAsync(h->keys[h->sorted], stream);
-        cudaFreeAsync(h->offsets, stream);
-        delete h;
-        return rc;
-    }
-#undef CC_TRY
-    *handle = h;
-    return AGX_OK;
-}
-
-extern "C" int agx_concat_edges_finish(void* handle, int32_t* out_src, int32_t* out_dst, void* stream_) {
-    cudaStream_t stream = (cudaStream_t)stream_;
-    if (handle == nullptr) return AGX_OK;
-    agx_concat* h = (agx_concat*)handle;
-    int rc = AGX_OK;
-    if (out_src && out_dst) {
-        const int64_t n_tiles = (h->n + CONCAT_TILE - 1) / CONCAT_TILE;
-        k_concat_fill<<<(unsigned)n_tiles, 256, 0, stream>>>(h->keys[h->sorted], h->n, h->offsets, out_src, out_dst);
+    int rc = agx_exclusive_scan(counts, n_tiles, offsets, n_unique, stream);  // reads the total back (one sync)
+    if (rc == AGX_OK) {
+        k_concat_fill<<<(unsigned)n_tiles, 256, 0, stream>>>(keys, n, offsets, out, out + *n_unique);
         agx_note_launch(1);
         if (cudaGetLastError() != cudaSuccess) {
-            agx_set_error("agx_concat_edges_finish: kernel launch failed");
+            agx_set_error("agx_concat_edges: kernel launch failed");
             rc = AGX_ERR_CUDA;
         }
     }
-    cudaFreeAsync(h->keys[h->sorted], stream);
-    cudaFreeAsync(h->offsets, stream);
-    delete h;
+#undef CC_TRY
+    cudaFreeAsync(keys, stream);
+    cudaFreeAsync(temp, stream);
+    cudaFreeAsync(counts, stream);
+    cudaFreeAsync(offsets, stream);
     return rc;
 }

@@ -25,8 +25,9 @@ def concat_edges_device(e1: torch.Tensor, e2: torch.Tensor, n_src_nodes: int | N
     """``torch.unique(cat, dim=1)`` of two CUDA (2, E) int32 edge lists: columns sorted by (src, dst), unique
     (utils.py:66-81) - ``agx_concat_edges_*``: both lists packed into 64-bit keys ``src << 32 | dst`` by one kernel, a
     radix sort over the key bits the node counts can set, the distinct keys unpacked straight into the rows of the
-    result.  Peak extra memory is two key buffers (twice the result); no concatenated int64 list, no ``torch.unique``."""
-    from ctypes import byref, c_int64, c_void_p
+    result.  The result allocation doubles as the sort's alternate buffer: the scratch besides it is one key buffer (8 bytes
+    per input edge); no concatenated int64 list, no ``torch.unique``."""
+    from ctypes import byref, c_int64
 
     from ._cabi import check, current_stream, load_library
 
@@ -35,17 +36,21 @@ def concat_edges_device(e1: torch.Tensor, e2: torch.Tensor, n_src_nodes: int | N
     for e in (e1, e2):
         assert e.is_cuda and e.dtype == torch.int32 and e.dim() == 2 and e.shape[0] == 2
     e1, e2 = e1.contiguous(), e2.contiguous()
-    lib = load_library()
-    handle, n_unique = c_void_p(), c_int64()
+    n = int(e1.shape[1]) + int(e2.shape[1])
+    # the result allocation, sized for "no duplicates": it doubles as the sort's alternate key buffer
+    buf = torch.empty(2 * max(n, 1), dtype=torch.int32, device=e1.device)
+    n_unique = c_int64()
     big = 2**31 - 1
     check(
-        lib.agx_concat_edges_begin(
+        load_library().agx_concat_edges(
             e1[0].data_ptr(), e1[1].data_ptr(), int(e1.shape[1]), e2[0].data_ptr(), e2[1].data_ptr(), int(e2.shape[1]),
-            int(n_src_nodes or big), int(n_dst_nodes or big), byref(handle), byref(n_unique), current_stream(),
+            int(n_src_nodes or big), int(n_dst_nodes or big), buf.data_ptr(), byref(n_unique), current_stream(),
         )
     )
-    out = torch.empty((2, n_unique.value), dtype=torch.int32, device=e1.device)
-    check(lib.agx_concat_edges_finish(handle, out[0].data_ptr(), out[1].data_ptr(), current_stream()))
+    u = n_unique.value
+    out = buf[: 2 * u].view(2, u)
+    if n > 0 and u < 0.75 * n:  # many duplicates: do not keep the worst-case allocation alive behind a small result
+        out = out.clone()
     return out
 
 

@@ -173,14 +173,14 @@ void agx_set_output_maps(const int64_t* src_map /*DEV or NULL*/, const int64_t* 
 /* ---- merged edge lists --------------------------------------------------------------------------------
  * utils.concat_edges (utils.py:66-81: torch.unique(torch.cat([e1, e2], dim=1), dim=1)): the columns of two (2, E) int32
  * edge lists sorted lexicographically by (source, target), duplicates removed - what a second edge builder on the same
- * node pair does to the edge set (edges/builder.py:105-110).  _begin packs both lists into 64-bit keys, sorts them (radix
- * sort over the key bits the node counts can set) and returns the number of distinct columns (one read-back); the caller
- * allocates the (2, n_unique) result and _finish unpacks into its rows and releases the scratch (call it with NULL rows
- * to release only).  Peak extra memory: 16 bytes per input edge = twice the result.                             */
-int agx_concat_edges_begin(const int32_t* a_src /*DEV na*/, const int32_t* a_dst, int64_t na, const int32_t* b_src /*DEV nb*/,
-                           const int32_t* b_dst, int64_t nb, int64_t n_src_nodes, int64_t n_dst_nodes, void** handle,
-                           int64_t* n_unique /*HOST*/, void* stream);
-int agx_concat_edges_finish(void* handle, int32_t* out_src /*DEV n_unique*/, int32_t* out_dst /*DEV n_unique*/, void* stream);
+ * node pair does to the edge set (edges/builder.py:105-110).  Both lists are packed into 64-bit keys by one kernel,
+ * radix-sorted over the key bits the node counts can set, and the distinct keys unpacked into `out`: the caller's
+ * RESULT allocation of 2 * (na + nb) int32, which doubles as the sort's alternate buffer - so the scratch besides the
+ * result is one key buffer (8 bytes per input edge).  On return (one read-back) the first 2 * n_unique int32 of `out`
+ * are the (2, n_unique) result, row-major.                                                                       */
+int agx_concat_edges(const int32_t* a_src /*DEV na*/, const int32_t* a_dst, int64_t na, const int32_t* b_src /*DEV nb*/,
+                     const int32_t* b_dst, int64_t nb, int64_t n_src_nodes, int64_t n_dst_nodes,
+                     int32_t* out /*DEV 2*(na+nb), 8-byte aligned*/, int64_t* n_unique /*HOST*/, void* stream);
 
 /* ---- node ordering, device half ---------------------------------------------------------------------------
  * get_coordinates_ordering (generate/utils.py:15-33): the two (unstable, order-defining) argsorts stay numpy's on the

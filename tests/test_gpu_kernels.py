@@ -621,8 +621,9 @@ def test_concat_edges_kernel_matches_torch_unique_and_reference_order():
 
 def test_concat_edges_120m_edges_within_twice_the_output():
     """>= 100 M edges: two 60 M-edge lists over 6.6 M x 164 k nodes, 25 % of the second duplicating
-    the first.  Sorted, unique, the right count - and the scratch high-water mark stays within 2 x the result (+ CUB's
-    histogram scratch), where cat -> int64 -> torch.unique needs > 5 x."""
+    the first.  Sorted, unique, the right count - and the memory beyond the result (the kernel's scratch high-water mark
+    + the worst-case slack of the result allocation, which doubles as the sort's second buffer) stays well within 2 x the
+    result, where cat -> int64 -> torch.unique needs > 5 x."""
     from anemoi_graphs_b200.utils import concat_edges_device
 
     n_src, n_dst, m = 6_599_680, 163_842, 60_000_000
@@ -638,7 +639,8 @@ def test_concat_edges_120m_edges_within_twice_the_output():
     torch.cuda.synchronize()
     peak = _pool_high_water()
     out_bytes = out.numel() * 4
-    assert peak <= 2 * out_bytes * 1.10 + (64 << 20), (peak, out_bytes)
+    slack = out.untyped_storage().nbytes() - out_bytes  # the allocation is sized for "no duplicates"
+    assert peak + slack <= 1.5 * out_bytes + (64 << 20), (peak, slack, out_bytes)
     key = (out[0].to(torch.int64) << 32) | out[1].to(torch.int64)
     assert bool((key[1:] > key[:-1]).all())  # strictly ascending (src, dst): sorted and unique
     del key
