@@ -508,3 +508,41 @@ def test_reference_contract_edge_builder_plugin(golden):
     np.testing.assert_array_equal(ei[0], (3 * np.arange(500)) % 162)
     want = R.edge_length(hx, graph["data"].x.numpy(), ei, "unit-std")
     np.testing.assert_allclose(graph[("hidden", "to", "data")]["edge_length"].numpy(), want, rtol=ATTR_RTOL)
+
+
+def test_describe_a_graph_built_on_the_gpu(tmp_path, capsys, golden):
+    """N4 (describe.py:20-225) on the device: a graph built by GraphCreator.create, saved, described - the descriptor's
+    reductions run on the GPU; sizes, isolated-node counts and attribute statistics equal the reference's expressions
+    (``num_nodes - len(torch.unique(row))``, min / mean / max / std per attribute) evaluated with numpy."""
+    from anemoi_graphs_b200.create import GraphCreator
+    from anemoi_graphs_b200.describe import GraphDescriptor
+
+    g = golden("toy")
+    path = tmp_path / "graph.pt"
+    graph = GraphCreator(
+        {
+            "nodes": {"data": latlon_nodes(g["data_lat_deg"], g["data_lon_deg"]), "hidden": tri_nodes(2)},
+            "edges": [
+                edges("data", "hidden", [{"_target_": T + "edges.CutOffEdges", "cutoff_factor": 0.6}], attr_cfg("unit-std")),
+                edges("hidden", "data", [{"_target_": T + "edges.KNNEdges", "num_nearest_neighbours": 3}], attr_cfg("unit-max")),
+            ],
+        }
+    ).create(save_path=path)
+    d = GraphDescriptor(path)
+    assert d._device.type == "cuda"
+    want_size = sum(v.numel() * v.element_size() for s in list(graph.node_stores) + list(graph.edge_stores)
+                    for v in s.values() if isinstance(v, torch.Tensor))  # fmt: skip
+    assert d.total_size == want_size
+    for row in d.get_edge_summary():
+        src, dst, n_edges, iso_src, iso_dst, dim, names = row
+        ei = graph[(src, "to", dst)].edge_index.numpy()
+        assert n_edges == ei.shape[1] and dim == 3 and names == "edge_length(1D), edge_dirs(2D)"
+        assert iso_src == graph[src].num_nodes - np.unique(ei[0]).size
+        assert iso_dst == graph[dst].num_nodes - np.unique(ei[1]).size
+    assert {r[0]: r[1] for r in d.get_node_summary()} == {"data": 2000, "hidden": 162}
+    for kind, where, name, dtype, lo, mean, hi, std in d.get_attribute_table():
+        s, t = where.split("-->")
+        v = graph[(s, "to", t)][name].numpy().astype(np.float64)
+        np.testing.assert_allclose([lo, mean, hi, std], [v.min(), v.mean(), v.max(), v.std(ddof=1)], rtol=2e-5, atol=1e-6)
+    d.describe()
+    assert "Graph ready." in capsys.readouterr().out
