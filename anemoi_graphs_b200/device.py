@@ -463,6 +463,30 @@ last_trace: dict = {}  # host timestamps of the most recent provisional node set
 LAZY_NODE_ORDER = __import__("os").environ.get("AGX_LAZY_ORDER", "1") != "0"
 
 
+# The thread that runs the node-order sort is pinned to one CPU of the process's affinity set (the last one, minus the
+# local rank) when several ranks share the host: the scheduler then does not migrate it while the other ranks' threads
+# are busy (N = 2, O1280 -> res 7: 6.05 -> 5.73 ms/step; no effect on a single process, where it stays off).
+# AGX_PIN_SORT=0 / 1 forces it off / on.
+PIN_SORT_THREAD = __import__("os").environ.get("AGX_PIN_SORT", "auto")
+_sort_thread_pinned = False
+
+
+def _pin_sort_thread(follower: bool) -> None:
+    global _sort_thread_pinned
+    want = PIN_SORT_THREAD == "1" or (PIN_SORT_THREAD == "auto" and world()[1] > 1)
+    if not want or _sort_thread_pinned or follower:
+        return
+    import os
+
+    try:
+        cpus = sorted(os.sched_getaffinity(0))
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        os.sched_setaffinity(0, {cpus[-1 - (local % len(cpus))]})
+        _sort_thread_pinned = True
+    except (AttributeError, OSError):
+        pass
+
+
 def _pool():
     global _order_pool
     if _order_pool is None:
@@ -556,6 +580,7 @@ class Provisional:
             from ._cabi import check, load_library
 
             torch.cuda.set_device(dev)  # the device context is per thread
+            _pin_sort_thread(follower)
             self.trace["worker_start"] = time.perf_counter()
             copied.synchronize()  # the coordinates are on the host (and complete on the device)
             self.trace["coords_on_host"] = time.perf_counter()
