@@ -1066,9 +1066,28 @@ class ChunkedGather:
 
 
 # --------------------------------------------------------------------------------------------------
-# VMM push (opt-in, AGX_VMM_PUSH=1): the exchange over peer-mapped memory, by the copy engines
+# VMM push (default of the gathered mode on one node; AGX_VMM_PUSH=0 disables): the exchange over peer-mapped memory, by the copy engines
 # --------------------------------------------------------------------------------------------------
-VMM_PUSH = __import__("os").environ.get("AGX_VMM_PUSH", "0") == "1"
+def _vmm_push_default() -> bool:
+    """The peer-mapped exchange is the default of the GATHERED output mode wherever it can work: all ranks on one node
+    (file descriptors travel over Unix sockets) and the CUDA driver bindings importable - conditions that are the same
+    on every rank.  Measured at N = 4, 100 M queries (gathered mode): KNN-3 7.4 -> 5.7 ms, KNN-16 33.4 -> 22.8 ms,
+    cut-off 22.2 -> 14.3 ms, bit-identical graphs (tools/dist_check.py).  AGX_VMM_PUSH=0 / 1 forces it off / on."""
+    import importlib.util
+    import os
+
+    env = os.environ.get("AGX_VMM_PUSH", "auto")
+    if env in ("0", "1"):
+        return env == "1"
+    same_node = os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")) == os.environ.get("WORLD_SIZE", "1")
+    try:
+        have_driver = importlib.util.find_spec("cuda.bindings.driver") is not None
+    except (ImportError, ValueError):
+        have_driver = False
+    return same_node and have_driver
+
+
+VMM_PUSH = _vmm_push_default()
 
 
 class _VmmHeap:
@@ -1191,7 +1210,7 @@ class VmmGather:
     pushed into the same byte range of every peer's staging buffer (``_VmmHeap``) on a second stream while the main
     stream searches the next chunk; after one stream-ordered barrier each rank copies the other ranks' blocks from
     its own staging buffer into ``full``.  No SMs are used by the exchange, so - unlike an NCCL kernel - it runs
-    while the persistent search kernels occupy the whole GPU.  Opt-in (AGX_VMM_PUSH=1): validated at N = 2 only."""
+    while the persistent search kernels occupy the whole GPU.  Validated at N = 2 and N = 4 (bit-identical graphs)."""
 
     def __init__(self, full: torch.Tensor, counts: list[list[int]]) -> None:
         import torch.distributed as dist
@@ -1260,7 +1279,7 @@ class VmmGather:
 
 
 def make_gather(full: torch.Tensor, counts: list[list[int]]):
-    """The exchange object of a sharded edge set: ``VmmGather`` when opted in (AGX_VMM_PUSH=1), else ``ChunkedGather``."""
+    """The exchange object of a sharded edge set: ``VmmGather`` (``VMM_PUSH``), else ``ChunkedGather``."""
     if VMM_PUSH and full.is_cuda:
         return VmmGather(full, counts)
     return ChunkedGather(full, counts)
