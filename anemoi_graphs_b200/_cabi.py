@@ -108,6 +108,7 @@ SIGNATURES = {
         c_int,
         [c_void_p, c_int64, c_void_p, c_int, c_int, c_void_p, c_int64, c_double, c_void_p, c_void_p, c_void_p],
     ),
+    "agx_voronoi_areas_small": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_double, c_void_p, c_void_p, c_void_p]),
     "agx_healpix_nodes": (c_int, [c_int, c_void_p, c_void_p]),
     "agx_hex_num_cells": (c_int64, [c_int]),
     "agx_hex_cells": (c_int, [c_int, c_void_p, c_void_p, c_void_p]),

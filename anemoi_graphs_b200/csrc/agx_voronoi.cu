@@ -196,3 +196,103 @@ extern "C" int agx_voronoi_areas(const float* latlon, int64_t n, const int32_t* 
     agx_note_launch(1);
     return AGX_OK;
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// Very few generators (n <= VOR_SMALL_N): a cell can be wider than a hemisphere, which the gnomonic plane at its
+// generator cannot hold.  Exhaustive form on the sphere itself, one thread per generator: every pair of half-space
+// normals n_a = q_a - p, n_b = q_b - p meets in the two directions +-(n_a x n_b) / |.|; a direction is a vertex of the
+// cell iff it satisfies every other half-space.  The vertices are ordered by azimuth about p (the cell is star-shaped
+// about its generator: every half-space contains p) and the area is the same Van Oosterom - Strackee sum.  O(n^3) per
+// cell - a few hundred thousand operations at most.
+// ------------------------------------------------------------------------------------------------------------------
+#define VOR_SMALL_N 64
+#define VOR_SMALL_MAXV 128
+
+__global__ void __launch_bounds__(64) k_voronoi_areas_small(const float2* __restrict__ latlon, int n,
+                                                            const int32_t* __restrict__ subset, int m, double radius,
+                                                            double* __restrict__ areas, int32_t* __restrict__ status) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= m) return;
+    const int i = subset ? subset[t] : t;
+    const double3 p = vor_xyz(latlon[i]);
+    const double3 ph = scale3(p, 1.0 / sqrt(dot3(p, p)));
+    double3 axis = fabs(ph.x) <= fabs(ph.y) && fabs(ph.x) <= fabs(ph.z) ? make_double3(1, 0, 0)
+                   : (fabs(ph.y) <= fabs(ph.z) ? make_double3(0, 1, 0) : make_double3(0, 0, 1));
+    double3 e1 = cross3(ph, axis);
+    e1 = scale3(e1, 1.0 / sqrt(dot3(e1, e1)));
+    const double3 e2 = cross3(ph, e1);
+    double3 vtx[VOR_SMALL_MAXV];
+    double ang[VOR_SMALL_MAXV];
+    int nv = 0;
+    int st = VOR_OK;
+    for (int a = 0; a < n && st == VOR_OK; ++a) {
+        if (a == i) continue;
+        const double3 na = sub3(vor_xyz(latlon[a]), p);
+        if (dot3(na, na) == 0.0) { st = VOR_DUPLICATE; break; }
+        for (int b = a + 1; b < n && st == VOR_OK; ++b) {
+            if (b == i) continue;
+            const double3 nb = sub3(vor_xyz(latlon[b]), p);
+            double3 w = cross3(na, nb);
+            const double wn = sqrt(dot3(w, w));
+            if (wn <= 1e-14 * sqrt(dot3(na, na) * dot3(nb, nb))) continue;  // parallel bisector planes: no vertex
+            w = scale3(w, 1.0 / wn);
+            for (int sgn = 0; sgn < 2; ++sgn) {
+                const double3 v = sgn ? scale3(w, -1.0) : w;
+                bool inside = true;
+                for (int q = 0; q < n && inside; ++q) {
+                    if (q == i || q == a || q == b) continue;
+                    const double3 nq = sub3(vor_xyz(latlon[q]), p);
+                    inside = dot3(v, nq) <= 1e-13 * sqrt(dot3(nq, nq));
+                }
+                if (!inside) continue;
+                bool dup = false;  // three or more bisectors through one point: keep one copy
+                for (int e = 0; e < nv && !dup; ++e) {
+                    const double3 d = sub3(vtx[e], v);
+                    dup = dot3(d, d) < 1e-24;
+                }
+                if (dup) continue;
+                if (nv == VOR_SMALL_MAXV) { st = VOR_OVERFLOW; break; }
+                vtx[nv] = v;
+                ang[nv] = atan2(dot3(v, e2), dot3(v, e1));
+                ++nv;
+            }
+        }
+    }
+    if (st == VOR_OK && nv < 3) st = VOR_UNBOUNDED;  // fewer than 4 generators in general position
+    double area = 0.0;
+    if (st == VOR_OK) {
+        for (int x = 1; x < nv; ++x) {  // insertion sort by azimuth
+            const double3 kv = vtx[x];
+            const double ka = ang[x];
+            int y = x - 1;
+            while (y >= 0 && ang[y] > ka) {
+                vtx[y + 1] = vtx[y];
+                ang[y + 1] = ang[y];
+                --y;
+            }
+            vtx[y + 1] = kv;
+            ang[y + 1] = ka;
+        }
+        for (int x = 0; x < nv; ++x) {
+            const double3 v0 = vtx[x], v1 = vtx[(x + 1) % nv];
+            const double num = dot3(p, cross3(v0, v1));
+            const double den = 1.0 + dot3(p, v0) + dot3(v0, v1) + dot3(v1, p);
+            area += fabs(2.0 * atan2(num, den));
+        }
+        areas[i] = area * radius * radius;
+    }
+    status[t] = st;
+}
+
+extern "C" int agx_voronoi_areas_small(const float* latlon, int64_t n, const int32_t* subset, int64_t m, double radius,
+                                       double* areas, int32_t* status, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    AGX_REQUIRE(n >= 4 && n <= VOR_SMALL_N, AGX_ERR_ARG, "agx_voronoi_areas_small: 4 <= n <= 64 generators");
+    AGX_REQUIRE(m >= 0 && m <= n, AGX_ERR_ARG, "agx_voronoi_areas_small: bad subset size");
+    if (m == 0) return AGX_OK;
+    AGX_REQUIRE(latlon && areas && status, AGX_ERR_ARG, "agx_voronoi_areas_small: NULL buffer");
+    k_voronoi_areas_small<<<((int)m + 63) / 64, 64, 0, stream>>>((const float2*)latlon, (int)n, subset, (int)m, radius, areas, status);
+    AGX_LAUNCH_OK();
+    agx_note_launch(1);
+    return AGX_OK;
+}

@@ -874,6 +874,7 @@ def healpix_nodes(resolution: int, device=None) -> torch.Tensor:
 # ----------------------------------------------------------------------------------------------
 # spherical Voronoi cell areas
 # ----------------------------------------------------------------------------------------------
+VORONOI_SMALL_N = 64  # up to this many generators unclosed cells go through the exhaustive spherical form
 VORONOI_K = (17, 33, 64)  # neighbours tried in turn (self included): a regular grid's cells close within the first 16
 
 
@@ -914,6 +915,18 @@ def voronoi_areas(x: torch.Tensor, radius: float = 1.0) -> torch.Tensor:
             subset = retry if subset is None else subset[retry.long()]
             if k == n:
                 break
+    if n <= VORONOI_SMALL_N:
+        # a handful of generators: cells wider than a hemisphere do not fit the gnomonic plane - exhaustive form on the
+        # sphere (every pair of bisector planes), the reference's range from 4 generators up
+        m = int(subset.numel())
+        status = torch.empty(m, dtype=torch.int32, device=xd.device)
+        with _span("voronoi_areas_small", m):
+            check(lib.agx_voronoi_areas_small(ptr(xd), n, ptr(subset), m, float(radius), ptr(areas), ptr(status), stream))
+        worst = int(status.max().item())
+        if worst == 0:
+            return areas
+        if worst == 3:
+            raise ValueError("Duplicate generators present.")
     raise NotImplementedError(
         f"{int(subset.numel())} Voronoi cells are not closed by their {VORONOI_K[-1] - 1} nearest neighbours "
         "(fewer than ~8 generators per hemisphere, or an extremely anisotropic point set)"

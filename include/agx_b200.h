@@ -332,6 +332,11 @@ int agx_healpix_nodes(int resolution /*log2 nside*/, float* latlon /*DEV npix*2*
 int agx_voronoi_areas(const float* latlon /*DEV n*2*/, int64_t n, const int32_t* knn /*DEV m*k*/, int k, int exhaustive,
                       const int32_t* subset /*DEV m or NULL*/, int64_t m, double radius, double* areas /*DEV n*/,
                       int32_t* status /*DEV m*/, void* stream);
+/* The same for at most 64 generators, whose cells can be wider than a hemisphere (the reference works from 4 generators):
+ * exhaustive on the sphere - every pair of bisector planes, both meeting directions, kept iff inside every other
+ * half-space; vertices ordered by azimuth about the generator; the same solid-angle sum.  status as above.        */
+int agx_voronoi_areas_small(const float* latlon /*DEV n*2*/, int64_t n, const int32_t* subset /*DEV m or NULL*/, int64_t m,
+                            double radius, double* areas /*DEV n*/, int32_t* status /*DEV m*/, void* stream);
 
 #ifdef __cplusplus
 }

@@ -192,8 +192,7 @@ def test_area_weights_very_few_generators(n):
             continue
         if np.isfinite(want).all() and abs(want.sum() - 4 * np.pi) < 1e-6:
             break
-    try:
-        got = ops.voronoi_areas(torch.from_numpy(x).cuda()).cpu().numpy()
-    except NotImplementedError:
-        pytest.skip("a cell wider than the gnomonic hemisphere: documented limit (fewer than ~8 generators)")
+    # cells wider than the gnomonic hemisphere go through the exhaustive spherical form (agx_voronoi_areas_small)
+    got = ops.voronoi_areas(torch.from_numpy(x).cuda()).cpu().numpy()
     np.testing.assert_allclose(got, want, rtol=1e-9, atol=0)
+    np.testing.assert_allclose(got.sum(), 4 * np.pi, rtol=1e-8)
