@@ -1,5 +1,5 @@
 #!/bin/bash
-# usage: bash tools/gpu_r2_sweepN.sh N
+# usage: bash tools/gpu_round2/sweep_n.sh N
 N=$1
 mkdir -p gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2952$N"
