@@ -103,9 +103,10 @@ class Shard:
         return {"rank": self.rank, "world": self.world, "counts": [int(c) for c in self.counts], "replicated": self.replicated}
 
 
-def host_tensor(shape, dtype: torch.dtype) -> torch.Tensor:
+def host_tensor(shape, dtype: torch.dtype, require_shared: bool = False) -> torch.Tensor:
     """Page-locked host tensor for a result: from the node-wide shared arena in sharded output mode (same bytes on
-    every rank), else this process's own pinned memory."""
+    every rank), else this process's own pinned memory.  ``require_shared``: the caller will fill only THIS rank's part
+    (a sharded edge set) - without a common arena (ranks on several nodes) that cannot give a complete tensor."""
     if sharded_output():
         from . import shm
 
@@ -114,6 +115,11 @@ def host_tensor(shape, dtype: torch.dtype) -> torch.Tensor:
             global _shared_host_used
             _shared_host_used = True
             return arena.tensor(shape, dtype)
+        if require_shared:
+            raise NotImplementedError(
+                "sharded output with host-resident graphs needs all ranks on one node (a common /dev/shm); keep the graph "
+                "on the devices (device.set_resident(True)) or use the gathered output mode"
+            )
     return torch.empty(tuple(shape), dtype=dtype, pin_memory=True)
 
 
@@ -261,7 +267,7 @@ def to_host(t: torch.Tensor, shard: Shard | None = None, dim: int = 0) -> torch.
             full_shape[dim] = shard.total
             lo, hi = shard.offset, shard.offset + int(t.shape[dim])
             src = t
-        full = host_tensor(full_shape, t.dtype)
+        full = host_tensor(full_shape, t.dtype, require_shared=True)
         if hi > lo:
             dst = full.narrow(dim, lo, hi - lo)
             if dst.is_contiguous() and src.is_contiguous():
@@ -615,9 +621,11 @@ class Provisional:
                         group.sleep_until_woken()
                     else:
                         time.sleep(max(0.0, 0.8 * t_first - (time.perf_counter() - t_prev)))
-                        while int(stamps[i]) != prov_seq + 1:
+                        while int(stamps[i]) not in (prov_seq + 1, -(prov_seq + 1)):
                             time.sleep(0)
                         group.drain_wakeups()
+                    if int(stamps[i]) == -(prov_seq + 1):
+                        raise RuntimeError("the rank that sorts the node order failed; see its traceback")
                     shm._spin(lambda i=i: int(stamps[i]) == prov_seq + 1, f"part {i} of node order {prov_seq}")
                     t_prev = time.perf_counter()
                     if i == 0:
@@ -625,7 +633,14 @@ class Provisional:
                     emit(None)
                 out = (None, None)
             else:
-                out = sorter(cols[0], cols[1], emit)
+                try:
+                    out = sorter(cols[0], cols[1], emit)
+                except BaseException:
+                    if group is not None:  # do not leave the followers asleep: a negative stamp tells them to give up
+                        stamps[:] = -(prov_seq + 1)
+                        for _ in range(max_parts):
+                            group.wake_followers()
+                    raise
                 out = out if isinstance(out, tuple) else (out,)
             self.trace["sorted"] = time.perf_counter()
             if self.combine == "latlon" and len(out) == 2 and len(sent) == 2:
@@ -810,7 +825,7 @@ def edge_index_like_input(edge_dev: torch.Tensor, reference_input: torch.Tensor)
         out = torch.empty(edge_dev.shape, dtype=edge_dev.dtype, pin_memory=True)
         lo, hi, cols = 0, int(edge_dev.shape[1]), None
     else:
-        out = host_tensor((2, shard.total), edge_dev.dtype)
+        out = host_tensor((2, shard.total), edge_dev.dtype, require_shared=True)
         if shard.replicated:
             lo, hi = shard_range(int(edge_dev.shape[1]), shard.rank, shard.world)
             cols = (lo, hi)  # of the (complete) device tensor

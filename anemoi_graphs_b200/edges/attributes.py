@@ -206,7 +206,7 @@ def _deferred_attributes(prov, meta, edge_index, src, dst, lengths, dirs, host_s
             if shard is None:
                 host = dest = torch.empty(dev_out.shape, dtype=dev_out.dtype, pin_memory=True)
             else:  # the complete array in the shared host buffer; this rank fills its rows
-                host = _device.host_tensor((shard.total, int(dev_out.shape[1])), dev_out.dtype)
+                host = _device.host_tensor((shard.total, int(dev_out.shape[1])), dev_out.dtype, require_shared=True)
                 dest = host[shard.offset : shard.offset + int(dev_out.shape[0])]
             host_targets.append((dev_out, dest))
             results[name] = host

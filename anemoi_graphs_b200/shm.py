@@ -149,6 +149,8 @@ class HostArena:
     order; rank 0's bookkeeping decides, the log carries the decision."""
 
     def __init__(self, group: LocalGroup) -> None:
+        if not hasattr(torch._C, "_storage_Use_Count"):  # what tells rank 0 that a segment's tensors are gone
+            raise RuntimeError("shared host arena: this torch build has no torch._C._storage_Use_Count")
         self.group = group
         self.segments: dict[int, torch.Tensor] = {}  # id -> uint8 tensor over the whole segment
         self._capacity: dict[int, int] = {}
