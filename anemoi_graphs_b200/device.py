@@ -685,8 +685,9 @@ class Provisional:
         self.fixups.append(fn)
 
     def add_finalizer(self, fn) -> None:
-        """``fn(self)`` runs after the registered rows carry final labels and their host copies are enqueued (the
-        normalisation of attributes whose statistics waited for a re-decision, and their host copies)."""
+        """``fn(self)`` runs after every fixup, CONCURRENTLY with the relabel of the registered rows (which happens on a
+        side stream): it must not read index rows - it is the normalisation of attributes whose statistics waited for
+        a re-decision, and their host copies."""
         self.finalizers.append(fn)
 
     def resolve(self) -> None:
@@ -712,7 +713,6 @@ class Provisional:
             order_dev = self.combine(*[parts_dev[i] for i in range(int(parts_dev.shape[0]))]).contiguous()
             rank[order_dev] = torch.arange(self.n, dtype=torch.int64, device=dev)
             torch.index_select(self.x_prov, 0, order_dev, out=self.x_final)
-        copy_replicated_to_host(order_dev, self.order_host)  # ``_node_ordering``: complete at flush like every host copy
         self.order_dev = order_dev
         self.rank = rank
         fixups, self.fixups = self.fixups, []
@@ -722,14 +722,33 @@ class Provisional:
 
         for tensor, row, host_row, cols in self.rows:
             wait_for(tensor)  # a sharded builder's all-gather may still be filling it
-        ops.relabel_rows([tensor[row] for tensor, row, host_row, cols in self.rows], rank)  # one launch for all rows
+        # The relabel of every provisional row (one launch, gather-latency-bound: 30 % of the DRAM rate) runs on a side
+        # stream WHILE the finalizers - the HBM-bound scaling pass of the attributes whose statistics waited for the tie
+        # re-decision - run on the main stream: different data, and the fixups that still read provisional labels are
+        # all enqueued before this point.
+        main = torch.cuda.current_stream()
+        side = _order_stream(dev)
+        fixed = torch.cuda.Event()
+        fixed.record(main)
+        with torch.cuda.stream(side):
+            side.wait_event(fixed)
+            ops.relabel_rows([tensor[row] for tensor, row, host_row, cols in self.rows], rank)  # one launch for all rows
+            relabelled = torch.cuda.Event()
+            relabelled.record(side)
+        for tensor, row, host_row, cols in self.rows:
+            tensor.record_stream(side)
+        rank.record_stream(side)
+        finalizers, self.finalizers = self.finalizers, []
+        for fn in finalizers:
+            fn(self)
+        main.wait_event(relabelled)
         for tensor, row, host_row, cols in self.rows:
             if host_row is not None and host_row.numel():
                 to_host_into(tensor[row] if cols is None else tensor[row, cols[0] : cols[1]], host_row)
         self.rows = []
-        finalizers, self.finalizers = self.finalizers, []
-        for fn in finalizers:
-            fn(self)
+        # host copies that nothing on the device waits for go last: ``_node_ordering`` and (host-resident graphs) ``x``
+        # are complete at flush like every host copy
+        copy_replicated_to_host(order_dev, self.order_host)
         if self.x_host is not None:
             copy_replicated_to_host(self.x_final, self.x_host)
         if self.state is not None:
