@@ -28,6 +28,9 @@ import torch
 RING = 256  # entries of each sequence-numbered ring in the control block
 PAYLOAD = 16  # int64 words per entry and rank
 SEGMENT_ALIGN = 2 << 20
+# free space /dev/shm must offer before the ranks of a node share buffers through it (two generations of a large
+# graph's host tensors: 2 x 0.7 GB for O1280 -> res 7)
+MIN_SHM_FREE_BYTES = int(float(os.environ.get("AGX_MIN_SHM_FREE_BYTES", "4e9")))
 
 
 def _spin(ready, what: str, timeout_s: float = 120.0) -> None:
@@ -237,14 +240,17 @@ class HostArena:
 
 _group: LocalGroup | None = None
 _arena: HostArena | None = None
+_unavailable = False  # rank 0 found /dev/shm too small: remembered, so that the question is one collective, not many
 
 
 def local_group() -> LocalGroup | None:
     """The shared-memory group of this process group, or None (single rank, or ranks spread over several nodes).
     Created on first use - a collective: every rank must call it at the same point."""
-    global _group, _arena
+    global _group, _arena, _unavailable
     if _group is not None:
         return _group
+    if _unavailable:
+        return None
     import torch.distributed as dist
 
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
@@ -255,8 +261,20 @@ def local_group() -> LocalGroup | None:
         return None
     import secrets
 
-    token = [secrets.token_hex(8) if rank == 0 else None]
+    # rank 0 decides for everybody: a token, or None when /dev/shm cannot hold the result buffers (a container with the
+    # 64 MB default: touching pages beyond the limit would raise SIGBUS inside cudaHostRegister)
+    token = [None]
+    if rank == 0:
+        try:
+            st = os.statvfs("/dev/shm")
+            free = st.f_bavail * st.f_frsize
+        except OSError:
+            free = 0
+        token = [secrets.token_hex(8) if free >= MIN_SHM_FREE_BYTES else None]
     dist.broadcast_object_list(token, src=0)
+    if token[0] is None:
+        _unavailable = True
+        return None
     _group = LocalGroup(rank, world, token[0])
     _arena = HostArena(_group)
     _group.barrier()
@@ -269,5 +287,5 @@ def arena() -> HostArena | None:
 
 def reset() -> None:
     """Forget the group (tests that re-initialise torch.distributed)."""
-    global _group, _arena
-    _group, _arena = None, None
+    global _group, _arena, _unavailable
+    _group, _arena, _unavailable = None, None, False

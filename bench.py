@@ -227,9 +227,15 @@ def bench_b200(args) -> dict:
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    shared_host = True
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         agx_device.set_sharded_output(True)
+        from anemoi_graphs_b200 import shm
+
+        if shm.local_group() is None:  # ranks on several nodes, or a /dev/shm too small for the result buffers
+            shared_host = False
+            agx_device.set_sharded_output(False)
     if world != args.gpus and rank == 0:
         print(f"note: --gpus {args.gpus} but WORLD_SIZE={world}; using {world}", file=sys.stderr)
 
@@ -377,7 +383,10 @@ def bench_b200(args) -> dict:
         "dtype": "f32 filter + f64 decisions, int32 indices",
         "data": "synthetic",
         "config": workload_config(args.workload, n_data, n_hidden, sizes),
-        "sharding": sharding_note(world),
+        "sharding": sharding_note(world) if shared_host else (
+            f"{world} ranks, GATHERED output (every rank ends with the complete graph): no node-wide shared memory available "
+            "for the sharded host output (ranks on several nodes, or /dev/shm below AGX_MIN_SHM_FREE_BYTES)"
+        ),
         "e2e": {
             "value": round(e2e_value, 1),
             "unit": "edges/s",

@@ -99,6 +99,36 @@ def test_shared_memory_group_and_arena_world2():
     assert not left, f"shared-memory segments were not removed: {left}"
 
 
+def _worker_small_shm(rank: int, world: int, port: int) -> None:
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), LOCAL_WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from anemoi_graphs_b200 import device as D
+    from anemoi_graphs_b200 import shm
+
+    try:
+        if rank == 0:  # only rank 0 looks at /dev/shm; its answer reaches the others with the token broadcast
+            shm.MIN_SHM_FREE_BYTES = 1 << 62
+        assert shm.local_group() is None and shm.arena() is None
+        assert shm.local_group() is None  # remembered: no second collective
+        # a tensor that must be node-wide cannot be had, and says so
+        D.set_sharded_output(True)
+        try:
+            D.host_tensor((4,), torch.int32, require_shared=True)
+            raised = False
+        except NotImplementedError:
+            raised = True
+        assert raised
+    finally:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def test_too_small_dev_shm_is_detected_not_crashed_into():
+    """A container with the 64 MB default /dev/shm: writing result buffers there would end in SIGBUS. Rank 0 checks the
+    free space; every rank learns that there is no node-wide group (bench.py then stays in gathered mode)."""
+    mp.spawn(_worker_small_shm, args=(2, _free_port()), nprocs=2, join=True)
+
+
 def test_shard_bookkeeping():
     from anemoi_graphs_b200.device import Shard
 
