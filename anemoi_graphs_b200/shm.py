@@ -9,7 +9,8 @@ This module is that plumbing, and nothing in it touches a GPU except the registr
   (edge counts of uneven shards), a one-directional publish log (rank 0 decides, the others follow), a barrier;
 * ``HostArena``   - shared, page-locked host buffers.  Rank 0 decides which segment backs a request (it alone tracks
   which segments are still referenced by tensors of an earlier build) and publishes the decision; the other ranks
-  map the same segment.  Segments are reused from build to build like a caching allocator's blocks;
+  map the same segment.  Segments are reused from build to build like a caching allocator's blocks.  Every name in
+  ``/dev/shm`` is removed as soon as all ranks hold the object open, so a job that is killed leaves nothing behind;
 * the same arena carries the node order of a provisionally numbered node set from the rank that sorts to the ranks
   that wait (``device.Provisional``): one host sort per node instead of one per GPU.
 
@@ -167,7 +168,7 @@ class HostArena:
     def _path(self, seg_id: int) -> str:
         return f"/dev/shm/agx_{self.group.token}_seg{seg_id}"
 
-    def _unlink_all(self) -> None:
+    def _unlink_all(self) -> None:  # only what a failed rendezvous left behind: names go away as soon as all ranks mapped
         for seg_id in list(self._capacity):
             try:
                 os.unlink(self._path(seg_id))
@@ -178,14 +179,19 @@ class HostArena:
     def _use_count(t: torch.Tensor) -> int:
         return int(torch._C._storage_Use_Count(t.untyped_storage()._cdata))
 
+    def _create(self, seg_id: int, capacity: int) -> None:
+        """Rank 0: the file behind a new segment (sized, not yet mapped)."""
+        fd = os.open(self._path(seg_id), os.O_CREAT | os.O_RDWR | os.O_TRUNC, 0o600)
+        os.ftruncate(fd, capacity)
+        os.close(fd)
+        self._capacity[seg_id] = capacity
+
     def _map(self, seg_id: int, capacity: int) -> torch.Tensor:
+        """Map (and page-lock) a segment in this process; a NEW segment is a rendezvous: once every rank has mapped it
+        rank 0 removes its name, so that nothing is left in /dev/shm however the job ends."""
         if seg_id in self.segments:
             return self.segments[seg_id]
         path = self._path(seg_id)
-        if self.group.rank == 0:
-            fd = os.open(path, os.O_CREAT | os.O_RDWR | os.O_TRUNC, 0o600)
-            os.ftruncate(fd, capacity)
-            os.close(fd)
         seg = torch.from_file(path, shared=True, size=capacity, dtype=torch.uint8)
         if torch.cuda.is_available():
             # page-lock the mapping in THIS process so the copy engines can reach it (what NCCL's shm transport does)
@@ -196,6 +202,12 @@ class HostArena:
         self.segments[seg_id] = seg
         self._capacity[seg_id] = capacity
         self._baseline[seg_id] = self._use_count(seg)
+        self.group.barrier()
+        if self.group.rank == 0:
+            try:
+                os.unlink(path)
+            except OSError:
+                pass
         return seg
 
     def _is_free(self, seg_id: int) -> bool:
@@ -215,11 +227,12 @@ class HostArena:
                 pick = self._next_id
                 self._next_id += 1
                 cap = (nbytes + SEGMENT_ALIGN - 1) // SEGMENT_ALIGN * SEGMENT_ALIGN
-                self._map(pick, cap)  # created before it is announced
+                self._create(pick, cap)  # the file exists before it is announced; all ranks map and page-lock it together
             seg_id, cap = self.group.publish([pick, self._capacity[pick], nbytes])[:2]
         else:
             seg_id, cap, want = self.group.publish([])[:3]
             if want != nbytes:
+                self._map(seg_id, cap)  # keep the rendezvous of a new segment: rank 0 must not hang on this rank's error
                 raise RuntimeError(f"shared arena: rank {self.group.rank} asks for {nbytes} bytes where rank 0 asked for {want}")
         return self._map(seg_id, cap)[:nbytes]
 
@@ -278,6 +291,8 @@ def local_group() -> LocalGroup | None:
     _group = LocalGroup(rank, world, token[0])
     _arena = HostArena(_group)
     _group.barrier()
+    if rank == 0:  # every rank holds the control block and its FIFO open: the names can go
+        _group._unlink()
     return _group
 
 

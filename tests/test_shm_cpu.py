@@ -57,6 +57,8 @@ def _worker(rank: int, world: int, port: int) -> None:
         shard = D.Shard(rank, world, counts)
         full = arena.tensor((2, shard.total), torch.int32)
         assert full.shape == (2, 7) and full.is_shared()
+        # names live only until every rank has mapped them: a job that is killed leaves nothing in /dev/shm
+        assert not [f for f in os.listdir("/dev/shm") if f.startswith(f"agx_{group.token}")]
         block = torch.full((2, counts[rank]), rank + 1, dtype=torch.int32)
         full[:, shard.offset : shard.offset + counts[rank]] = block  # every rank writes only its own columns
         group.barrier()
