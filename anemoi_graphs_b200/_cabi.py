@@ -14,7 +14,7 @@ import torch
 
 LIB_PATH = Path(__file__).resolve().parent / "lib" / "libagx_b200.so"
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 AGX_OK = 0
 AGX_ERR_CUDA = -1
 AGX_ERR_ARG = -2
@@ -58,6 +58,9 @@ SIGNATURES = {
     "agx_max_positive": (c_int, [c_void_p, c_int64, POINTER(c_double), POINTER(c_int64), c_void_p]),
     "agx_host_reference_rdist": (c_int, [c_void_p, c_void_p, c_int64, c_int, POINTER(c_double)]),
     "agx_order_resolve": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "agx_gate_supported": (c_int, []),
+    "agx_gate_wait": (c_int, [c_void_p, c_void_p]),
+    "agx_gate_open": (c_int, [c_void_p, c_void_p]),
     "agx_mark_nodes": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
     "agx_relabel_nodes": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "agx_set_output_maps": (None, [c_void_p, c_void_p]),

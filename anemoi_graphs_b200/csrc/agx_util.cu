@@ -60,6 +60,64 @@ int agx_readback(void* host_dst, const void* dev_src, int words, cudaStream_t st
     return AGX_OK;
 }
 
+// Stream gates (agx_b200.h): work queued behind agx_gate_wait starts when the gate word - 4 bytes of page-locked host
+// memory - becomes 1, either through agx_gate_open queued on ANOTHER stream (ordered behind that stream's work) or
+// through a plain store by the CPU.  Driver stream memory operations (cuStreamWaitValue32 / cuStreamWriteValue32),
+// looked up through the runtime so that the library does not link libcuda: no SM is held while waiting.
+#include <cuda.h>
+typedef CUresult (*agx_memop32_fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+
+static int agx_memop(const char* symbol, agx_memop32_fn* out) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult found = cudaDriverEntryPointSymbolNotFound;
+    AGX_CUDA_OK(cudaGetDriverEntryPoint(symbol, &fn, cudaEnableDefault, &found));
+    AGX_REQUIRE(found == cudaDriverEntryPointSuccess && fn, AGX_ERR_CUDA, "%s is not available in this driver", symbol);
+    *out = (agx_memop32_fn)fn;
+    return AGX_OK;
+}
+
+static int agx_gate_device_pointer(const void* gate, CUdeviceptr* out) {
+    AGX_REQUIRE(gate && ((uintptr_t)gate & 3) == 0, AGX_ERR_ARG, "stream gate: NULL or unaligned word");
+    void* dev_view = nullptr;
+    AGX_CUDA_OK(cudaHostGetDevicePointer(&dev_view, const_cast<void*>(gate), 0));  // fails for pageable memory
+    *out = (CUdeviceptr)(uintptr_t)dev_view;
+    return AGX_OK;
+}
+
+extern "C" int agx_gate_supported(void) {
+    // CUDA 12 drivers enable the (v2) stream memory operations on every device they support
+    agx_memop32_fn wait_value = nullptr, write_value = nullptr;
+    return agx_memop("cuStreamWaitValue32", &wait_value) == AGX_OK && agx_memop("cuStreamWriteValue32", &write_value) == AGX_OK;
+}
+
+extern "C" int agx_gate_wait(const uint32_t* gate, void* stream) {
+    static agx_memop32_fn wait_value = nullptr;
+    if (!wait_value) {
+        int rc = agx_memop("cuStreamWaitValue32", &wait_value);
+        if (rc) return rc;
+    }
+    CUdeviceptr addr;
+    int rc = agx_gate_device_pointer(gate, &addr);
+    if (rc) return rc;
+    CUresult res = wait_value((CUstream)stream, addr, 1u, CU_STREAM_WAIT_VALUE_EQ);
+    AGX_REQUIRE(res == CUDA_SUCCESS, AGX_ERR_CUDA, "cuStreamWaitValue32 failed: CUresult %d", (int)res);
+    return AGX_OK;
+}
+
+extern "C" int agx_gate_open(uint32_t* gate, void* stream) {
+    static agx_memop32_fn write_value = nullptr;
+    if (!write_value) {
+        int rc = agx_memop("cuStreamWriteValue32", &write_value);
+        if (rc) return rc;
+    }
+    CUdeviceptr addr;
+    int rc = agx_gate_device_pointer(gate, &addr);
+    if (rc) return rc;
+    CUresult res = write_value((CUstream)stream, addr, 1u, CU_STREAM_WRITE_VALUE_DEFAULT);
+    AGX_REQUIRE(res == CUDA_SUCCESS, AGX_ERR_CUDA, "cuStreamWriteValue32 failed: CUresult %d", (int)res);
+    return AGX_OK;
+}
+
 // Query-order decision of the tile kernels (agx_tile.cuh agx_query_order): a caller that searches ONE query set in
 // several chunks lets the first call decide (sampling costs a stream synchronisation) and pins that decision for the
 // remaining chunks, so that the host can run ahead of the device.

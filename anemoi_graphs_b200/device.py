@@ -509,6 +509,31 @@ def _upload_helper():
     return _upload_pool
 
 
+# Everything that follows the node order (upload of the index arrays, agx_order_resolve, tie re-decision, relabel,
+# scaling pass, device -> host copies) is queued on the main stream BEFORE the sort has ended, behind stream gates
+# (agx_gate_wait) that the sorting thread opens with a plain store the moment an index array lies in page-locked host
+# memory: the host's launch work (0.25 ms) leaves the critical path.  Only the CPU opens a gate and the sorting thread
+# needs no GPU after its coordinates have arrived, so a waiting stream can never wait for work queued behind itself.
+PRELAUNCH_TAIL = os.environ.get("AGX_PRELAUNCH_TAIL", "0") == "1"
+_gate_ring = None
+_gate_next = 0
+GATE_RING = 256
+
+
+def _new_gates(count: int) -> torch.Tensor:
+    """``count`` consecutive closed gates (int32 words of page-locked host memory, from a ring that outlives every build)."""
+    global _gate_ring, _gate_next
+    if _gate_ring is None:
+        _gate_ring = torch.zeros(GATE_RING, dtype=torch.int32, pin_memory=True)
+    if _gate_next % GATE_RING + count > GATE_RING:
+        _gate_next += GATE_RING - _gate_next % GATE_RING
+    lo = _gate_next % GATE_RING
+    _gate_next += count
+    gates = _gate_ring[lo : lo + count]
+    gates.zero_()
+    return gates
+
+
 def _pool():
     global _order_pool
     if _order_pool is None:
@@ -597,6 +622,14 @@ class Provisional:
         ostream = _order_stream(dev)
         for t in (parts_dev, self.order_dev, self.rank, self.x_final, self.x_prov):
             t.record_stream(ostream)
+        import threading
+
+        gates = None
+        if PRELAUNCH_TAIL and combine == "latlon" and _cabi.load_library().agx_gate_supported():
+            gates = _new_gates(max_parts)
+        gates_np = gates.numpy() if gates is not None else None
+        self._gates, self._parts_pinned, self._parts_dev, self._group = gates, parts_pinned, parts_dev, group
+        self._coords_ready = threading.Event()  # the worker needs nothing from the GPU any more
 
         def work():
             from ._cabi import check, load_library
@@ -605,6 +638,7 @@ class Provisional:
             _pin_sort_thread(follower)
             self.trace["worker_start"] = time.perf_counter()
             copied.synchronize()  # the coordinates are on the host (and complete on the device)
+            self._coords_ready.set()
             self.trace["coords_on_host"] = time.perf_counter()
             cols = staged.numpy()
             sent = []
@@ -615,6 +649,9 @@ class Provisional:
                     if group is not None:
                         stamps[i] = prov_seq + 1  # the followers may read part i now ...
                         group.wake_followers()  # ... and are asleep in read(2): one byte each
+                if gates_np is not None:
+                    gates_np[i] = 1  # the main stream's queued upload of part i may start (x86: stores stay in order)
+                    return
                 with torch.cuda.stream(ostream):
                     parts_dev[i].copy_(parts_pinned[i], non_blocking=True)
 
@@ -671,6 +708,10 @@ class Provisional:
                     raise
                 out = out if isinstance(out, tuple) else (out,)
             self.trace["sorted"] = time.perf_counter()
+            if gates_np is not None:
+                if len(sent) != max_parts:
+                    raise RuntimeError(f"node order: the sorter emitted {len(sent)} index arrays, {max_parts} were queued for")
+                return None  # the upload and agx_order_resolve are (being) queued by resolve() behind the gates
             if self.combine == "latlon" and len(out) == 2 and len(sent) == 2:
                 # order, its inverse and the re-ordered coordinates in one kernel, launched from here
                 check(
@@ -689,7 +730,21 @@ class Provisional:
             assert not follower, "a shared node order needs the 'latlon' combine"
             return out
 
-        self.future = _pool().submit(work)
+        def guarded():
+            try:
+                return work()
+            except BaseException:
+                # never leave the device waiting for index arrays that will not come: valid (identity) arrays, gates open;
+                # resolve() re-raises this failure
+                self._coords_ready.set()
+                if gates_np is not None:
+                    import numpy as np
+
+                    parts_pinned.numpy()[:] = np.arange(n, dtype=np.int64)
+                    gates_np[:] = 1
+                raise
+
+        self.future = _pool().submit(guarded)
         _provisionals.append(self)
 
     def __getstate__(self):  # never pickled with its worker future / pinned buffers
@@ -727,11 +782,36 @@ class Provisional:
         import time
 
         self.trace["resolve_enter"] = time.perf_counter()
-        parts = self.future.result()  # None: the worker has launched the resolve kernel itself
-        self.trace["resolve_got_order"] = time.perf_counter()
         dev = self.x_prov.device
         order_dev, rank = self.order_dev, self.rank
-        if parts is None:
+        gated = self._gates is not None
+        if gated:
+            from ._cabi import check, load_library
+
+            lib = load_library()
+            self._coords_ready.wait()  # from here on only the CPU stands between the device and an open gate
+            main = torch.cuda.current_stream()
+            for i in range(int(self._gates.numel())):
+                check(lib.agx_gate_wait(self._gates.data_ptr() + 4 * i, main.cuda_stream))
+                self._parts_dev[i].copy_(self._parts_pinned[i], non_blocking=True)
+            if self._group is not None:
+                uploaded = torch.cuda.Event()
+                uploaded.record(main)
+                _pending.append(uploaded)  # awaited before the end-of-build barrier: the shared arrays have been read
+            check(
+                lib.agx_order_resolve(
+                    self._parts_dev[0].data_ptr(), self._parts_dev[1].data_ptr(), self.n, self.x_prov.data_ptr(),
+                    self.x_final.data_ptr(), order_dev.data_ptr(), rank.data_ptr(), main.cuda_stream,
+                )
+            )
+            self.trace["order_launched"] = time.perf_counter()
+            parts = None
+        else:
+            parts = self.future.result()  # None: the worker has launched the resolve kernel itself
+            self.trace["resolve_got_order"] = time.perf_counter()
+        if gated:
+            pass
+        elif parts is None:
             torch.cuda.current_stream().wait_event(self._order_ready)
         else:
             staged = torch.empty((len(parts), self.n), dtype=torch.int64, pin_memory=True)
@@ -779,6 +859,10 @@ class Provisional:
         copy_replicated_to_host(order_dev, self.order_host)
         if self.x_host is not None:
             copy_replicated_to_host(self.x_final, self.x_host)
+        if gated:
+            self.trace["tail_queued"] = time.perf_counter()
+            self.future.result()  # the sort (a failure surfaces here; its handler has opened the gates)
+            self.trace["resolve_got_order"] = time.perf_counter()
         if self.state is not None:
             st = self.state
             st.prov = None

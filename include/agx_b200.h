@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define AGX_ABI_VERSION 2
+#define AGX_ABI_VERSION 3
 
 #define AGX_OK 0
 #define AGX_ERR_CUDA -1      /* CUDA runtime / launch failure (includes "no device") */
@@ -190,6 +190,19 @@ int agx_concat_edges(const int32_t* a_src /*DEV na*/, const int32_t* a_dst, int6
 int agx_order_resolve(const int64_t* index_latitude /*DEV n*/, const int64_t* index_longitude /*DEV n*/, int64_t n,
                       const float* x_in /*DEV n*2*/, float* x_out /*DEV n*2*/, int64_t* order /*DEV n*/,
                       int64_t* rank /*DEV n*/, void* stream);
+
+/* ---- stream gates -------------------------------------------------------------------------------------------
+ * What lets the host queue the work that FOLLOWS the node order (tie re-decision, relabel, scaling, device -> host
+ * copies) while numpy is still sorting (generate/utils.py:15-33 is host code in the reference and stays host code
+ * here): everything queued on `stream` behind agx_gate_wait starts when *gate == 1.  `gate` is one 32-bit word of
+ * page-locked HOST memory (cudaHostAlloc / cudaHostRegister), 0 when the wait is queued.  It is opened by
+ * agx_gate_open queued on another stream (behind the upload of the order and agx_order_resolve) or, when the sorting
+ * thread failed, by a plain CPU store of 1 so that the device never waits for a result that will not come.
+ * Implemented with cuStreamWaitValue32 / cuStreamWriteValue32: no SM is occupied while waiting.
+ * agx_gate_supported: 1 if the driver offers both operations.                                                  */
+int agx_gate_supported(void);
+int agx_gate_wait(const uint32_t* gate /*HOST page-locked*/, void* stream);
+int agx_gate_open(uint32_t* gate /*HOST page-locked*/, void* stream);
 
 /* ---- edge attributes ------------------------------------------------------------------------------
  * agx_node_tables: everything the attribute kernel needs from ONE node, as one 32-byte record per role:

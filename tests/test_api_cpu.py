@@ -127,7 +127,7 @@ def test_cabi_exports_every_declared_symbol():
     lib = _cabi.load_library()
     for name in declared:
         assert isinstance(getattr(lib, name), ctypes._CFuncPtr)
-    assert lib.agx_abi_version() == _cabi.ABI_VERSION == 2
+    assert lib.agx_abi_version() == _cabi.ABI_VERSION == 3
     assert lib.agx_edge_attrs_workspace() > 16
     assert lib.agx_multiscale_scratch_per_node(8, 1) == 9 * 7
 

@@ -376,13 +376,44 @@ def test_remove_unconnected_nodes_random_graph_matches_reference_algorithm(resid
     assert graph["b"].num_nodes == n_b
 
 
+def test_failed_node_order_sort_opens_the_gates_and_is_reported(monkeypatch):
+    """Pre-launched tail: the device waits behind stream gates for index arrays the host is sorting.  A sort that fails
+    must not leave it waiting: the gates open over valid (identity) arrays and the failure is raised by the build."""
+    from anemoi_graphs_b200 import device as agx_device
+    from anemoi_graphs_b200.create import GraphCreator
+    from anemoi_graphs_b200.generate import tri_icosahedron
+    from anemoi_graphs_b200.graph import HeteroData
+
+    def broken_sort(lat, lon, emit=None):
+        raise FloatingPointError("sort failed on purpose")
+
+    monkeypatch.setattr(agx_device, "PRELAUNCH_TAIL", True)
+    monkeypatch.setattr(tri_icosahedron, "_sort_columns_host", broken_sort)
+    recipe = {
+        "nodes": {"hidden": tri_nodes(3)},
+        "edges": [edges("hidden", "hidden", [{"_target_": T + "edges.MultiScaleEdges", "x_hops": 1}], attr_cfg("unit-max"))],
+    }
+    prev = agx_device.set_resident(True)
+    try:
+        with pytest.raises(FloatingPointError):
+            GraphCreator(recipe).update_graph(HeteroData())
+        torch.cuda.synchronize()  # returns: nothing is left waiting on the device
+    finally:
+        agx_device.set_resident(prev)
+        agx_device.flush()
+
+
 # ------------------------------------------------------------------------------------------------
 # provisional node numbering (device.Provisional): building while the node order is still being sorted must give
 # the same graph as sorting first
 # ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("prelaunch", [False, True])
 @pytest.mark.parametrize("resident", [False, True])
-def test_provisional_numbering_gives_the_same_graph(golden, resident):
+def test_provisional_numbering_gives_the_same_graph(golden, resident, prelaunch, monkeypatch):
     from anemoi_graphs_b200 import device as agx_device
+
+    # prelaunch: everything behind the node order is queued behind stream gates before the sort has ended
+    monkeypatch.setattr(agx_device, "PRELAUNCH_TAIL", prelaunch)
     from anemoi_graphs_b200.create import GraphCreator
     from anemoi_graphs_b200.graph import HeteroData
 
