@@ -495,9 +495,10 @@ def _pin_sort_thread(follower: bool) -> None:
 
 
 _upload_pool = None
-# the sorting thread hands every index array but the last to a helper thread for its pinned copy + upload
-# (AGX_UPLOAD_HANDOVER=0: the sorting thread does it itself, between the sorts)
-UPLOAD_HANDOVER = os.environ.get("AGX_UPLOAD_HANDOVER", "1") != "0"
+# AGX_UPLOAD_HANDOVER=1: the sorting thread hands every index array but the last to a helper thread for its pinned copy
+# + upload.  Measured (tools/tail_ab.py): the 0.15 ms leave the sorting thread, the step does not get shorter
+# (5.22 / 5.24 ms, host-resident 14.2 / 14.3 ms: the helper competes with the main thread's launches) - off by default.
+UPLOAD_HANDOVER = os.environ.get("AGX_UPLOAD_HANDOVER", "0") == "1"
 
 
 def _upload_helper():
@@ -514,7 +515,17 @@ def _upload_helper():
 # (agx_gate_wait) that the sorting thread opens with a plain store the moment an index array lies in page-locked host
 # memory: the host's launch work (0.25 ms) leaves the critical path.  Only the CPU opens a gate and the sorting thread
 # needs no GPU after its coordinates have arrived, so a waiting stream can never wait for work queued behind itself.
-PRELAUNCH_TAIL = os.environ.get("AGX_PRELAUNCH_TAIL", "0") == "1"
+# Measured on B200 (tools/tail_ab.py, modes interleaved in one process, O1280 -> res 7): device-resident build
+# 5.22 -> 5.05 ms per step; host-resident build 14.2 -> 14.45 ms (the build is bound by the device -> host DMA queue there
+# and the early queueing disturbs it).  "auto": on for device-resident graphs only; "1" / "0": always / never.
+PRELAUNCH_TAIL = os.environ.get("AGX_PRELAUNCH_TAIL", "auto")
+
+
+def _prelaunch_wanted() -> bool:
+    mode = PRELAUNCH_TAIL
+    if isinstance(mode, bool):
+        return mode
+    return mode == "1" or (mode == "auto" and _resident)
 _gate_ring = None
 _gate_next = 0
 GATE_RING = 256
@@ -625,7 +636,7 @@ class Provisional:
         import threading
 
         gates = None
-        if PRELAUNCH_TAIL and combine == "latlon" and _cabi.load_library().agx_gate_supported():
+        if _prelaunch_wanted() and combine == "latlon" and _cabi.load_library().agx_gate_supported():
             gates = _new_gates(max_parts)
         gates_np = gates.numpy() if gates is not None else None
         self._gates, self._parts_pinned, self._parts_dev, self._group = gates, parts_pinned, parts_dev, group
