@@ -84,10 +84,32 @@ static int agx_gate_device_pointer(const void* gate, CUdeviceptr* out) {
     return AGX_OK;
 }
 
+extern "C" int agx_gate_wait(const uint32_t* gate, void* stream);
+extern "C" int agx_gate_open(uint32_t* gate, void* stream);
+
+// One functional self-test per device, remembered: a write through a stream opens a gate, a wait behind it passes.
+// (CUDA 12 drivers enable the stream memory operations everywhere they run; a virtualised or restricted device that
+// refuses them makes the callers keep their un-gated path instead of failing a build.)
 extern "C" int agx_gate_supported(void) {
-    // CUDA 12 drivers enable the (v2) stream memory operations on every device they support
-    agx_memop32_fn wait_value = nullptr, write_value = nullptr;
-    return agx_memop("cuStreamWaitValue32", &wait_value) == AGX_OK && agx_memop("cuStreamWriteValue32", &write_value) == AGX_OK;
+    static std::atomic<int> verdict[32];  // 0 unknown, 1 yes, 2 no
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 32) return 0;
+    int known = verdict[dev].load(std::memory_order_relaxed);
+    if (known) return known == 1;
+    int ok = 0;
+    uint32_t* word = nullptr;
+    cudaStream_t probe = nullptr;
+    if (cudaHostAlloc((void**)&word, sizeof(uint32_t), cudaHostAllocMapped | cudaHostAllocPortable) == cudaSuccess &&
+        cudaStreamCreateWithFlags(&probe, cudaStreamNonBlocking) == cudaSuccess) {
+        *word = 0;
+        ok = agx_gate_open(word, probe) == AGX_OK && agx_gate_wait(word, probe) == AGX_OK &&
+             cudaStreamSynchronize(probe) == cudaSuccess && *(volatile uint32_t*)word == 1u;
+    }
+    if (probe) cudaStreamDestroy(probe);
+    if (word) cudaFreeHost(word);
+    cudaGetLastError();  // a refused operation must not linger as this thread's last error
+    verdict[dev].store(ok ? 1 : 2, std::memory_order_relaxed);
+    return ok;
 }
 
 extern "C" int agx_gate_wait(const uint32_t* gate, void* stream) {

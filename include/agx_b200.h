@@ -199,7 +199,8 @@ int agx_order_resolve(const int64_t* index_latitude /*DEV n*/, const int64_t* in
  * agx_gate_open queued on another stream (behind the upload of the order and agx_order_resolve) or, when the sorting
  * thread failed, by a plain CPU store of 1 so that the device never waits for a result that will not come.
  * Implemented with cuStreamWaitValue32 / cuStreamWriteValue32: no SM is occupied while waiting.
- * agx_gate_supported: 1 if the driver offers both operations.                                                  */
+ * agx_gate_supported: 1 if both operations work on the current device (one functional self-test per device,
+ * remembered); callers keep their un-gated path otherwise.                                                      */
 int agx_gate_supported(void);
 int agx_gate_wait(const uint32_t* gate /*HOST page-locked*/, void* stream);
 int agx_gate_open(uint32_t* gate /*HOST page-locked*/, void* stream);
