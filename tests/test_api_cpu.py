@@ -316,3 +316,19 @@ def test_recipe_is_validated_up_front():
     ok["edges"][0]["edge_builders"][0]["num_nearest_neighbours"] = 65
     with pytest.raises(NotImplementedError, match="65 > 64"):
         GraphCreator(ok)
+
+
+def test_prelaunch_mode_rule(monkeypatch):
+    """AGX_PRELAUNCH_TAIL: "auto" queues the post-sort work behind stream gates for device-resident graphs only (the
+    measured rule); "1" / "0" (or a bool set by a test) force it."""
+    from anemoi_graphs_b200 import device as D
+
+    prev = D.set_resident(False)
+    try:
+        for mode, resident, want in (("auto", False, False), ("auto", True, True), ("1", False, True), ("0", True, False),
+                                     (True, False, True), (False, True, False)):  # fmt: skip
+            monkeypatch.setattr(D, "PRELAUNCH_TAIL", mode)
+            D.set_resident(resident)
+            assert D._prelaunch_wanted() is want, (mode, resident)
+    finally:
+        D.set_resident(prev)
