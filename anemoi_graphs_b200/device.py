@@ -526,6 +526,8 @@ def _prelaunch_wanted() -> bool:
     if isinstance(mode, bool):
         return mode
     return mode == "1" or (mode == "auto" and _resident)
+
+
 _gate_ring = None
 _gate_next = 0
 GATE_RING = 256
@@ -816,12 +818,11 @@ class Provisional:
                 )
             )
             self.trace["order_launched"] = time.perf_counter()
-            parts = None
         else:
             parts = self.future.result()  # None: the worker has launched the resolve kernel itself
             self.trace["resolve_got_order"] = time.perf_counter()
         if gated:
-            pass
+            pass  # order / rank / x_final are produced in stream order by what was just queued
         elif parts is None:
             torch.cuda.current_stream().wait_event(self._order_ready)
         else:
