@@ -91,6 +91,11 @@ class GraphCreator:
     def update_graph(self, graph):
         """Instantiate the node and edge builders of the recipe and apply them to the graph (create.py:62-92)."""
         with _device.deferred():
+            # host coordinates of node sets the graph arrives with start their way to the device before anything else
+            named = {n for e in self.config.get("edges", {}) for n in (e.get("source_name"), e.get("target_name"))}
+            for name in named:
+                if name in graph.node_types and name not in self.config.get("nodes", {}):
+                    _device.prefetch_coordinates(graph[name])
             for nodes_name, nodes_cfg in self.config.get("nodes", {}).items():
                 node_builder = instantiate(nodes_cfg.node_builder, name=nodes_name)
                 _device.flush_for(node_builder)  # a foreign (reference-style) plugin reads complete host tensors

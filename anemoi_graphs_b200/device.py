@@ -278,20 +278,7 @@ def to_host(t: torch.Tensor, shard: Shard | None = None, dim: int = 0) -> torch.
                 for r in range(int(t.shape[0])):
                     to_host_into(src[r], dst[r])
         return full
-    out = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
-    if t.numel() == 0:
-        return out
-    ready = torch.cuda.Event()
-    ready.record()
-    side = _copy_stream(t.device)
-    with torch.cuda.stream(side):
-        side.wait_event(ready)
-        out.copy_(t, non_blocking=True)
-        done = torch.cuda.Event()
-        done.record(side)
-    t.record_stream(side)
-    _pending.append(done)
-    return out
+    return to_host_into(t, torch.empty(t.shape, dtype=t.dtype, pin_memory=True))
 
 
 def copy_replicated_to_host(t: torch.Tensor, out: torch.Tensor) -> None:
@@ -316,19 +303,28 @@ def _is_shared_host(t: torch.Tensor) -> bool:
     return any(base <= p < base + size for base, size in ((seg.data_ptr(), seg.numel()) for seg in arena.segments.values()))
 
 
+copy_trace: list | None = None  # tools/copy_timeline.py: (bytes, ready, begin, done) timing events of every host copy
+
+
 def to_host_into(t: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
     """``to_host`` into an existing pinned host tensor (or a view of one)."""
     wait_for(t)
     if t.numel() == 0:
         return out
-    ready = torch.cuda.Event()
+    timing = copy_trace is not None
+    ready = torch.cuda.Event(enable_timing=timing)
     ready.record()
     side = _copy_stream(t.device)
     with torch.cuda.stream(side):
         side.wait_event(ready)
+        if timing:
+            begin = torch.cuda.Event(enable_timing=True)
+            begin.record(side)
         out.copy_(t, non_blocking=True)
-        done = torch.cuda.Event()
+        done = torch.cuda.Event(enable_timing=timing)
         done.record(side)
+    if timing:
+        copy_trace.append((t.numel() * t.element_size(), ready, begin, done))
     t.record_stream(side)
     _pending.append(done)
     return out
@@ -372,11 +368,52 @@ def node_state(nodes, provisional_ok: bool = False) -> NodeState:
         st.prov.resolve()
         st = nodes[STATE_ATTR]
     if isinstance(st, NodeState) and st.key == _key(x):
+        uploaded = st.extras.pop("uploaded", None)  # prefetch_coordinates: the copy runs on a side stream
+        if uploaded is not None:
+            torch.cuda.current_stream().wait_event(uploaded)
         return st
     wait_copies()  # x may be a pinned tensor one of our own copies is still filling
     st = NodeState(key=_key(x), x=upload_replicated(x))
     nodes[STATE_ATTR] = st
     return st
+
+
+_upload_streams: dict = {}
+PREFETCH_MIN_BYTES = 1 << 20
+
+
+def prefetch_coordinates(nodes) -> None:
+    """Start the upload of a host node set's coordinates NOW, on a side stream: ``GraphCreator.update_graph`` calls it for
+    the node sets a graph arrives with and the recipe's edges name.  The copy engine works while the first kernels of
+    the build run (node generation, the reference distance of the OTHER node set); the first ``node_state(nodes)`` orders
+    the calling stream behind it.  53 MB of O1280 coordinates: 1 ms that no longer precedes the first search.
+    Pinned float32 inputs only (a pageable source is staged synchronously by the driver: nothing to overlap); sharded
+    output mode has its own sliced upload."""
+    if not torch.cuda.is_available() or sharded_output():
+        return
+    x = nodes.get("x", None) if hasattr(nodes, "get") else None
+    if not isinstance(x, torch.Tensor) or x.is_cuda or x.dtype != torch.float32 or x.dim() != 2 or not x.is_pinned():
+        return
+    if x.numel() * x.element_size() < PREFETCH_MIN_BYTES or not x.is_contiguous():
+        return
+    st = nodes.get(STATE_ATTR, None)
+    if isinstance(st, NodeState) and (st.prov is not None or st.key == _key(x)):
+        return
+    dev = compute_device()
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    if key not in _upload_streams:
+        _upload_streams[key] = torch.cuda.Stream(device=dev)
+    side = _upload_streams[key]
+    x_dev = torch.empty(x.shape, dtype=torch.float32, device=dev)
+    side.wait_stream(torch.cuda.current_stream())  # the block may have been freed by work still queued on this stream
+    with torch.cuda.stream(side):
+        x_dev.copy_(x, non_blocking=True)
+        uploaded = torch.cuda.Event()
+        uploaded.record(side)
+    x_dev.record_stream(side)
+    st = NodeState(key=_key(x), x=x_dev)
+    st.extras["uploaded"] = uploaded
+    nodes[STATE_ATTR] = st
 
 
 # host node sets from this many bytes are uploaded once per NODE in a sharded multi-GPU build (each rank 1/W over its
