@@ -60,6 +60,7 @@ class GraphCreator:
     # limits of the CUDA path: found here, before any kernel runs, instead of mid-build
     MAX_KNN_K = 64
     MAX_X_HOPS = 8
+    EARLY_ROW_MIN_TARGETS = 1 << 18  # smaller target sets: the a-priori target row is not worth a separate copy
 
     def _validate(self) -> None:
         """Resolve every ``_target_`` of the recipe (an unknown or unbuilt class - the ICON builders,
@@ -101,6 +102,7 @@ class GraphCreator:
                 _device.flush_for(node_builder)  # a foreign (reference-style) plugin reads complete host tensors
                 graph = node_builder.update_graph(graph, attrs_config=nodes_cfg.get("attributes", {}))
 
+            self._emit_known_rows(graph)
             for edges_cfg in self.config.get("edges", {}):
                 for edge_builder_cfg in edges_cfg.edge_builders:
                     edge_builder = instantiate(
@@ -113,6 +115,35 @@ class GraphCreator:
                 graph = edge_builder.register_attributes(graph, edges_cfg.get("attributes", {}))
 
         return graph
+
+    def _emit_known_rows(self, graph) -> None:
+        """Host-resident graphs: the target row of an edge set built by ONE unmasked KNNEdges over a node set the graph
+        arrived with is known before any search (``device.emit_regular_target_row``) and starts its way to the host now,
+        behind the node builders' own copies."""
+        from .config import resolve_target
+        from .edges import KNNEdges
+
+        if not torch.cuda.is_available() or _device.is_resident() or _device.sharded_output():
+            return
+        for edges_cfg in self.config.get("edges", {}):
+            builders = edges_cfg.get("edge_builders", [])
+            if len(builders) != 1:
+                continue
+            b = builders[0]
+            src, dst, k = edges_cfg.get("source_name"), edges_cfg.get("target_name"), b.get("num_nearest_neighbours")
+            try:
+                ours = resolve_target(str(b.get("_target_", ""))) is KNNEdges
+            except Exception:
+                ours = False
+            if not ours or not isinstance(k, int) or k <= 0 or k > self.MAX_KNN_K:
+                continue
+            if b.get("source_mask_attr_name") is not None or b.get("target_mask_attr_name") is not None:
+                continue
+            if dst not in graph.node_types or dst in self.config.get("nodes", {}) or (src, "to", dst) in graph.edge_types:
+                continue
+            x = graph[dst].get("x", None)
+            if isinstance(x, torch.Tensor) and not x.is_cuda and x.dim() == 2 and int(x.shape[0]) >= self.EARLY_ROW_MIN_TARGETS:
+                _device.emit_regular_target_row(int(x.shape[0]), k)
 
     def clean(self, graph):
         """Remove private attributes used during creation from the graph (create.py:94-114)."""

@@ -307,6 +307,7 @@ class KNNEdges(BaseEdgeBuilder, NodeMaskingMixin):
             tie_list = ops.compact_flags(flags)  # ascending ids of the tied queries, count on the device: no read-back
             meta.fixup, meta.tie_flags, meta.tie_list, meta.regular_k, meta.shard = src_prov, flags, tie_list, k, shard
             meta.flag_base = lo  # ``flags`` is indexed by target id - lo
+            meta.regular_targets = not sharded_out and (lo, hi) == (0, nq)  # unmasked by construction (provisional source)
             # ``index`` stays alive in the closure: the re-decision searches it again, no second index
             src_prov.add_fixup(lambda prov, index=index, out=out, tl=tie_list, q=q, k=k: self._redecide_ties(prov, index, out, tl, q, k))  # fmt: skip
             return out
@@ -356,6 +357,7 @@ class KNNEdges(BaseEdgeBuilder, NodeMaskingMixin):
         out = _device.tag_rows(out, *self._row_provs)
         meta = _device.edge_meta(out, create=True)
         meta.regular_k, meta.local = k, local  # k edges per target, target after target: attributes walk it by target
+        meta.regular_targets = src_sel is None and dst_sel is None  # complete list, row 1 = column // k
         return out
 
 

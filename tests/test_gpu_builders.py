@@ -376,6 +376,52 @@ def test_remove_unconnected_nodes_random_graph_matches_reference_algorithm(resid
     assert graph["b"].num_nodes == n_b
 
 
+@pytest.mark.parametrize("hidden_first", [False, True])
+def test_early_target_row_is_adopted_and_equal(golden, monkeypatch, hidden_first):
+    """Host-resident graph, KNN decoder over a node set the graph arrives with: its target row is sent to the host at the
+    top of the build and adopted by the builder (provisional source: hidden_first False; final source: True)."""
+    from anemoi_graphs_b200 import device as agx_device
+    from anemoi_graphs_b200.create import GraphCreator
+    from anemoi_graphs_b200.graph import HeteroData
+
+    g = golden("toy")
+    monkeypatch.setattr(GraphCreator, "EARLY_ROW_MIN_TARGETS", 0)
+    recipe = {
+        "nodes": {"hidden": tri_nodes(2)},
+        "edges": [edges("hidden", "data", [{"_target_": T + "edges.KNNEdges", "num_nearest_neighbours": 3}], attr_cfg("l2"))],
+    }
+
+    def run(early):
+        monkeypatch.setattr(agx_device, "EARLY_TARGET_ROW", early)
+        monkeypatch.setattr(agx_device, "LAZY_NODE_ORDER", not hidden_first)
+        graph = HeteroData()
+        graph["data"].x = torch.from_numpy(g["data_x"]).pin_memory()
+        graph["data"].node_type = "LatLonNodes"
+        adopted = []
+        real = agx_device.edge_index_like_input
+
+        def spy(edge_dev, ref):
+            before = len(agx_device._early_rows)
+            out = real(edge_dev, ref)
+            adopted.append(before - len(agx_device._early_rows))
+            return out
+
+        monkeypatch.setattr(agx_device, "edge_index_like_input", spy)
+        graph = GraphCreator(recipe).update_graph(graph)
+        monkeypatch.setattr(agx_device, "edge_index_like_input", real)
+        assert not agx_device._early_rows
+        return graph, sum(adopted)
+
+    (a, n_a), (b, n_b) = run(True), run(False)
+    assert (n_a, n_b) == (1, 0)
+    key = ("hidden", "to", "data")
+    ea, eb = a[key].edge_index, b[key].edge_index
+    assert ea.dtype == torch.int32 and not ea.is_cuda and ea.is_pinned()
+    np.testing.assert_array_equal(ea.numpy(), eb.numpy())
+    np.testing.assert_array_equal(canon(ea), canon(g["knn3_edge_index"]))
+    np.testing.assert_array_equal(a[key].edge_length.numpy(), b[key].edge_length.numpy())
+
+
 def test_failed_node_order_sort_opens_the_gates_and_is_reported(monkeypatch):
     """Pre-launched tail: the device waits behind stream gates for index arrays the host is sorting.  A sort that fails
     must not leave it waiting: the gates open over valid (identity) arrays and the failure is raised by the build."""
