@@ -332,3 +332,47 @@ def test_prelaunch_mode_rule(monkeypatch):
             assert D._prelaunch_wanted() is want, (mode, resident)
     finally:
         D.set_resident(prev)
+
+
+def test_known_rows_are_emitted_only_for_single_unmasked_knn_builders(monkeypatch):
+    """GraphCreator._emit_known_rows (host-resident graphs): the a-priori target row is sent ahead only where a builder
+    will adopt it - ONE unmasked KNNEdges on a node pair without edges yet, over a host node set the graph arrived with."""
+    import torch
+
+    from anemoi_graphs_b200 import device as D
+    from anemoi_graphs_b200.create import GraphCreator
+    from anemoi_graphs_b200.graph import HeteroData
+
+    T = "anemoi.graphs."
+    knn = {"_target_": T + "edges.KNNEdges", "num_nearest_neighbours": 3}
+    masked = dict(knn, target_mask_attr_name="m")
+    cut = {"_target_": T + "edges.CutOffEdges", "cutoff_factor": 0.6}
+
+    def recipe(*edge_cfgs):
+        return {"nodes": {"hidden": {"node_builder": {"_target_": T + "nodes.TriNodes", "resolution": 1}}},
+                "edges": [{"source_name": s, "target_name": t, "edge_builders": list(b), "attributes": {}} for s, t, b in edge_cfgs]}  # fmt: skip
+
+    emitted = []
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    monkeypatch.setattr(D, "emit_regular_target_row", lambda n, k: emitted.append((n, k)))
+    monkeypatch.setattr(GraphCreator, "EARLY_ROW_MIN_TARGETS", 4)
+    graph = HeteroData()
+    graph["data"].x = torch.zeros((10, 2))
+    graph["tiny"].x = torch.zeros((2, 2))
+
+    def rows(*edge_cfgs):
+        emitted.clear()
+        GraphCreator(recipe(*edge_cfgs))._emit_known_rows(graph)
+        return list(emitted)
+
+    assert rows(("hidden", "data", [knn])) == [(10, 3)]
+    assert rows(("hidden", "data", [masked])) == []  # a mask changes which targets have edges
+    assert rows(("hidden", "data", [knn, cut])) == []  # merged builders: sorted unique columns
+    assert rows(("hidden", "data", [cut])) == []
+    assert rows(("data", "hidden", [knn])) == []  # the target set is generated by this recipe: unknown size, device side
+    assert rows(("hidden", "tiny", [knn])) == []  # not worth a separate copy
+    prev = D.set_resident(True)
+    try:
+        assert rows(("hidden", "data", [knn])) == []  # device-resident graphs copy nothing
+    finally:
+        D.set_resident(prev)
