@@ -101,6 +101,40 @@ def test_shared_memory_group_and_arena_world2():
     assert not left, f"shared-memory segments were not removed: {left}"
 
 
+def _worker_many(rank: int, world: int, port: int) -> None:
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), LOCAL_WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from anemoi_graphs_b200 import device as D
+    from anemoi_graphs_b200 import shm
+
+    try:
+        group, arena = shm.local_group(), shm.arena()
+        assert group is not None and group.world == world
+        counts = [3 + r for r in range(world)]
+        for build in range(3):  # three "builds": the segments of the first are reused by the third
+            shard = D.Shard(rank, world, counts)
+            full = arena.tensor((2, shard.total), torch.int32)
+            keep = arena.tensor((shard.total, 3), torch.float32)
+            full[:, shard.offset : shard.offset + counts[rank]] = 100 * build + rank
+            keep[shard.offset : shard.offset + counts[rank]] = float(build)
+            group.barrier()
+            want = np.concatenate([np.full(c, 100 * build + r, dtype=np.int32) for r, c in enumerate(counts)])
+            assert np.array_equal(full[0].numpy(), want) and np.array_equal(full[1].numpy(), want)
+            assert float(keep.sum()) == build * 3 * shard.total
+            group.barrier()
+            del full, keep
+        assert len(arena.segments) <= 4  # two size classes, at most two generations each
+        assert not [f for f in os.listdir("/dev/shm") if f.startswith(f"agx_{group.token}")]
+    finally:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def test_arena_rendezvous_world4():
+    """Four ranks: every new segment is a rendezvous (all ranks map it, then its name goes away), reuse across builds."""
+    mp.spawn(_worker_many, args=(4, _free_port()), nprocs=4, join=True)
+
+
 def _worker_small_shm(rank: int, world: int, port: int) -> None:
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), LOCAL_WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
