@@ -376,3 +376,35 @@ def test_known_rows_are_emitted_only_for_single_unmasked_knn_builders(monkeypatc
         assert rows(("hidden", "data", [knn])) == []  # device-resident graphs copy nothing
     finally:
         D.set_resident(prev)
+
+
+def test_committed_bench_lines_keep_the_contract():
+    """The bench lines kept under profiles/ carry every key the driver's contract names (bench.py prints them; a renamed
+    key would silently turn a measured number into an unmeasured one)."""
+    import json
+    import pathlib
+
+    import bench
+
+    root = pathlib.Path(__file__).resolve().parents[1] / "profiles"
+    base = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+            "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline"}  # fmt: skip
+    for name, with_cpu in (("r02_bench_n1_final.json", False), ("r02_bench_n1_slow_box.json", True)):
+        line = json.loads((root / name).read_text())
+        assert base <= set(line), base - set(line)
+        assert line["metric"] == bench.METRIC and line["unit"] == "edges/s" and line["higher_is_better"] is True
+        assert line["vs_baseline"] is None and line["data"] == "synthetic" and line["n_gpus"] == 1
+        assert {"bound", "achieved", "peak", "unit", "frac", "traffic", "fp32"} <= set(line["roofline"])
+        assert abs(line["roofline"]["frac"] - line["roofline"]["achieved"] / line["roofline"]["peak"]) < 1e-3
+        assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(line["e2e"])
+        assert line["e2e"]["h2d_bytes_per_step"] > 0 and line["e2e"]["d2h_bytes_per_step"] > 0
+        assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(line["clocks"]) and line["gpu_launches"] > 0
+        assert line["config"] == bench.workload_config(
+            "o1280_res7", 6599680, 163842,
+            {bench.EDGE_KEYS[0]: 10394844, bench.EDGE_KEYS[1]: 1310700, bench.EDGE_KEYS[2]: 19799040},
+        )
+        # value and ms_per_step describe the same time
+        edges = sum(line["config"]["edges"].values())
+        assert abs(line["value"] - edges / (line["ms_per_step"] * 1e-3)) / line["value"] < 1e-3
+        if with_cpu:
+            assert {"value", "unit", "cores", "kind", "sample"} <= set(line["cpu_baseline"])
